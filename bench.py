@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the IMGP hot path on B200 (BASELINE.json configs[2], "cfg-C"):
+
+    synthetic torus in R^3, N = 1M points, k = 32 (31 out-edges per node), symmetric Laplacian with self loops,
+    Matern precision (2nu/kappa^2 + L)^nu with nu = 2, one batched CG solve (16 right-hand sides) to 1e-6.
+
+One "step" = one full CG solve.  Metric = milliseconds per solve (lower is better).  The JSON line also carries
+the SpMM roofline (algorithmic bytes of SURVEY.md 8(d) / CUDA-event time of the SpMM launches), the kNN build time,
+the end-to-end number through the public API with host buffers, and a CPU baseline (oracle port, bounded sample).
+
+    python bench.py                       # N=1 GPU, defaults
+    python bench.py --impl reference      # the reference's CPU path (oracle port) on the host cores
+    torchrun ... bench.py --gpus 8        # row-partitioned strong scaling (see manifold_gp_b200/distributed.py)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ---- workload definition (every number below is reported in the JSON line) -----------------------
+CFG = dict(workload="torus_R3_N1M_k32_nu2_cg16rhs", n=1_000_000, k=32, nu=2, kappa=0.5, rhs=16, tol=1e-6,
+           max_iter=4000, normalization="symmetric", self_loops=True, seed=0, rhs_seed=1)
+# CG iterations the GPU solve of exactly this configuration needs (deterministic; measured on B200, see profiles/).
+# Used only by the CPU arms to scale their bounded sample (a few iterations) to a full solve.
+CG_ITERS_FULL_SOLVE = None
+
+
+def spmm_algorithmic_bytes(n, nnz, c, w=4):
+    """nnz*(4 + w) + N*(2*C*w + w)."""
+    return nnz * (4 + w) + n * (2 * c * w + w)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
+def build_problem(dev, n, k, seed):
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200.utils import synthetic
+    x = synthetic.torus(n, seed=seed, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    knn = mgp.NearestNeighbors(x)
+    dist, nbr = knn.search(x, k)
+    torch.cuda.synchronize()
+    t_search = time.perf_counter() - t0
+    idx, val = knn.graph(k)
+    torch.cuda.synchronize()
+    t_graph = time.perf_counter() - t0 - t_search     # search again + symmetrise (graph() searches itself)
+    eps = float(dist[:, k - 1].sqrt().median())       # graph bandwidth = median k-th-NN distance
+    return x, idx, val, eps, t_search, t_graph
+
+
+def run_ours(args):
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph, solvers, _lib
+    rank, world, local = dist_info()
+    if world > 1:
+        from manifold_gp_b200 import distributed
+        return distributed.bench_main(args, CFG)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    n, k, c = args.n, CFG["k"], CFG["rhs"]
+    x, idx, val, eps, t_search, t_graph = build_problem(dev, n, k, CFG["seed"])
+    m = idx.shape[1]
+    nnz = 2 * m
+    t0 = time.perf_counter()
+    lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[eps]], device=dev), CFG["normalization"], CFG["self_loops"])
+    prec = mgp.PrecisionMaternOperator(lap, CFG["nu"], torch.tensor([[CFG["kappa"]]], device=dev))
+    lap.structure
+    torch.cuda.synchronize()
+    t_struct = time.perf_counter() - t0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(); lap._values(); ev1.record(); torch.cuda.synchronize()
+    t_values_ms = ev0.elapsed_time(ev1)
+
+    g = torch.Generator(device=dev).manual_seed(CFG["rhs_seed"])
+    B = torch.randn(n, c, device=dev, generator=g)
+    Bh = B.cpu().pin_memory()
+    Xh = torch.empty_like(Bh).pin_memory()
+
+    def solve_dev():
+        return solvers.linear_cg(prec, B, tolerance=CFG["tol"], max_iter=CFG["max_iter"], return_info=True)
+
+    def solve_e2e():
+        b = Bh.to(dev, non_blocking=True)
+        xs, info = solvers.linear_cg(prec, b, tolerance=CFG["tol"], max_iter=CFG["max_iter"], return_info=True)
+        Xh.copy_(xs, non_blocking=True)
+        torch.cuda.synchronize()
+        return info
+
+    import warnings
+    warnings.simplefilter("ignore", RuntimeWarning)
+    for _ in range(args.warmup):
+        sol, info = solve_dev()
+    torch.cuda.synchronize()
+    _lib.reset_launch_count()
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            sol, info = solve_dev()
+        ev1.record()
+        torch.cuda.synchronize()
+    launches = _lib.launch_count()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    iters = info["iterations"]
+
+    # residual check of the timed result (true residual, fp64 accumulation of the norm)
+    res = (prec.matmul(sol) - B)
+    true_rel = float((res.double().norm(dim=0) / B.double().norm(dim=0)).mean())
+
+    # ---- end-to-end through the public API with host buffers ---------------------------------------------------------
+    solve_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        solve_e2e()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, min(args.steps, 3))
+
+    # ---- dominant kernel: the C=16 SpMM, timed with CUDA events over back-to-back launches (inputs >> L2) --------------
+    _, _, diag, a = lap._values()
+    shift = prec._shift()
+    P = torch.randn(n, c, device=dev)
+    V = torch.empty_like(P)
+    reps = 50
+    for _ in range(5):
+        graph.lap_spmm(lap.structure, a, diag, P, shift=shift, out=V)
+    ev0.record()
+    for _ in range(reps // 2):
+        graph.lap_spmm(lap.structure, a, diag, P, shift=shift, out=V)
+        graph.lap_spmm(lap.structure, a, diag, V, shift=shift, out=P)
+    ev1.record(); torch.cuda.synchronize()
+    spmm16_us = ev0.elapsed_time(ev1) * 1e3 / (2 * (reps // 2))
+    p1 = torch.randn(n, 1, device=dev); v1 = torch.empty_like(p1)
+    for _ in range(5):
+        graph.lap_spmm(lap.structure, a, diag, p1, out=v1)
+    ev0.record()
+    for _ in range(reps // 2):
+        graph.lap_spmm(lap.structure, a, diag, p1, out=v1)
+        graph.lap_spmm(lap.structure, a, diag, v1, out=p1)
+    ev1.record(); torch.cuda.synchronize()
+    spmv1_us = ev0.elapsed_time(ev1) * 1e3 / (2 * (reps // 2))
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    b16 = spmm_algorithmic_bytes(n, nnz, c)
+    b1 = spmm_algorithmic_bytes(n, nnz, 1)
+    ach16 = b16 / (spmm16_us * 1e-6) / 1e9
+    ach1 = b1 / (spmv1_us * 1e-6) / 1e9
+
+    out = {
+        "metric": "precision_cg_solve_time", "value": round(ms_step, 3), "unit": "ms", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": CFG["workload"], "n": n, "k": k, "edges_M": m, "nnz": nnz, "nu": CFG["nu"], "kappa": CFG["kappa"],
+                   "eps": round(eps, 6), "rhs": c, "tol": CFG["tol"], "normalization": CFG["normalization"],
+                   "self_loops": CFG["self_loops"], "l2": "inputs larger than L2 (matrix 8*nnz B + 4 vectors of N*16*4 B >> 126 MB)"},
+        "cg_iterations": iters, "cg_converged": bool(info["converged"]), "cg_recurrence_residual": info["mean_residual"],
+        "cg_true_relative_residual": true_rel,
+        "e2e": {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": Bh.numel() * 4, "d2h_bytes_per_step": Xh.numel() * 4},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "lap_spmm_csr_kernel (C=16 SpMM of the precision operator)",
+                     "achieved": round(ach16, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach16 / hbm_peak, 4),
+                     "frac_of_nominal_8000": round(ach16 / 8000.0, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": b16, "us_per_launch": round(spmm16_us, 2),
+                     "spmm_share_of_step": round(2 * iters * spmm16_us * 1e-3 / ms_step, 3)},
+        "spmv_c1": {"us_per_launch": round(spmv1_us, 2), "achieved_gbs": round(ach1, 1), "frac": round(ach1 / hbm_peak, 4),
+                    "algorithmic_bytes_per_launch": b1},
+        "knn_build_s": round(t_search, 4), "graph_symmetrize_s": round(max(t_graph - t_search, 0.0), 4),
+        "structure_build_s": round(t_struct, 4), "laplacian_values_ms": round(t_values_ms, 3),
+        "clocks": clk.summary(),
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(idx.cpu(), val.cpu(), n, eps, iters)
+    print(json.dumps(out))
+    return out
+
+
+# =====================================================================================================================
+# CPU arms: the reference's torch-sparse path restated (oracle), timed on the host cores
+# =====================================================================================================================
+def cpu_baseline(idx, val, n, eps, full_iters, sample_iters=1, threads=None):
+    """Time `sample_iters` CG iterations of the same solve with the oracle port (index_select -> mul -> scatter_add on the
+    int64 upper-triangular COO, exactly what torch_sparse.spmm lowers to) and scale to the full iteration count."""
+    import oracle
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    olap = oracle.LaplacianOracle(val, idx, n, eps, CFG["normalization"], CFG["self_loops"])
+    g = torch.Generator().manual_seed(CFG["rhs_seed"])
+    p = torch.randn(n, CFG["rhs"], generator=g)
+    olap.laplacian_triu  # value build (untimed here)
+    A = lambda v: oracle.precision_matmul(olap, CFG["nu"], CFG["kappa"], v)
+    r = p.clone(); x = torch.zeros_like(p)
+    A(p[:, :1])  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(sample_iters):
+        v = A(p)
+        alpha = (r * r).sum(0) / (p * v).sum(0)
+        x = x + alpha * p
+        rn = r - alpha * v
+        beta = (rn * rn).sum(0) / (r * r).sum(0)
+        p = rn + beta * p
+        r = rn
+    per_iter = (time.perf_counter() - t0) / sample_iters
+    full = full_iters or CG_ITERS_FULL_SOLVE or 1000
+    return {"value": round(per_iter * full * 1e3, 1), "unit": "ms", "cores": threads, "kind": "port",
+            "sample": f"{sample_iters} CG iteration(s) of the same N={n} solve ({CFG['nu']} Laplacian matvecs with C={CFG['rhs']} each) "
+                      f"timed at {per_iter:.3f} s/iteration, scaled to the {full} iterations of the full solve",
+            "cpu_model": _cpu_model()}
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    """The reference's own CPU path (oracle port; the reference itself cannot be imported: gpytorch / linear_operator /
+    torch_sparse / faiss are absent and there is no network).  Graph build (untimed setup) uses scipy's kd-tree."""
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return None
+    import numpy as np
+    import oracle
+    from scipy.spatial import cKDTree
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    n, k = args.n, CFG["k"]
+    x = oracle.datasets.torus(n, seed=CFG["seed"])
+    tree = cKDTree(x.numpy())
+    d, i = tree.query(x.numpy(), k=k, workers=-1)
+    d2 = torch.from_numpy((d.astype(np.float32)) ** 2)
+    eps = float(np.median(d[:, k - 1]))
+    idx, val = oracle.symmetrize_coalesce(d2, torch.from_numpy(i.astype(np.int64)), n)
+    times = []
+    base = None
+    for s in range(args.warmup + args.steps):
+        base = cpu_baseline(idx, val, n, eps, CG_ITERS_FULL_SOLVE, sample_iters=1, threads=threads)
+        if s >= args.warmup:
+            times.append(base["value"])
+    ms = sum(times) / len(times)
+    base["value"] = round(ms, 1)
+    out = {"impl": "reference", "metric": "precision_cg_solve_time", "value": round(ms, 1), "unit": "ms", "n_gpus": 0,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": False,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": CFG["workload"], "n": n, "k": k, "edges_M": int(idx.shape[1]), "nu": CFG["nu"],
+                      "kappa": CFG["kappa"], "eps": round(eps, 6), "rhs": CFG["rhs"], "tol": CFG["tol"]},
+           "cpu_baseline": base,
+           "e2e": {"value": round(ms, 1), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=CFG["n"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,234 @@
+/*
+ * mgp_b200.h -- C ABI of the B200-native IMGP hot path (libmgp_b200.so).
+ *
+ * One entry point per operation the reference reaches through faiss / torch_sparse / torch_scatter /
+ * linear_operator on this path.  Reference citations are file:line under the
+ * reference repository (nash169/manifold-gp).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer on the current CUDA device unless its name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is enqueued on it;
+ *     no call synchronises unless its documentation says so.
+ *   - No entry point allocates device memory.  Calls that need scratch take `ws` / `ws_bytes`; the matching
+ *     `*_ws_bytes` query returns the size to allocate (the Python host allocates it with torch).
+ *   - Dense operands are row-major with an explicit leading dimension (`ld*`, in elements).
+ *   - Hyper-parameters that live in torch Parameters (graph bandwidth eps, Matern shift 2nu/kappa^2, CG scalars)
+ *     are passed as device scalars so that no call forces a device->host read.
+ *   - Return value: 0 on success, a negative MGP_E* code otherwise; mgp_last_error() describes the last failure
+ *     of the calling thread.  There is NO CPU fallback anywhere behind this ABI.
+ *   - `_f32` / `_f64` suffix = arithmetic type of values and vectors.  Indices are int32 on the device
+ *     (the reference's int64 COO is accepted / produced at the boundary calls only).
+ */
+#ifndef MGP_B200_H_
+#define MGP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGP_OK 0
+#define MGP_EINVAL (-1)    /* bad argument (shape, alignment, null pointer) */
+#define MGP_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed  */
+#define MGP_EWORKSPACE (-3) /* workspace too small                          */
+#define MGP_EUNSUPPORTED (-4)
+
+const char* mgp_last_error(void);
+/* Library / build identification: "mgp_b200 <version> sm_100a". */
+const char* mgp_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches claim). */
+int64_t mgp_launch_count(void);
+void mgp_reset_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * (a2) Exact brute-force kNN, squared L2, ascending.  Replaces faiss Index{Flat,IVFFlat(nlist=1)}.search
+ *      as called by NearestNeighbors.search -- manifold_gp/utils/nearest_neighbors.py:35-37 (index built at :17-33).
+ *      db[n,d], q[nq,d] row-major fp32; dist2[nq,k] fp32 ascending; idx[nq,k] int64 (faiss' index type).
+ *      Distances are sum_d (q_d - x_d)^2 evaluated in fp32 in ascending d (ties broken by ascending index);
+ *      entries beyond n are (+inf, -1).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t mgp_knn_search_ws_bytes(int64_t n, int64_t nq, int32_t d, int32_t k);
+int mgp_knn_search_f32(const float* db, int64_t n, const float* q, int64_t nq, int32_t d, int32_t k,
+                       float* dist2, int64_t* idx, void* ws, size_t ws_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * (a3) Directed kNN lists -> upper-triangular, lexicographically sorted, mean-coalesced COO.
+ *      Replaces NearestNeighbors.graph -- nearest_neighbors.py:39-55 (torch_sparse.coalesce(op='mean') at :51).
+ *      dist2/idx are [n,k] as returned by mgp_knn_search_f32; drop_first != 0 drops column 0 (:42-43).
+ *      eidx is [2, cap] int64 with cap = n*(k - drop_first) (row 0 = eidx, row 1 = eidx + cap), eval[cap] fp32.
+ *      The number of undirected edges M is written to *m_out (device int64); the first M columns are valid.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t mgp_graph_symmetrize_ws_bytes(int64_t n, int32_t k);
+int mgp_graph_symmetrize_f32(const float* dist2, const int64_t* idx, int64_t n, int32_t k, int32_t drop_first,
+                             int64_t* eidx, float* eval, int64_t cap, int64_t* m_out,
+                             void* ws, size_t ws_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Row-major directed structure of the symmetric graph, built once per graph (hyper-parameter independent).
+ *      From the reference's COO (`idx[2,M]`, row<col as produced at nearest_neighbors.py:48-51; ld = distance in
+ *      elements between the two rows of idx) build CSR over BOTH directions of every edge:
+ *      rowptr[n+1], col[2M], eid[2M] (undirected edge id of each directed entry).  A diagonal COO entry (i,i)
+ *      (nearest_neighbors.py duplicates quirk) contributes two entries to row i, as the two scatter/spmm passes
+ *      of graph_laplacian_operator.py:63-69,118-119 do.  Column indices inside a row are ascending.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t mgp_csr_build_ws_bytes(int64_t n, int64_t m);
+int mgp_csr_build(const int64_t* eidx, int64_t ld, int64_t m, int64_t n,
+                  int32_t* rowptr, int32_t* col, int32_t* eid, void* ws, size_t ws_bytes, void* stream);
+/* out[p] = val[eid[p]] : per-directed-entry copy of a per-edge array (squared distances). */
+int mgp_gather_edge_f32(const float* val, const int32_t* eid, int64_t nnz, float* out, void* stream);
+int mgp_gather_edge_f64(const double* val, const int32_t* eid, int64_t nnz, double* out, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * (a4) Laplacian values for one graph bandwidth eps.  Replaces the cached properties of GraphLaplacianOperator
+ *      -- manifold_gp/operators/graph_laplacian_operator.py:52-106:
+ *        W = exp(-d2/(4 eps^2)) (:56);  Dt_i = [1] + sum_j W_ij (:60-69);  At = W/(Dt_i Dt_j) (:75);
+ *        D_i = [Dt_i^-2] + sum_j At_ij (:79-88);  diag_i = (1 - [Dt_i^-2]/D_i)/eps^2 | 1/eps^2 (:92-97);
+ *        a_ij = At_ij/(sqrt(D_i) sqrt(D_j))/eps^2 (:106)            ([.] only with self_loops)
+ *      Deterministic row sums over the CSR (no atomics, unlike scatter_add_).  d2csr is the per-directed-entry
+ *      squared distance (mgp_gather_edge).  Outputs: deg_unnorm[n], deg[n], diag[n], a[nnz].
+ *      `eps` is a device scalar.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mgp_lap_values_f32(const int32_t* rowptr, const int32_t* col, const float* d2csr, int64_t n,
+                       const float* eps, int32_t self_loops,
+                       float* deg_unnorm, float* deg, float* diag, float* a, void* stream);
+int mgp_lap_values_f64(const int32_t* rowptr, const int32_t* col, const double* d2csr, int64_t n,
+                       const double* eps, int32_t self_loops,
+                       double* deg_unnorm, double* deg, double* diag, double* a, void* stream);
+
+/* Backward of mgp_lap_values w.r.t. eps (what autograd through graph_laplacian_operator.py:52-106 yields for
+ * raw_graphbandwidth; exercised by the reference's test_grad / test_ml, test/_test_functions.py:59-104):
+ *   *g_eps = sum_p g_a[p] da_p/deps + sum_i ( g_diag_i ddiag_i/deps + g_deg_unnorm_i dDt_i/deps + g_deg_i dD_i/deps )
+ * computed with forward-mode tangents (three streaming passes, deterministic reduction).  g_deg_unnorm / g_deg may be
+ * NULL.  ws: mgp_lap_values_grad_ws_bytes(n) bytes, first 256 bytes zero on first use. */
+size_t mgp_lap_values_grad_ws_bytes(int64_t n);
+int mgp_lap_values_grad_f32(const int32_t* rowptr, const int32_t* col, const float* d2csr, int64_t n, const float* eps,
+                            int32_t self_loops, const float* deg_unnorm, const float* deg, const float* diag,
+                            const float* a, const float* g_deg_unnorm, const float* g_deg, const float* g_diag,
+                            const float* g_a, float* g_eps, void* ws, void* stream);
+int mgp_lap_values_grad_f64(const int32_t* rowptr, const int32_t* col, const double* d2csr, int64_t n, const double* eps,
+                            int32_t self_loops, const double* deg_unnorm, const double* deg, const double* diag,
+                            const double* a, const double* g_deg_unnorm, const double* g_deg, const double* g_diag,
+                            const double* g_a, double* g_eps, void* ws, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * (a5,a8) Fused Laplacian / Matern-step SpMM:   Y = post .* ( (diag + shift) .* (pre .* X)  -  A (pre .* X) )
+ *      Replaces GraphLaplacianOperator._matmul -- graph_laplacian_operator.py:108-124 (two torch_sparse.spmm + diagonal
+ *      + D^{+-1/2} scalings) and one step of PrecisionMaternOperator._matmul -- precision_matern_operator.py:26-37
+ *      (out <- (out + c L out)/c  ==  (1/c + L) out, i.e. shift = 2 nu / kappa^2).
+ *      A = (rowptr, col, a) from mgp_lap_values; `shift` device scalar or NULL (0); `pre`, `post` [n] or NULL (1).
+ *      X [n, ncols] ld ldx; Y [n, ncols] ld ldy; X and Y must not alias.
+ *      Optional fused reduction (CG's p^T A p, Lanczos' alpha): if dot_out != NULL, dot_out[c] = sum_i dot_with[i,c]*Y[i,c]
+ *      (dot_with ld = ldx), accumulated deterministically; needs `dot_ws` of mgp_lap_spmm_dot_ws_bytes(n,ncols).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t mgp_lap_spmm_dot_ws_bytes(int64_t n, int32_t ncols);
+int mgp_lap_spmm_f32(const int32_t* rowptr, const int32_t* col, const float* a, const float* diag,
+                     const float* shift, const float* pre, const float* post,
+                     const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n, int32_t ncols,
+                     const float* dot_with, float* dot_out, void* dot_ws, void* stream);
+int mgp_lap_spmm_f64(const int32_t* rowptr, const int32_t* col, const double* a, const double* diag,
+                     const double* shift, const double* pre, const double* post,
+                     const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols,
+                     const double* dot_with, double* dot_out, void* dot_ws, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Backward of the SpMM w.r.t. the matrix entries (what autograd through torch_sparse.spmm computes for `value`,
+ * graph_laplacian_operator.py:117-119, reached via linear_operator's _bilinear_derivative):
+ *      g_a[p]   = - sum_c L[i,c] * R[col_p,c]      (i = row of entry p)
+ *      g_diag[i] =   sum_c L[i,c] * R[i,c]
+ * with L = post .* grad_Y and R = pre .* X.   g_a [nnz], g_diag [n].
+ * ---------------------------------------------------------------------------------------------------------- */
+int mgp_lap_sddmm_f32(const int32_t* rowptr, const int32_t* col, const float* pre, const float* post,
+                      const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t n, int32_t ncols,
+                      float* g_a, float* g_diag, void* stream);
+int mgp_lap_sddmm_f64(const int32_t* rowptr, const int32_t* col, const double* pre, const double* post,
+                      const double* gy, int64_t ldgy, const double* x, int64_t ldx, int64_t n, int32_t ncols,
+                      double* g_a, double* g_diag, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * (a17) Batched CG vector kernels (mBCG of linear_operator.utils.linear_cg, third party; call sites
+ *      utils/train_model.py:55,67-68, precision_matern_operator.py:53, schur_complement_operator.py:28).
+ *      The host loop calls the operator's matvec (mgp_lap_spmm chain) and these fused updates; all scalars stay on
+ *      the device in `state` (layout below, in elements of the value type, C = ncols):
+ *        [0,C) rhs_norm  [C,2C) rz (=r^T r)  [2C,3C) pAp  [3C,4C) alpha  [4C,5C) beta  [5C,6C) resid_norm
+ *        [6C,7C) flags (bit0 rhs_is_zero, bit1 has_converged)   [7C] mean residual norm  [7C+1] done flag
+ *        [7C+2] iteration counter   [7C+3] tolerance  [7C+4] eps  [7C+5] stop_updating_after
+ *        [7C+6] min_iter (= min(10, max_iter-1))  [7C+7] n_tridiag_min (iterations the tridiagonal still needs)
+ *      hist [max_hist, 2, C]: alpha_k, beta_k per iteration (the Lanczos tridiagonals are assembled from these).
+ *      Every kernel returns immediately when the done flag is set, so the host may enqueue iterations in chunks
+ *      and poll the flag; reductions are deterministic (per-block partials reduced in fixed order by the last block).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t mgp_cg_state_elems(int32_t ncols);
+size_t mgp_cg_ws_bytes(int64_t n, int32_t ncols);
+/* r = b / |b|, p = r, x = 0, rz = |r|^2; fills state.  b [n,ncols] ld ldb; x,r,p [n,ncols] ld ld. */
+int mgp_cg_init_f32(const float* b, int64_t ldb, float* x, float* r, float* p, int64_t ld, int64_t n, int32_t ncols,
+                    float tolerance, float eps, float stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter,
+                    float* state, void* ws, void* stream);
+int mgp_cg_init_f64(const double* b, int64_t ldb, double* x, double* r, double* p, int64_t ld, int64_t n, int32_t ncols,
+                    double tolerance, double eps, double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter,
+                    double* state, void* ws, void* stream);
+/* pAp[c] = sum_i p*v (skipped when the SpMM epilogue already produced state.pAp: have_pap != 0), then
+ * alpha = rz/pAp with the safe-division / convergence masks. */
+int mgp_cg_alpha_f32(const float* p, const float* v, int64_t ld, int64_t n, int32_t ncols, int32_t have_pap,
+                     float* state, void* ws, void* stream);
+int mgp_cg_alpha_f64(const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols, int32_t have_pap,
+                     double* state, void* ws, void* stream);
+/* x += alpha p; r -= alpha v; rz' = |r|^2; beta = rz'/rz; residual norms, convergence flags, done flag,
+ * iteration counter, hist[k] = (alpha, beta). */
+int mgp_cg_update_f32(float* x, float* r, const float* p, const float* v, int64_t ld, int64_t n, int32_t ncols,
+                      float* state, float* hist, int32_t max_hist, void* ws, void* stream);
+int mgp_cg_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
+                      double* state, double* hist, int32_t max_hist, void* ws, void* stream);
+/* p = r + beta p */
+int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream);
+int mgp_cg_pupdate_f64(double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream);
+/* out[i,c] = x[i,c] * rhs_norm[c]  (un-normalise; out ld ldo) */
+int mgp_cg_finalize_f32(const float* x, int64_t ld, float* out, int64_t ldo, int64_t n, int32_t ncols,
+                        const float* state, void* stream);
+int mgp_cg_finalize_f64(const double* x, int64_t ld, double* out, int64_t ldo, int64_t n, int32_t ncols,
+                        const double* state, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * (a7,a17) Lanczos kernels (linear_operator.utils.lanczos.lanczos_tridiag, third party; call site
+ *      graph_laplacian_operator.py:132-135).  Q is stored vector-major: Q[j] is a contiguous length-n vector (ldq >= n).
+ *      mgp_lanczos_reorth:  c = Q[0:j]^T r ;  r -= Q[0:j] c   (one full re-orthogonalisation pass; c [j] is also
+ *                           returned so the host can test max|c| against tol), then nrm2[0] = |r|^2.
+ *      mgp_lanczos_dots:    c = Q[0:j]^T r only.
+ *                           j = 0 is allowed (norm only).  Running one pass against ALL previous vectors also removes the
+ *                           alpha_k q_k and beta_{k-1} q_{k-1} terms of the three-term recurrence: alpha_k = c[k].
+ *      mgp_lanczos_normalize: q_out = r / sqrt(*nrm2); *beta_out = sqrt(*nrm2)   (beta_out may be NULL).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t mgp_lanczos_ws_bytes(int64_t n, int32_t j);
+int mgp_lanczos_reorth_f32(const float* q, int64_t ldq, int32_t j, float* r, int64_t n, float* c, float* nrm2,
+                           void* ws, void* stream);
+int mgp_lanczos_reorth_f64(const double* q, int64_t ldq, int32_t j, double* r, int64_t n, double* c, double* nrm2,
+                           void* ws, void* stream);
+/* r -= Q[0:j] c (c given), nrm2[0] = |r|^2 -- the second half of mgp_lanczos_reorth. */
+int mgp_lanczos_axpy_f32(const float* q, int64_t ldq, int32_t j, float* r, int64_t n, const float* c, float* nrm2,
+                         void* ws, void* stream);
+int mgp_lanczos_axpy_f64(const double* q, int64_t ldq, int32_t j, double* r, int64_t n, const double* c, double* nrm2,
+                         void* ws, void* stream);
+int mgp_lanczos_normalize_f32(const float* r, int64_t n, const float* nrm2, float* q_out, float* beta_out, void* stream);
+int mgp_lanczos_normalize_f64(const double* r, int64_t n, const double* nrm2, double* q_out, double* beta_out, void* stream);
+int mgp_lanczos_dots_f32(const float* q, int64_t ldq, int32_t j, const float* r, int64_t n, float* c, void* ws, void* stream);
+int mgp_lanczos_dots_f64(const double* q, int64_t ldq, int32_t j, const double* r, int64_t n, double* c, void* ws, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * (a15) Out-of-sample (Nystrom) extension: an ELL SpMM with fixed row length k.
+ *      Replaces GraphLaplacianOperator.out_of_sample -- graph_laplacian_operator.py:146-157:
+ *        w = exp(-d2/(4 eps^2)); w /= Dt[idx] * rowsum(w); symmetric: w /= sqrt(D[idx]) * sqrt(rowsum(w));
+ *        randomwalk: w /= rowsum(w);  out[q,:] = sum_k w[q,k] phi[idx[q,k],:]
+ *      d2 [nq,k], idx [nq,k] int64, phi [n,m] ld ldphi, out [nq,m] ld ldo.  normalization: 0 symmetric, 1 randomwalk.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mgp_out_of_sample_f32(const float* d2, const int64_t* idx, int64_t nq, int32_t k, const float* eps,
+                          const float* deg_unnorm, const float* deg, int32_t normalization,
+                          const float* phi, int64_t ldphi, int32_t m, float* out, int64_t ldo, void* stream);
+int mgp_out_of_sample_f64(const double* d2, const int64_t* idx, int64_t nq, int32_t k, const double* eps,
+                          const double* deg_unnorm, const double* deg, int32_t normalization,
+                          const double* phi, int64_t ldphi, int32_t m, double* out, int64_t ldo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGP_B200_H_ */

@@ -1,0 +1,462 @@
+// Batched conjugate gradients: the fused vector kernels of mBCG.
+//
+// Algorithm: linear_operator.utils.linear_cg (third party; restated in oracle/solvers.py; reference call sites
+// utils/train_model.py:55,67-68, operators/precision_matern_operator.py:53, operators/schur_complement_operator.py:28).
+// linear_operator runs ~10 un-fused elementwise / reduction launches per iteration and reads the residual norm
+// back to the host every iteration.  Here an iteration is
+//     [operator matvec, optionally with the p^T A p epilogue]  ->  cg_update  ->  cg_pupdate
+// all scalars (alpha, beta, norms, masks, iteration counter, convergence flag) live in a device `state` block,
+// reductions are deterministic (per-block partials + last-block fixed-order reduce), and every kernel is a no-op
+// once the done flag is set, so the host enqueues iterations in chunks and polls one flag.
+//
+// State layout (elements of T, C = ncols):  8 arrays of C then 16 scalars -- see CgState below / mgp_b200.h.
+#include "common.cuh"
+
+namespace mgp {
+
+enum : int { S_RHSNORM = 0, S_RZ, S_PAP, S_ALPHA, S_BETA, S_RESID, S_RHSZERO, S_CONV, S_NARR };
+enum : int { K_MEAN = 0, K_DONE, K_ITER, K_TOL, K_EPS, K_STOP, K_MINITER, K_NTRIMIN, K_MAXITER, K_NSCAL = 16 };
+
+constexpr int kCgBlock = 256;
+constexpr int kCgMaxCols = 128;
+constexpr int kCgMaxCB = kCgMaxCols / 32;
+
+static inline int cg_grid(int64_t n, int rows_per_block) {
+  int64_t b = ceil_div(n, rows_per_block);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+static inline int col_lanes(int ncols) {
+  int cp = 1;
+  while (cp < ncols && cp < 32) cp <<= 1;
+  return cp;
+}
+
+// Block-level per-column reduction of `acc[cb]` (column = cb*CP + tid%CP) into partials[blockIdx.x*ncols + c].
+template <typename T>
+__device__ __forceinline__ void block_col_reduce(const T* acc, int ncb, int CP, int ncols, T* partials) {
+  __shared__ T sm[kCgBlock / 32][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cl = tid % CP;  // CP divides 32, so cl == lane % CP
+  for (int cb = 0; cb < ncb; ++cb) {
+    T v = acc[cb];
+    v = subwarp_sum(v, CP, 32);
+    __syncthreads();
+    if (lane < CP) sm[warp][lane] = v;
+    __syncthreads();
+    if (tid < CP) {
+      T s = T(0);
+#pragma unroll
+      for (int w = 0; w < kCgBlock / 32; ++w) s += sm[w][tid];
+      const int c = cb * CP + cl;
+      if (c < ncols) partials[(int64_t)blockIdx.x * ncols + c] = s;
+    }
+  }
+}
+
+// Fixed-order reduction of partials over blocks by the calling (last) block; result for column c in smem out[c].
+template <typename T>
+__device__ __forceinline__ void last_block_reduce(const T* partials, int ncols, T* out /* smem [kCgMaxCols] */) {
+  __shared__ T red[kCgBlock];
+  const int tid = threadIdx.x;
+  for (int cbase = 0; cbase < ncols; cbase += 32) {
+    const int cw = min(32, ncols - cbase);
+    const int per = kCgBlock / cw;
+    const int c = tid % cw, r = tid / cw;
+    T s = T(0);
+    if (r < per)
+      for (int b = r; b < (int)gridDim.x; b += per) s += __ldcg(partials + (int64_t)b * ncols + cbase + c);
+    __syncthreads();
+    red[tid] = (r < per) ? s : T(0);
+    __syncthreads();
+    if (tid < cw) {
+      T t = T(0);
+      for (int rr = 0; rr < per; ++rr) t += red[rr * cw + tid];
+      out[cbase + tid] = t;
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+struct CgWs {
+  unsigned int* counter;
+  T* partials;
+};
+template <typename T>
+__host__ __device__ inline CgWs<T> cg_ws(void* ws) {
+  CgWs<T> w;
+  w.counter = reinterpret_cast<unsigned int*>(ws);
+  w.partials = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + 256);
+  return w;
+}
+
+// ---- init pass 1: column norms of b ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_norm_kernel(const T* __restrict__ b, int64_t ldb, int64_t n, int ncols, int CP, T eps, T* __restrict__ state,
+               void* ws) {
+  CgWs<T> w = cg_ws<T>(ws);
+  const int tid = threadIdx.x;
+  const int cl = tid % CP, rl = tid / CP, rpb = kCgBlock / CP;
+  const int ncb = (ncols + CP - 1) / CP;
+  T acc[kCgMaxCB];
+#pragma unroll
+  for (int i = 0; i < kCgMaxCB; ++i) acc[i] = T(0);
+  for (int64_t row = (int64_t)blockIdx.x * rpb + rl; row < n; row += (int64_t)gridDim.x * rpb) {
+#pragma unroll
+    for (int cb = 0; cb < kCgMaxCB; ++cb) {
+      const int c = cb * CP + cl;
+      if (cb < ncb && c < ncols) {
+        const T v = b[row * ldb + c];
+        acc[cb] = fma(v, v, acc[cb]);
+      }
+    }
+  }
+  block_col_reduce<T>(acc, ncb, CP, ncols, w.partials);
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    for (int c = tid; c < ncols; c += kCgBlock) {
+      T nrm = dev_sqrt<T>(tot[c]);
+      const bool zero = nrm < eps;
+      state[S_RHSZERO * ncols + c] = zero ? T(1) : T(0);
+      state[S_RHSNORM * ncols + c] = zero ? T(1) : nrm;
+    }
+  }
+}
+
+// ---- init pass 2: r = b/|b|, p = r, x = 0, rz = |r|^2 ----------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_init_kernel(const T* __restrict__ b, int64_t ldb, T* __restrict__ x, T* __restrict__ r, T* __restrict__ p,
+               int64_t ld, int64_t n, int ncols, int CP, T tol, T eps, T stop, int max_iter, int n_tridiag_iter,
+               T* __restrict__ state, void* ws) {
+  CgWs<T> w = cg_ws<T>(ws);
+  const int tid = threadIdx.x;
+  const int cl = tid % CP, rl = tid / CP, rpb = kCgBlock / CP;
+  const int ncb = (ncols + CP - 1) / CP;
+  T acc[kCgMaxCB], inv[kCgMaxCB];
+#pragma unroll
+  for (int cb = 0; cb < kCgMaxCB; ++cb) {
+    acc[cb] = T(0);
+    const int c = cb * CP + cl;
+    inv[cb] = (cb < ncb && c < ncols) ? state[S_RHSNORM * ncols + c] : T(1);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * rpb + rl; row < n; row += (int64_t)gridDim.x * rpb) {
+#pragma unroll
+    for (int cb = 0; cb < kCgMaxCB; ++cb) {
+      const int c = cb * CP + cl;
+      if (cb < ncb && c < ncols) {
+        const T v = b[row * ldb + c] / inv[cb];
+        r[row * ld + c] = v;
+        p[row * ld + c] = v;
+        x[row * ld + c] = T(0);
+        acc[cb] = fma(v, v, acc[cb]);
+      }
+    }
+    // zero the padding columns so vectorised consumers never see garbage
+    for (int c = ncols + tid % CP; c < ld; c += CP) {
+      r[row * ld + c] = T(0); p[row * ld + c] = T(0); x[row * ld + c] = T(0);
+    }
+  }
+  block_col_reduce<T>(acc, ncb, CP, ncols, w.partials);
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    __shared__ T msum[kCgBlock];
+    T local = T(0);
+    int all_conv = 1;
+    for (int c = tid; c < ncols; c += kCgBlock) {
+      const T rn = dev_sqrt<T>(tot[c]);
+      state[S_RZ * ncols + c] = tot[c];
+      state[S_RESID * ncols + c] = rn;
+      state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
+      state[S_PAP * ncols + c] = T(0);
+      state[S_ALPHA * ncols + c] = T(0);
+      state[S_BETA * ncols + c] = T(0);
+      local += rn;
+      if (!(rn < stop)) all_conv = 0;
+    }
+    msum[tid] = local;
+    const int any_unconv = __syncthreads_or(!all_conv);
+    if (tid == 0) {
+      T s = T(0);
+      for (int i = 0; i < kCgBlock; ++i) s += msum[i];
+      T* k = state + S_NARR * ncols;
+      k[K_MEAN] = s / T(ncols);
+      // published: "if has_converged.all() and not n_tridiag: n_iter = 0"
+      k[K_DONE] = (!any_unconv && n_tridiag_iter == 0) ? T(1) : T(0);
+      k[K_ITER] = T(0);
+      k[K_TOL] = tol;
+      k[K_EPS] = eps;
+      k[K_STOP] = stop;
+      k[K_MINITER] = T(min(10, max_iter - 1));
+      k[K_NTRIMIN] = T(n_tridiag_iter > 0 ? min(n_tridiag_iter, max_iter - 1) : 0);
+      k[K_MAXITER] = T(max_iter);
+      if (max_iter <= 0) k[K_DONE] = T(2);
+    }
+  }
+}
+
+// ---- pAp reduction (only when the matvec did not fuse it) ------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_pap_kernel(const T* __restrict__ p, const T* __restrict__ v, int64_t ld, int64_t n, int ncols, int CP,
+              T* __restrict__ state, void* ws) {
+  if (state[S_NARR * ncols + K_DONE] != T(0)) return;
+  CgWs<T> w = cg_ws<T>(ws);
+  const int tid = threadIdx.x;
+  const int cl = tid % CP, rl = tid / CP, rpb = kCgBlock / CP;
+  const int ncb = (ncols + CP - 1) / CP;
+  T acc[kCgMaxCB];
+#pragma unroll
+  for (int i = 0; i < kCgMaxCB; ++i) acc[i] = T(0);
+  for (int64_t row = (int64_t)blockIdx.x * rpb + rl; row < n; row += (int64_t)gridDim.x * rpb) {
+#pragma unroll
+    for (int cb = 0; cb < kCgMaxCB; ++cb) {
+      const int c = cb * CP + cl;
+      if (cb < ncb && c < ncols) acc[cb] = fma(p[row * ld + c], v[row * ld + c], acc[cb]);
+    }
+  }
+  block_col_reduce<T>(acc, ncb, CP, ncols, w.partials);
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    for (int c = tid; c < ncols; c += kCgBlock) state[S_PAP * ncols + c] = tot[c];
+  }
+}
+
+// alpha_k from (rz, pAp, masks): the published "safe division"
+template <typename T>
+__device__ __forceinline__ T cg_alpha_of(const T* state, int ncols, int c, T eps) {
+  const T pap = state[S_PAP * ncols + c];
+  const T rz = state[S_RZ * ncols + c];
+  const bool is_zero = pap < eps;
+  T alpha = is_zero ? T(0) : rz / pap;
+  if (state[S_CONV * ncols + c] != T(0)) alpha = T(0);
+  return alpha;
+}
+
+// ---- x += alpha p ; r -= alpha v ; rz' = |r|^2 ; beta, norms, flags, history ------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_update_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ v, int64_t ld,
+                 int64_t n, int ncols, int CP, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws) {
+  T* k = state + S_NARR * ncols;
+  if (k[K_DONE] != T(0)) return;
+  CgWs<T> w = cg_ws<T>(ws);
+  const int tid = threadIdx.x;
+  const int cl = tid % CP, rl = tid / CP, rpb = kCgBlock / CP;
+  const int ncb = (ncols + CP - 1) / CP;
+  const T eps = k[K_EPS];
+  T acc[kCgMaxCB], alpha[kCgMaxCB];
+#pragma unroll
+  for (int cb = 0; cb < kCgMaxCB; ++cb) {
+    acc[cb] = T(0);
+    const int c = cb * CP + cl;
+    alpha[cb] = (cb < ncb && c < ncols) ? cg_alpha_of<T>(state, ncols, c, eps) : T(0);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * rpb + rl; row < n; row += (int64_t)gridDim.x * rpb) {
+#pragma unroll
+    for (int cb = 0; cb < kCgMaxCB; ++cb) {
+      const int c = cb * CP + cl;
+      if (cb < ncb && c < ncols) {
+        const int64_t o = row * ld + c;
+        const T a = alpha[cb];
+        const T rn = fma(-a, v[o], r[o]);
+        r[o] = rn;
+        x[o] = fma(a, p[o], x[o]);
+        acc[cb] = fma(rn, rn, acc[cb]);
+      }
+    }
+  }
+  block_col_reduce<T>(acc, ncb, CP, ncols, w.partials);
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    __shared__ T msum[kCgBlock];
+    const int it = (int)k[K_ITER];
+    const T stop = k[K_STOP];
+    T local = T(0);
+    for (int c = tid; c < ncols; c += kCgBlock) {
+      const T a = cg_alpha_of<T>(state, ncols, c, eps);
+      const T rz_old = state[S_RZ * ncols + c];
+      const T rz_new = tot[c];
+      const bool bz = rz_old < eps;
+      const T beta = bz ? T(0) : rz_new / rz_old;
+      T rn = dev_sqrt<T>(rz_new);
+      if (state[S_RHSZERO * ncols + c] != T(0)) rn = T(0);
+      state[S_ALPHA * ncols + c] = a;
+      state[S_BETA * ncols + c] = beta;
+      state[S_RZ * ncols + c] = rz_new;
+      state[S_RESID * ncols + c] = rn;
+      state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
+      if (hist && it < max_hist) {
+        hist[((int64_t)it * 2 + 0) * ncols + c] = a;
+        hist[((int64_t)it * 2 + 1) * ncols + c] = beta;
+      }
+      local += rn;
+    }
+    msum[tid] = local;
+    __syncthreads();
+    if (tid == 0) {
+      T s = T(0);
+      for (int i = 0; i < kCgBlock; ++i) s += msum[i];
+      const T mean = s / T(ncols);
+      k[K_MEAN] = mean;
+      k[K_ITER] = T(it + 1);
+      // published stopping rule: k >= min(10, max_iter-1) and mean residual < tol and the tridiagonal has enough rows
+      const bool tri_pending = (k[K_NTRIMIN] > T(0)) && (T(it) < k[K_NTRIMIN]);
+      if (T(it) >= k[K_MINITER] && mean < k[K_TOL] && !tri_pending) k[K_DONE] = T(1);
+      else if (T(it + 1) >= k[K_MAXITER]) k[K_DONE] = T(2);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_pupdate_kernel(T* __restrict__ p, const T* __restrict__ r, int64_t ld, int64_t n, int ncols,
+                  const T* __restrict__ state) {
+  // runs even on the final iteration (as the published loop does); p is not used afterwards
+  const int64_t total = n * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % ld);
+    if (c < ncols) p[e] = fma(state[S_BETA * ncols + c], p[e], r[e]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_finalize_kernel(const T* __restrict__ x, int64_t ld, T* __restrict__ out, int64_t ldo, int64_t n, int ncols,
+                   const T* __restrict__ state) {
+  const int64_t total = n * ncols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / ncols;
+    const int c = (int)(e - row * ncols);
+    out[row * ldo + c] = x[row * ld + c] * state[S_RHSNORM * ncols + c];
+  }
+}
+
+template <typename T>
+static int cg_check(int64_t n, int ncols, int64_t ld) {
+  MGP_CHECK_ARG(n > 0 && ncols > 0 && ncols <= kCgMaxCols, "cg: need 0 < ncols <= %d (got %d), n > 0", kCgMaxCols, ncols);
+  MGP_CHECK_ARG(ld >= ncols, "cg: ld %lld < ncols %d", (long long)ld, ncols);
+  return MGP_OK;
+}
+
+template <typename T>
+static int cg_init(const T* b, int64_t ldb, T* x, T* r, T* p, int64_t ld, int64_t n, int ncols, T tol, T eps, T stop,
+                   int max_iter, int n_tridiag_iter, T* state, void* ws, cudaStream_t st) {
+  int rc = cg_check<T>(n, ncols, ld);
+  if (rc) return rc;
+  MGP_CHECK_ARG(b && x && r && p && state && ws && ldb >= ncols, "cg_init: bad arguments");
+  const int CP = col_lanes(ncols);
+  const int grid = cg_grid(n, kCgBlock / CP);
+  cg_norm_kernel<T><<<grid, kCgBlock, 0, st>>>(b, ldb, n, ncols, CP, eps, state, ws);
+  MGP_LAUNCH_CHECK();
+  cg_init_kernel<T><<<grid, kCgBlock, 0, st>>>(b, ldb, x, r, p, ld, n, ncols, CP, tol, eps, stop, max_iter, n_tridiag_iter, state, ws);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+template <typename T>
+static int cg_alpha(const T* p, const T* v, int64_t ld, int64_t n, int ncols, int have_pap, T* state, void* ws,
+                    cudaStream_t st) {
+  int rc = cg_check<T>(n, ncols, ld);
+  if (rc) return rc;
+  if (have_pap) return MGP_OK;  // alpha itself is derived inside cg_update from (rz, pAp, masks)
+  MGP_CHECK_ARG(p && v && state && ws, "cg_alpha: null pointer");
+  const int CP = col_lanes(ncols);
+  cg_pap_kernel<T><<<cg_grid(n, kCgBlock / CP), kCgBlock, 0, st>>>(p, v, ld, n, ncols, CP, state, ws);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+template <typename T>
+static int cg_update(T* x, T* r, const T* p, const T* v, int64_t ld, int64_t n, int ncols, T* state, T* hist,
+                     int max_hist, void* ws, cudaStream_t st) {
+  int rc = cg_check<T>(n, ncols, ld);
+  if (rc) return rc;
+  MGP_CHECK_ARG(x && r && p && v && state && ws, "cg_update: null pointer");
+  const int CP = col_lanes(ncols);
+  cg_update_kernel<T><<<cg_grid(n, kCgBlock / CP), kCgBlock, 0, st>>>(x, r, p, v, ld, n, ncols, CP, state, hist, max_hist, ws);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+}  // namespace mgp
+
+using namespace mgp;
+
+extern "C" {
+
+size_t mgp_cg_state_elems(int32_t ncols) { return (size_t)S_NARR * ncols + K_NSCAL; }
+
+size_t mgp_cg_ws_bytes(int64_t n, int32_t ncols) {
+  (void)n;
+  return 256 + (size_t)kNumSMs * 8 * (size_t)ncols * 8;
+}
+
+int mgp_cg_init_f32(const float* b, int64_t ldb, float* x, float* r, float* p, int64_t ld, int64_t n, int32_t ncols,
+                    float tolerance, float eps, float stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter,
+                    float* state, void* ws, void* stream) {
+  return cg_init<float>(b, ldb, x, r, p, ld, n, ncols, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter, state, ws, (cudaStream_t)stream);
+}
+int mgp_cg_init_f64(const double* b, int64_t ldb, double* x, double* r, double* p, int64_t ld, int64_t n, int32_t ncols,
+                    double tolerance, double eps, double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter,
+                    double* state, void* ws, void* stream) {
+  return cg_init<double>(b, ldb, x, r, p, ld, n, ncols, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter, state, ws, (cudaStream_t)stream);
+}
+int mgp_cg_alpha_f32(const float* p, const float* v, int64_t ld, int64_t n, int32_t ncols, int32_t have_pap, float* state,
+                     void* ws, void* stream) {
+  return cg_alpha<float>(p, v, ld, n, ncols, have_pap, state, ws, (cudaStream_t)stream);
+}
+int mgp_cg_alpha_f64(const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols, int32_t have_pap,
+                     double* state, void* ws, void* stream) {
+  return cg_alpha<double>(p, v, ld, n, ncols, have_pap, state, ws, (cudaStream_t)stream);
+}
+int mgp_cg_update_f32(float* x, float* r, const float* p, const float* v, int64_t ld, int64_t n, int32_t ncols,
+                      float* state, float* hist, int32_t max_hist, void* ws, void* stream) {
+  return cg_update<float>(x, r, p, v, ld, n, ncols, state, hist, max_hist, ws, (cudaStream_t)stream);
+}
+int mgp_cg_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
+                      double* state, double* hist, int32_t max_hist, void* ws, void* stream) {
+  return cg_update<double>(x, r, p, v, ld, n, ncols, state, hist, max_hist, ws, (cudaStream_t)stream);
+}
+int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream) {
+  MGP_CHECK_ARG(p && r && state && n > 0 && ncols > 0 && ld >= ncols, "cg_pupdate: bad arguments");
+  const int64_t total = n * ld;
+  int64_t g = ceil_div(total, kCgBlock); if (g > kNumSMs * 16) g = kNumSMs * 16;
+  cg_pupdate_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(p, r, ld, n, ncols, state);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_pupdate_f64(double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream) {
+  MGP_CHECK_ARG(p && r && state && n > 0 && ncols > 0 && ld >= ncols, "cg_pupdate: bad arguments");
+  const int64_t total = n * ld;
+  int64_t g = ceil_div(total, kCgBlock); if (g > kNumSMs * 16) g = kNumSMs * 16;
+  cg_pupdate_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(p, r, ld, n, ncols, state);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_finalize_f32(const float* x, int64_t ld, float* out, int64_t ldo, int64_t n, int32_t ncols, const float* state,
+                        void* stream) {
+  MGP_CHECK_ARG(x && out && state && n > 0 && ncols > 0 && ld >= ncols && ldo >= ncols, "cg_finalize: bad arguments");
+  int64_t g = ceil_div(n * ncols, kCgBlock); if (g > kNumSMs * 16) g = kNumSMs * 16;
+  cg_finalize_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, ld, out, ldo, n, ncols, state);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_finalize_f64(const double* x, int64_t ld, double* out, int64_t ldo, int64_t n, int32_t ncols,
+                        const double* state, void* stream) {
+  MGP_CHECK_ARG(x && out && state && n > 0 && ncols > 0 && ld >= ncols && ldo >= ncols, "cg_finalize: bad arguments");
+  int64_t g = ceil_div(n * ncols, kCgBlock); if (g > kNumSMs * 16) g = kNumSMs * 16;
+  cg_finalize_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, ld, out, ldo, n, ncols, state);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// Exact brute-force kNN (squared L2, ascending), v1: fp32 CUDA-core distance tiles + fused threshold filter + rare-path
+// warp-cooperative insertion.  Any d; bit-identical candidate ordering to the oracle's "direct" form
+// (sum_d (q_d - x_d)^2 in ascending d, ties by ascending index).
+//
+// Reference: NearestNeighbors.search, manifold_gp/utils/nearest_neighbors.py:35-37 -> faiss Index{Flat,IVFFlat(nlist=1)}
+// .search (exhaustive; riemann_kernel.py:40 builds the index with nlist=1).
+//
+// Shape: one CTA owns 64 query rows and sweeps the whole database in 64-point tiles.  256 threads each hold a 4x4
+// micro-tile of squared distances in registers (d is consumed in chunks of 16 staged through shared memory).  Each
+// distance is compared in-register with its row's current k-th best (tau); only survivors (~k ln(N/k) per row over the
+// whole sweep) are pushed to a small shared-memory queue that the warps drain into per-row sorted lists.  The filter
+// keeps the selection cost at ~1 compare per candidate, which is what bounds small-d searches (d = 3: the "contraction"
+// is 3 FMAs per pair).  The tcgen05/TMEM variant for large d replaces only the distance-tile producer.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace mgp {
+
+constexpr int kKnnQ = 64;        // query rows per CTA
+constexpr int kKnnT = 64;        // database points per tile
+constexpr int kKnnD = 16;        // dims per shared-memory chunk
+constexpr int kKnnThreads = 256;
+constexpr int kKnnQueue = 2048;  // survivor queue capacity per tile
+constexpr int kKnnMaxK = 128;
+
+struct KnnSmem {
+  float qs[kKnnD][kKnnQ];
+  float ds[kKnnD][kKnnT];
+  float tau[kKnnQ];
+  int qcount;
+  float qd[kKnnQueue];
+  int qi[kKnnQueue];
+  int qr[kKnnQueue];
+  // followed by: float listd[kKnnQ][k]; int listi[kKnnQ][k];
+};
+
+__device__ __forceinline__ bool lex_less(float d0, int i0, float d1, int i1) { return d0 < d1 || (d0 == d1 && i0 < i1); }
+
+// Warp-cooperative insertion of (dnew, inew) into the ascending list of one row (k entries in shared memory).
+__device__ __forceinline__ void knn_insert(float* ld, int* li, int k, float dnew, int inew, int lane, float* tau_r) {
+  if (!lex_less(dnew, inew, ld[k - 1], li[k - 1])) return;  // warp-uniform (same smem values for every lane)
+  int cnt = 0;
+  for (int s = lane; s < k; s += 32) cnt += lex_less(ld[s], li[s], dnew, inew) ? 1 : 0;
+  const int pos = warp_sum(cnt);
+  float vd[kKnnMaxK / 32];
+  int vi[kKnnMaxK / 32];
+#pragma unroll
+  for (int t = 0; t < kKnnMaxK / 32; ++t) {
+    const int s = lane + 32 * t;
+    if (s > pos && s < k) { vd[t] = ld[s - 1]; vi[t] = li[s - 1]; }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < kKnnMaxK / 32; ++t) {
+    const int s = lane + 32 * t;
+    if (s > pos && s < k) { ld[s] = vd[t]; li[s] = vi[t]; }
+    if (s == pos) { ld[s] = dnew; li[s] = inew; }
+  }
+  __syncwarp();
+  if (lane == 0) *tau_r = ld[k - 1];
+}
+
+// Drain `count` queued survivors into the row lists.  Warp w owns rows r with (r & 7) == w.
+__device__ __forceinline__ void knn_drain(KnnSmem* s, float* listd, int* listi, int k, int count, int warp, int lane) {
+  for (int base = 0; base < count; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < count;
+    const int row_e = valid ? s->qr[e] : -1;
+    const float d_e = valid ? s->qd[e] : 0.f;
+    const int i_e = valid ? s->qi[e] : 0;
+    unsigned mask = __ballot_sync(0xffffffffu, valid && ((row_e & 7) == warp));
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int r = __shfl_sync(0xffffffffu, row_e, src);
+      const float dn = __shfl_sync(0xffffffffu, d_e, src);
+      const int in = __shfl_sync(0xffffffffu, i_e, src);
+      knn_insert(listd + r * k, listi + r * k, k, dn, in, lane, &s->tau[r]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kKnnThreads)
+knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q, int64_t nq, int d, int k,
+           float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KnnSmem* s = reinterpret_cast<KnnSmem*>(smem_raw);
+  float* listd = reinterpret_cast<float*>(smem_raw + sizeof(KnnSmem));
+  int* listi = reinterpret_cast<int*>(listd + kKnnQ * k);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 thread grid, 4 x 4 micro-tile each
+  const int64_t q0 = (int64_t)blockIdx.x * kKnnQ;
+
+  for (int e = tid; e < kKnnQ * k; e += kKnnThreads) { listd[e] = FLT_MAX * 2.f; listi[e] = 0x7fffffff; }  // +inf
+  if (tid < kKnnQ) s->tau[tid] = FLT_MAX * 2.f;
+  if (tid == 0) s->qcount = 0;
+  __syncthreads();
+
+  const int64_t ntiles = (n + kKnnT - 1) / kKnnT;
+  const int64_t t_first = (q0 / kKnnT) % ntiles;  // start with the tile that holds the block's own rows (self-search)
+  const bool single_chunk = d <= kKnnD;
+
+  auto load_q_chunk = [&](int d0) {
+    for (int e = tid; e < kKnnD * kKnnQ; e += kKnnThreads) {
+      const int r = e % kKnnQ, dd = e / kKnnQ;
+      const int64_t qi = q0 + r;
+      s->qs[dd][r] = (qi < nq && d0 + dd < d) ? __ldg(q + qi * d + d0 + dd) : 0.f;
+    }
+  };
+  if (single_chunk) load_q_chunk(0);
+
+  for (int64_t tt = 0; tt < ntiles; ++tt) {
+    const int64_t tile = (t_first + tt) % ntiles;
+    const int64_t c0 = tile * kKnnT;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    for (int d0 = 0; d0 < d; d0 += kKnnD) {
+      __syncthreads();  // previous consumers of qs/ds (and the previous drain) are done
+      if (!single_chunk) load_q_chunk(d0);
+      for (int e = tid; e < kKnnD * kKnnT; e += kKnnThreads) {
+        const int r = e % kKnnT, dd = e / kKnnT;
+        const int64_t ci = c0 + r;
+        s->ds[dd][r] = (ci < n && d0 + dd < d) ? __ldg(db + ci * d + d0 + dd) : 0.f;
+      }
+      __syncthreads();
+      const int dmax = min(kKnnD, d - d0);
+      for (int dd = 0; dd < dmax; ++dd) {
+        const float4 qv = *reinterpret_cast<const float4*>(&s->qs[dd][ty * 4]);
+        const float4 cv = *reinterpret_cast<const float4*>(&s->ds[dd][tx * 4]);
+        const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+        const float ca[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const float df = __fsub_rn(qa[a], ca[b]);
+            acc[a][b] = __fadd_rn(acc[a][b], __fmul_rn(df, df));  // no FMA contraction: matches the oracle's mul-then-add
+          }
+      }
+    }
+
+    // ---- fused selection: in-register threshold filter, survivors to the queue --------------------------------
+    float tau[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) tau[a] = s->tau[ty * 4 + a];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t ci = c0 + tx * 4 + b;
+        if (acc[a][b] <= tau[a] && ci < n && q0 + ty * 4 + a < nq) {
+          const int pos = atomicAdd(&s->qcount, 1);
+          if (pos < kKnnQueue) { s->qd[pos] = acc[a][b]; s->qi[pos] = (int)ci; s->qr[pos] = ty * 4 + a; }
+        }
+      }
+    __syncthreads();
+    const int count = s->qcount;
+    if (count <= kKnnQueue) {
+      if (count > 0) knn_drain(s, listd, listi, k, count, warp, lane);
+      __syncthreads();
+      if (tid == 0) s->qcount = 0;
+    } else {
+      // overflow (only while tau is still loose, i.e. the first tiles): redo the tile's selection in 16 sub-steps of
+      // at most 256 survivors each; nothing from the overflowing attempt was inserted, so there are no duplicates.
+      __syncthreads();
+      if (tid == 0) s->qcount = 0;
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int64_t ci = c0 + tx * 4 + b;
+          if (acc[a][b] <= s->tau[ty * 4 + a] && ci < n && q0 + ty * 4 + a < nq) {
+            const int pos = atomicAdd(&s->qcount, 1);
+            s->qd[pos] = acc[a][b]; s->qi[pos] = (int)ci; s->qr[pos] = ty * 4 + a;
+          }
+          __syncthreads();
+          const int cnt2 = s->qcount;
+          if (cnt2 > 0) knn_drain(s, listd, listi, k, cnt2, warp, lane);
+          __syncthreads();
+          if (tid == 0) s->qcount = 0;
+          __syncthreads();
+        }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < kKnnQ * k; e += kKnnThreads) {
+    const int r = e / k, c = e % k;
+    const int64_t qi = q0 + r;
+    if (qi < nq) {
+      const int id = listi[e];
+      const bool filled = id != 0x7fffffff;
+      out_d[qi * k + c] = filled ? listd[e] : __int_as_float(0x7f800000);
+      out_i[qi * k + c] = filled ? (int64_t)id : (int64_t)-1;
+    }
+  }
+}
+
+}  // namespace mgp
+
+using namespace mgp;
+
+extern "C" {
+
+size_t mgp_knn_search_ws_bytes(int64_t n, int64_t nq, int32_t d, int32_t k) {
+  (void)n; (void)nq; (void)d; (void)k;
+  return 256;  // v1 keeps all state in shared memory
+}
+
+int mgp_knn_search_f32(const float* db, int64_t n, const float* q, int64_t nq, int32_t d, int32_t k, float* dist2,
+                       int64_t* idx, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  MGP_CHECK_ARG(db && q && dist2 && idx, "knn_search: null pointer");
+  MGP_CHECK_ARG(n > 0 && nq > 0 && d > 0, "knn_search: n, nq, d must be positive");
+  MGP_CHECK_ARG(k > 0 && k <= kKnnMaxK, "knn_search: k must be in [1, %d] (got %d)", kKnnMaxK, k);
+  MGP_CHECK_ARG(n < ((int64_t)1 << 31), "knn_search: n must be < 2^31");
+  const size_t smem = sizeof(KnnSmem) + (size_t)kKnnQ * k * 8;
+  MGP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = ceil_div(nq, kKnnQ);
+  MGP_CHECK_ARG(grid < ((int64_t)1 << 31), "knn_search: too many queries for one launch");
+  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, (cudaStream_t)stream>>>(db, n, q, nq, d, k, dist2, idx);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+"""Host drivers of the CUDA solvers: batched CG (mBCG), Lanczos, SLQ log-det, and the dispatch rules of
+``LinearOperator.solve / inv_quad_logdet / diagonalization``.
+
+These replace the linear_operator loops the reference reaches at utils/train_model.py:55,67-68,
+operators/precision_matern_operator.py:53, operators/schur_complement_operator.py:28 and
+operators/graph_laplacian_operator.py:132-135 (third party; algorithm restated in oracle/solvers.py).  The
+arithmetic of every iteration is in libmgp_b200.so (fused SpMM with dot epilogue + fused vector updates);
+the host only enqueues launches and polls one device flag every ``settings.cg_check_interval`` iterations.
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+
+from . import _lib, settings
+from ._compat.linear_operator import DenseEigenvectors
+from ._lib import c_double, c_float, c_int32, c_int64, ptr, stream
+
+# state layout (must match csrc/cg.cu)
+S_RHSNORM, S_RZ, S_PAP, S_ALPHA, S_BETA, S_RESID, S_RHSZERO, S_CONV, S_NARR = range(9)
+K_MEAN, K_DONE, K_ITER = 0, 1, 2
+MAX_CG_COLS = 128
+
+
+def _pad_ld(c: int, dtype) -> int:
+    v = 4 if dtype == torch.float32 else 2
+    return (c + v - 1) // v * v
+
+
+class CGInfo(dict):
+    pass
+
+
+def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter):
+    """mBCG on <= 128 columns.  Returns (solution [n,C], hist (cpu) or None, info)."""
+    n, c = rhs.shape
+    dt, dev = rhs.dtype, rhs.device
+    sfx = _lib.suffix(dt)
+    fused = hasattr(op, "_mgp_matvec") and getattr(op, "_native", lambda: True)()
+    ld = _pad_ld(c, dt) if fused else c
+    fl = c_float if dt == torch.float32 else c_double
+
+    x = torch.empty((n, ld), dtype=dt, device=dev)
+    r = torch.empty((n, ld), dtype=dt, device=dev)
+    p = torch.empty((n, ld), dtype=dt, device=dev)
+    v = torch.zeros((n, ld), dtype=dt, device=dev)
+    tmp = torch.zeros((n, ld), dtype=dt, device=dev) if fused else None
+    state = torch.zeros(_lib.query("mgp_cg_state_elems", c_int32(c)), dtype=dt, device=dev)
+    ws = torch.zeros(_lib.query("mgp_cg_ws_bytes", c_int64(n), c_int32(c)), dtype=torch.uint8, device=dev)
+    max_hist = max(1, min(max_iter, n_tridiag_iter)) if n_tridiag else 1
+    hist = torch.zeros((max_hist, 2, c), dtype=dt, device=dev) if n_tridiag else None
+    rhs_c = rhs if rhs.stride(1) == 1 else rhs.contiguous()
+
+    _lib.call("mgp_cg_init_" + sfx, ptr(rhs_c), c_int64(rhs_c.stride(0)), ptr(x), ptr(r), ptr(p), c_int64(ld), c_int64(n),
+              c_int32(c), fl(tolerance), fl(eps), fl(stop_updating_after), c_int32(max_iter),
+              c_int32(n_tridiag_iter if n_tridiag else 0), ptr(state), ptr(ws), stream())
+    pap = state[S_PAP * c:(S_PAP + 1) * c]
+    check = max(1, int(settings.cg_check_interval.value()))
+    k = 0
+    done = 0.0
+    scal = S_NARR * c
+    while k < max_iter:
+        steps = min(check, max_iter - k)
+        for _ in range(steps):
+            if fused:
+                op._mgp_matvec(p, v, tmp, dot_with=p, dot_out=pap, ncols=c)   # pAp comes out of the last SpMM launch
+                have_pap = 1
+            else:
+                with torch.no_grad():
+                    out = op._matmul(p)
+                v.copy_(out)
+                have_pap = 0
+            _lib.call("mgp_cg_alpha_" + sfx, ptr(p), ptr(v), c_int64(ld), c_int64(n), c_int32(c), c_int32(have_pap),
+                      ptr(state), ptr(ws), stream())
+            _lib.call("mgp_cg_update_" + sfx, ptr(x), ptr(r), ptr(p), ptr(v), c_int64(ld), c_int64(n), c_int32(c),
+                      ptr(state), ptr(hist), c_int32(max_hist if n_tridiag else 0), ptr(ws), stream())
+            _lib.call("mgp_cg_pupdate_" + sfx, ptr(p), ptr(r), c_int64(ld), c_int64(n), c_int32(c), ptr(state), stream())
+        k += steps
+        done = float(state[scal + K_DONE].item())   # the only device->host read of the loop
+        if done != 0.0:
+            break
+    out = torch.empty((n, c), dtype=dt, device=dev)
+    _lib.call("mgp_cg_finalize_" + sfx, ptr(x), c_int64(ld), ptr(out), c_int64(c), c_int64(n), c_int32(c), ptr(state), stream())
+    tail = state[scal:scal + 3].tolist()
+    info = CGInfo(iterations=int(tail[K_ITER]), mean_residual=float(tail[K_MEAN]), converged=(done == 1.0),
+                  residual_norm=state[S_RESID * c:(S_RESID + 1) * c].clone())
+    return out, (hist.cpu() if n_tridiag else None), info
+
+
+def _tridiag_from_hist(hist, n_rows, n_tridiag, dtype):
+    """Lanczos tridiagonals from the CG coefficients, as linear_cg assembles them (incl. the update_tridiag latch)."""
+    t = torch.zeros(n_rows, n_rows, n_tridiag, dtype=hist.dtype)
+    update = True
+    last = 0
+    prev_ar = prev_b = None
+    for k in range(n_rows):
+        if not update:
+            break
+        a = hist[k, 0, :n_tridiag].clone()
+        b = hist[k, 1, :n_tridiag].clone()
+        ar = a.masked_fill(a.eq(0), 1).reciprocal()
+        if k == 0:
+            t[0, 0] = ar
+        else:
+            t[k, k] = ar + prev_b * prev_ar
+            off = prev_b.sqrt() * prev_ar
+            t[k, k - 1] = off
+            t[k - 1, k] = off
+            if t[k - 1, k].max() < 1e-6:
+                update = False
+        last = k
+        prev_ar, prev_b = ar, b
+    t = t[: last + 1, : last + 1]
+    return t.permute(2, 0, 1).contiguous().to(dtype)
+
+
+def linear_cg(op, rhs, n_tridiag=0, tolerance=None, eps=1e-10, stop_updating_after=1e-10, max_iter=None,
+              max_tridiag_iter=None, return_info=False):
+    """CUDA mBCG.  ``op`` is a LinearOperator (``_matmul``; the fused path is used when it offers ``_mgp_matvec``).
+    Same arguments / defaults / stopping rules as ``linear_operator.utils.linear_cg`` (no preconditioner)."""
+    if not rhs.is_cuda:
+        raise RuntimeError("linear_cg: rhs must be a CUDA tensor (no CPU fallback exists)")
+    is_vector = rhs.dim() == 1
+    if is_vector:
+        rhs = rhs.unsqueeze(-1)
+    if max_iter is None:
+        max_iter = settings.max_cg_iterations.value()
+    if max_tridiag_iter is None:
+        max_tridiag_iter = settings.max_lanczos_quadrature_iterations.value()
+    if tolerance is None:
+        tolerance = settings.eval_cg_tolerance.value() if settings._use_eval_tolerance.on() else settings.cg_tolerance.value()
+    if max_tridiag_iter > max_iter:
+        raise RuntimeError("Getting a tridiagonalization larger than the number of CG iterations run is not possible!")
+    n, c = rhs.shape
+    n_iter = min(max_iter, n) if settings.terminate_cg_by_size.on() else max_iter
+    n_tridiag_iter = min(max_tridiag_iter, n)
+    if n_tridiag > MAX_CG_COLS:
+        raise RuntimeError(f"linear_cg: at most {MAX_CG_COLS} tridiagonals per call")
+    outs, infos, hist0 = [], [], None
+    for c0 in range(0, c, MAX_CG_COLS):
+        # NB column chunks converge independently (the published mean-over-columns test is applied per chunk)
+        nt = n_tridiag if c0 == 0 else 0
+        o, h, info = _cg_chunk(op, rhs[:, c0:c0 + MAX_CG_COLS], nt, float(tolerance), float(eps), float(stop_updating_after),
+                               int(n_iter), int(n_tridiag_iter))
+        outs.append(o)
+        infos.append(info)
+        if c0 == 0:
+            hist0 = h
+    result = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+    info = infos[0] if len(infos) == 1 else CGInfo(
+        iterations=max(i["iterations"] for i in infos), converged=all(i["converged"] for i in infos),
+        mean_residual=sum(i["mean_residual"] for i in infos) / len(infos),
+        residual_norm=torch.cat([i["residual_norm"] for i in infos]))
+    if not info["converged"] and n_iter > 0:
+        warnings.warn("CG terminated in {} iterations with average residual norm {} which is larger than the tolerance "
+                      "of {} specified by settings.cg_tolerance.".format(info["iterations"], info["mean_residual"], tolerance),
+                      RuntimeWarning)
+    if is_vector:
+        result = result.squeeze(-1)
+    if n_tridiag:
+        k_done = infos[0]["iterations"]
+        rows = k_done - 1 if infos[0]["converged"] else k_done
+        rows = max(1, min(rows, n_tridiag_iter))
+        t_mat = _tridiag_from_hist(hist0, rows, n_tridiag, rhs.dtype).to(rhs.device)
+        return (result, t_mat, info) if return_info else (result, t_mat)
+    return (result, info) if return_info else result
+
+
+# ---- Lanczos ----------------------------------------------------------------------------------------------------------
+def lanczos_tridiag(op, max_iter, init_vec=None, tol=1e-5, generator=None):
+    """Lanczos with full re-orthogonalisation.  Returns ``q_mat[j, n]`` (vector-major!) and ``t_mat[j, j]``.
+
+    Each step: r = A q_k (fused SpMM), then classical Gram-Schmidt against ALL previous vectors in one fused pass
+    (``mgp_lanczos_reorth``: removes alpha_k q_k, beta_{k-1} q_{k-1} and every other component; alpha_k = c[k]),
+    then check passes (``mgp_lanczos_dots`` / ``mgp_lanczos_axpy``) while any |q_j . r| / |r| > tol (<= 10), as
+    linear_operator.utils.lanczos.lanczos_tridiag does; early exit when beta < 1e-6.
+    """
+    n = op.shape[0]
+    dt, dev = op.dtype, op.device
+    if dev.type != "cuda":
+        raise RuntimeError("lanczos_tridiag: operator must live on a CUDA device (no CPU fallback exists)")
+    sfx = _lib.suffix(dt)
+    num_iter = min(int(max_iter), n)
+    if init_vec is None:
+        init_vec = torch.randn(n, dtype=dt, device=dev, generator=generator)
+    q = torch.empty((num_iter + 1, n), dtype=dt, device=dev)
+    r = init_vec.reshape(n).to(dt).clone()
+    c = torch.zeros(num_iter + 1, dtype=dt, device=dev)
+    nrm2 = torch.zeros(1, dtype=dt, device=dev)
+    beta = torch.zeros(1, dtype=dt, device=dev)
+    ws = torch.zeros(_lib.query("mgp_lanczos_ws_bytes", c_int64(n), c_int32(num_iter + 1)), dtype=torch.uint8, device=dev)
+    alphas = torch.zeros(num_iter, dtype=dt, device=dev)
+    betas = torch.zeros(num_iter, dtype=dt, device=dev)
+    fused = hasattr(op, "_mgp_matvec") and getattr(op, "_native", lambda: True)()
+    tmp = torch.empty((n, 1), dtype=dt, device=dev) if fused else None
+
+    _lib.call("mgp_lanczos_reorth_" + sfx, None, c_int64(n), c_int32(0), ptr(r), c_int64(n), ptr(c), ptr(nrm2), ptr(ws), stream())
+    _lib.call("mgp_lanczos_normalize_" + sfx, ptr(r), c_int64(n), ptr(nrm2), ptr(q[0]), None, stream())
+    steps = 0
+    for k in range(num_iter):
+        qk = q[k].unsqueeze(-1)
+        if fused:
+            op._mgp_matvec(qk, r.unsqueeze(-1), tmp, ncols=1)
+        else:
+            with torch.no_grad():
+                r.copy_(op._matmul(qk).reshape(n))
+        j = k + 1
+        _lib.call("mgp_lanczos_reorth_" + sfx, ptr(q), c_int64(n), c_int32(j), ptr(r), c_int64(n), ptr(c), ptr(nrm2), ptr(ws), stream())
+        alphas[k:k + 1].copy_(c[k:k + 1])
+        steps = k + 1
+        if k + 1 >= num_iter:
+            break
+        ok = False
+        for _ in range(10):
+            _lib.call("mgp_lanczos_dots_" + sfx, ptr(q), c_int64(n), c_int32(j), ptr(r), c_int64(n), ptr(c), ptr(ws), stream())
+            worst, nr2 = torch.stack((c[:j].abs().max(), nrm2[0])).tolist()   # one device->host read per pass
+            if nr2 <= 0.0 or worst / (nr2 ** 0.5) <= tol:
+                ok = True
+                break
+            _lib.call("mgp_lanczos_axpy_" + sfx, ptr(q), c_int64(n), c_int32(j), ptr(r), c_int64(n), ptr(c), ptr(nrm2), ptr(ws), stream())
+        _lib.call("mgp_lanczos_normalize_" + sfx, ptr(r), c_int64(n), ptr(nrm2), ptr(q[k + 1]), ptr(beta), stream())
+        betas[k:k + 1].copy_(beta)
+        if nr2 ** 0.5 <= 1e-6 or not ok:
+            break
+    t = torch.diag(alphas[:steps])
+    if steps > 1:
+        off = betas[:steps - 1]
+        t = t + torch.diag(off, 1) + torch.diag(off, -1)
+    return q[:steps], t
+
+
+def lanczos_tridiag_to_diag(t_mat):
+    """eigh of the tridiagonal; negative Ritz values -> 1 with zeroed vectors (published behaviour)."""
+    evals, evecs = torch.linalg.eigh(t_mat)
+    mask = evals.ge(0)
+    evecs = evecs * mask.to(evecs.dtype).unsqueeze(-2)
+    evals = evals.masked_fill(~mask, 1)
+    return evals, evecs
+
+
+def diagonalization(op, method=None):
+    """``LinearOperator.diagonalization``: 'symeig' (dense) when size <= max_cholesky_size, else 'lanczos' with
+    ``settings.max_root_decomposition_size`` steps.  Returns (evals ascending, DenseEigenvectors)."""
+    n = op.shape[0]
+    if method is None:
+        method = "symeig" if n <= settings.max_cholesky_size.value() else "lanczos"
+    if method == "symeig":
+        with torch.no_grad():
+            evals, evecs = torch.linalg.eigh(op.to_dense())
+        return evals, DenseEigenvectors(evecs)
+    if method == "lanczos":
+        with torch.no_grad():
+            q, t = lanczos_tridiag(op, settings.max_root_decomposition_size.value())
+            evals, v = lanczos_tridiag_to_diag(t)
+            evecs = q.T @ v       # plain library GEMM [n, j] x [j, j]
+        return evals, DenseEigenvectors(evecs)
+    raise RuntimeError(f"Unknown diagonalization method '{method}'")
+
+
+# ---- solve / inv_quad_logdet ---------------------------------------------------------------------------------------------
+def _params_requiring_grad(op):
+    return [t for t in op.representation() if t.is_floating_point() and t.requires_grad]
+
+
+def _cg_tol():
+    return settings.eval_cg_tolerance.value() if settings._use_eval_tolerance.on() else settings.cg_tolerance.value()
+
+
+class _CGSolveFn(torch.autograd.Function):
+    """x = A^-1 b by CUDA CG; backward: g_b = A^-1 g, g_theta = -(A^-1 g)^T (dA/dtheta) x  (A symmetric)."""
+
+    @staticmethod
+    def forward(ctx, op, rhs, *params):
+        ctx.op = op
+        with torch.no_grad():
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                x = linear_cg(op, rhs, tolerance=_cg_tol())
+        ctx.save_for_backward(x)
+        ctx.n_params = len(params)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        op = ctx.op
+        with torch.no_grad():
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                u = linear_cg(op, g.contiguous(), tolerance=_cg_tol())
+        grads = [None] * ctx.n_params
+        params = _params_requiring_grad(op)
+        if params:
+            with torch.enable_grad():
+                val = -(u * op._matmul(x)).sum()
+                pg = torch.autograd.grad(val, params, allow_unused=True)
+            # map back onto the positional params given to forward (same order as _params_requiring_grad)
+            grads = list(pg)
+        return (None, u if ctx.needs_input_grad[1] else None, *grads)
+
+
+def solve(op, rhs):
+    """``LinearOperator.solve``: dense Cholesky when size <= max_cholesky_size, CUDA CG otherwise."""
+    n = op.shape[0]
+    squeeze = rhs.dim() == 1
+    r = rhs.unsqueeze(-1) if squeeze else rhs
+    if n <= settings.max_cholesky_size.value():
+        chol = torch.linalg.cholesky(op.to_dense())
+        out = torch.cholesky_solve(r, chol)
+    else:
+        params = _params_requiring_grad(op) if torch.is_grad_enabled() else []
+        if params or (torch.is_grad_enabled() and r.requires_grad):
+            out = _CGSolveFn.apply(op, r, *params)
+        else:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                out = linear_cg(op, r, tolerance=_cg_tol())
+    return out.squeeze(-1) if squeeze else out
+
+
+def inv_quad_logdet(op, inv_quad_rhs=None, logdet=False, reduce_inv_quad=True, probes=None, return_info=False):
+    """``LinearOperator.inv_quad_logdet``.
+
+    size <= max_cholesky_size: dense Cholesky (differentiable through the dense matmul).
+    otherwise: one mBCG run on [probes | rhs]; log|A| by stochastic Lanczos quadrature from the CG tridiagonals;
+    gradients via the same identities linear_operator's ``InvQuadLogdet.backward`` uses, expressed as surrogates
+    through one differentiable operator matvec:  d log|A| = E_z[(A^-1 z)^T dA z],  d (r^T A^-1 r) = -s^T dA s + 2 s^T dr.
+    """
+    n = op.shape[0]
+    dt, dev = op.dtype, op.device
+    zero = torch.zeros((), dtype=dt, device=dev)
+    rhs = None
+    if inv_quad_rhs is not None:
+        rhs = inv_quad_rhs if inv_quad_rhs.dim() == 2 else inv_quad_rhs.unsqueeze(-1)
+    if n <= settings.max_cholesky_size.value():
+        chol = torch.linalg.cholesky(op.to_dense())
+        iq = zero
+        if rhs is not None:
+            sol = torch.linalg.solve_triangular(chol, rhs.to(dt), upper=False)
+            iq = sol.pow(2).sum(-2)
+            if reduce_inv_quad:
+                iq = iq.sum(-1)
+        ld = chol.diagonal().log().sum() * 2 if logdet else zero
+        return (iq, ld, None) if return_info else (iq, ld)
+
+    cols = []
+    n_probe = 0
+    if logdet:
+        if probes is None:
+            probes = torch.randn(n, settings.num_trace_samples.value(), dtype=dt, device=dev)
+        pn = probes.norm(2, dim=-2, keepdim=True)
+        probes_unit = probes / pn
+        cols.append(probes_unit)
+        n_probe = probes.shape[1]
+    if rhs is not None:
+        cols.append(rhs.detach().to(dt))
+    allrhs = torch.cat(cols, dim=1).contiguous()
+    with torch.no_grad():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            if n_probe:
+                solves, t_mat, info = linear_cg(op, allrhs, n_tridiag=n_probe, tolerance=_cg_tol(), return_info=True)
+            else:
+                solves, info = linear_cg(op, allrhs, tolerance=_cg_tol(), return_info=True)
+    iq, ld = zero, zero
+    need_grad = torch.is_grad_enabled() and (bool(_params_requiring_grad(op)) or (rhs is not None and inv_quad_rhs.requires_grad))
+    if logdet:
+        evals, evecs = lanczos_tridiag_to_diag(t_mat)
+        ld = (n / float(n_probe)) * (evecs[..., 0, :].pow(2) * evals.log()).sum(-1).sum(0)
+    if rhs is not None:
+        s = solves[:, n_probe:]
+        iq = (s * rhs.detach()).sum(-2)
+    if need_grad:
+        # one differentiable matvec on [z | s]
+        zs = []
+        if logdet:
+            zs.append(probes_unit * pn)           # un-normalised probes z
+        if rhs is not None:
+            zs.append(solves[:, n_probe:])
+        az = op._matmul(torch.cat(zs, dim=1).contiguous())
+        if logdet:
+            u = solves[:, :n_probe] * pn          # A^-1 z
+            sur = (u * az[:, :n_probe]).sum() / n_probe
+            ld = ld + (sur - sur.detach())
+        if rhs is not None:
+            s = solves[:, n_probe:]
+            a_s = az[:, n_probe if logdet else 0:]
+            sur = 2.0 * (s * (inv_quad_rhs if inv_quad_rhs.dim() == 2 else inv_quad_rhs.unsqueeze(-1))).sum(-2) - (s * a_s).sum(-2)
+            iq = iq + (sur - sur.detach())
+    if rhs is not None and reduce_inv_quad:
+        iq = iq.sum(-1)
+    return (iq, ld, info) if return_info else (iq, ld)

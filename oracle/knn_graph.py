@@ -38,7 +38,8 @@ def knn_search(db: torch.Tensor, q: torch.Tensor, k: int, block: int = 2048, for
             d2 = torch.zeros(qb.shape[0], n, dtype=db.dtype)
             for j in range(db.shape[1]):  # sequential over d: the summation order the CUDA kernel uses for small d
                 diff = qb[:, j:j + 1] - db[:, j].unsqueeze(0)
-                d2.addcmul_(diff, diff)
+                sq = diff * diff          # rounded product, then a rounded add: no FMA contraction (the CUDA
+                d2 += sq                  # kernel uses __fmul_rn / __fadd_rn so the two agree bit for bit)
         # stable sort on (distance, index): ascending distance, ties by ascending index
         dd, ii = torch.sort(d2, dim=1, stable=True)
         out_d[s:s + block, :k_eff] = dd[:, :k_eff]

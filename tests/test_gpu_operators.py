@@ -1,0 +1,238 @@
+"""GPU parity of the operators (through the C ABI) against the reference's dense operators (golden fixtures) and
+the oracle.  Tolerances are the north-star's: matvecs 1e-5 relative in fp32, 1e-10 in fp64."""
+import pytest
+import torch
+
+import oracle
+from conftest import NORMALIZATIONS, PARAM_SETS_K10, gtag, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float64: 1e-10, torch.float32: 1e-5}
+
+
+def _ops(g, eps, kappa, nu, normalization, self_loops, dtype, requires_grad=False):
+    import manifold_gp_b200 as mgp
+    idx = torch.from_numpy(g["idx"]).long().to(DEV)
+    val = torch.from_numpy(g["val"]).to(dtype).to(DEV)
+    n = g["V"].shape[0]
+    e = torch.tensor([[eps]], dtype=dtype, device=DEV, requires_grad=requires_grad)
+    kp = torch.tensor([[kappa]], dtype=dtype, device=DEV, requires_grad=requires_grad)
+    lap = mgp.GraphLaplacianOperator(val, idx, n, e, normalization, self_loops)
+    prec = mgp.PrecisionMaternOperator(lap, nu, kp)
+    return lap, prec, e, kp
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("self_loops", [True, False])
+@pytest.mark.parametrize("normalization", NORMALIZATIONS)
+@pytest.mark.parametrize("eps,kappa,nu", PARAM_SETS_K10)
+def test_operators_vs_reference_dense(golden_k10, eps, kappa, nu, normalization, self_loops, dtype):
+    import manifold_gp_b200 as mgp
+    g = golden_k10
+    tag = gtag(eps, kappa, nu, normalization, self_loops)
+    tol = TOL[dtype]
+    lap, prec, _, _ = _ops(g, eps, kappa, nu, normalization, self_loops, dtype)
+    V = torch.from_numpy(g["V"]).to(dtype).to(DEV)
+    assert lap.shape == (V.shape[0], V.shape[0])
+    assert rel_err(lap.degree_unnorm_mat, g[f"{tag}_deg_unnorm"]) < tol
+    assert rel_err(lap.degree_mat, g[f"{tag}_deg"]) < tol
+    assert rel_err(lap.diagonal(), g[f"{tag}_Ldiag"]) < tol                                   # test_diag
+    assert rel_err(lap.matmul(V[:, 1:]), g[f"{tag}_LV"][:, 1:]) < tol                          # test_mv
+    assert rel_err(lap.T.matmul(V[:, 1:]), g[f"{tag}_LtV"][:, 1:]) < tol                       # test_mv_transpose
+    assert rel_err(lap.matmul(V), g[f"{tag}_LV"]) < tol * 20                                   # incl. the smooth column
+    y1 = lap.matmul(V[:, 0])                                                                   # 1-D rhs
+    assert y1.shape == (V.shape[0],)
+    scale = float((lap.laplacian_diag * V[:, 0]).double().norm())
+    assert float((y1.double().cpu() - torch.from_numpy(g[f"{tag}_LV"][:, 0])).norm()) / scale < tol
+    ptol = tol * (10 if dtype == torch.float32 and nu == 3 else 1)
+    assert rel_err(prec.matmul(V), g[f"{tag}_PV"]) < ptol
+    assert prec.T is prec
+    oscale = torch.tensor(1.7, dtype=dtype, device=DEV)
+    noise = torch.tensor(0.02, dtype=dtype, device=DEV)
+    assert rel_err(mgp.ScaleWrapperOperator(prec, oscale).matmul(V), g[f"{tag}_PmulV"]) < ptol
+    pdiv = mgp.ScaleWrapperOperator(prec, oscale, inverse_scale=True)
+    assert rel_err(pdiv.matmul(V), g[f"{tag}_PdivV"]) < ptol
+    if dtype == torch.float64 or nu < 3:
+        assert rel_err(mgp.NoiseWrapperOperator(pdiv, noise).matmul(V), g[f"{tag}_PnoisyV"]) < ptol * 10
+    # per-edge arrays the reference exposes
+    olap = oracle.LaplacianOracle(torch.from_numpy(g["val"]).to(dtype), torch.from_numpy(g["idx"]).long(), V.shape[0],
+                                  eps, normalization, self_loops)
+    assert rel_err(lap.laplacian_triu, olap.laplacian_triu) < tol
+    assert rel_err(lap.adjacency_mat, olap.adjacency_mat) < tol
+
+
+@pytest.mark.parametrize("normalization", NORMALIZATIONS)
+def test_k50_test_laplacian_configuration(golden_k50, normalization):
+    """test/test_laplacian.py:34-50: k=50, nu=1, eps=0.5, kappa=0.5, self_loops=False."""
+    g = golden_k50
+    tag = gtag(0.5, 0.5, 1, normalization, False)
+    for dtype in (torch.float64, torch.float32):
+        lap, prec, _, _ = _ops(g, 0.5, 0.5, 1, normalization, False, dtype)
+        V = torch.from_numpy(g["V"]).to(dtype).to(DEV)
+        assert rel_err(lap.matmul(V[:, 1:]), g[f"{tag}_LV"][:, 1:]) < TOL[dtype]
+        assert rel_err(lap.T.matmul(V[:, 1:]), g[f"{tag}_LtV"][:, 1:]) < TOL[dtype]
+        assert rel_err(prec.matmul(V), g[f"{tag}_PV"]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("ncols", [1, 2, 3, 4, 7, 8, 10, 16, 20, 33, 100])
+def test_spmm_column_counts_vs_oracle(ncols, dtype):
+    """Every kernel instantiation (vector widths 16/8/4, scalar widths 1..32, multi-pass) on a 30k-point torus."""
+    import manifold_gp_b200 as mgp
+    x = oracle.datasets.torus(30000, seed=1)
+    oidx, oval = oracle.knn_graph(x, 16)
+    n = x.shape[0]
+    eps, kappa, nu = 0.12, 0.5, 2
+    gen = torch.Generator().manual_seed(ncols)
+    V = torch.randn(n, ncols, generator=gen, dtype=dtype)
+    for normalization in NORMALIZATIONS:
+        olap = oracle.LaplacianOracle(oval.double(), oidx, n, eps, normalization, True)
+        ref_l = olap.matmul(V.double())
+        ref_p = oracle.precision_matmul(olap, nu, kappa, V.double())
+        lap = mgp.GraphLaplacianOperator(oval.to(dtype).to(DEV), oidx.to(DEV), n,
+                                         torch.tensor([[eps]], dtype=dtype, device=DEV), normalization)
+        prec = mgp.PrecisionMaternOperator(lap, nu, torch.tensor([[kappa]], dtype=dtype, device=DEV))
+        assert rel_err(lap.matmul(V.to(DEV)), ref_l) < TOL[dtype]
+        assert rel_err(prec.matmul(V.to(DEV)), ref_p) < TOL[dtype]
+        # non-contiguous rhs (a column slice of a wider buffer)
+        wide = torch.zeros(n, ncols + 3, dtype=dtype, device=DEV)
+        wide[:, 1:1 + ncols] = V.to(DEV)
+        assert rel_err(lap.matmul(wide[:, 1:1 + ncols]), ref_l) < TOL[dtype]
+
+
+def test_linearity_and_symmetry_at_scale():
+    """Size-independent properties at N = 1M, k = 32 (BASELINE cfg-C): <u, P v> == <P u, v>, P(au+bv) == aPu + bPv."""
+    import manifold_gp_b200 as mgp
+    x = oracle.datasets.torus(1_000_000, seed=0).to(DEV)
+    idx, val = mgp.NearestNeighbors(x).graph(32)
+    n = x.shape[0]
+    assert abs(idx.shape[1] - 16_720_874) <= 20    # M at N=1M, k=32, seed 0 from an independent CPU kd-tree (fp32/fp64 near-ties may flip a few edges)
+    lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[0.0274]], device=DEV), "symmetric")
+    prec = mgp.PrecisionMaternOperator(lap, 2, torch.tensor([[0.5]], device=DEV))
+    g = torch.Generator(device=DEV).manual_seed(3)
+    u = torch.randn(n, 16, device=DEV, generator=g)
+    v = torch.randn(n, 16, device=DEV, generator=g)
+    pu, pv = prec.matmul(u), prec.matmul(v)
+    a = (u.double() * pv.double()).sum()
+    b = (pu.double() * v.double()).sum()
+    assert abs(float(a - b)) / abs(float(a)) < 1e-5
+    comb = prec.matmul(0.3 * u - 1.7 * v)
+    assert rel_err(comb, 0.3 * pu - 1.7 * pv) < 1e-5
+    # the Laplacian annihilates D^{1/2} 1 (constant function on the random-walk side)
+    one = lap.degree_mat.sqrt().unsqueeze(-1)
+    assert float(lap.matmul(one).norm() / (lap.laplacian_diag.unsqueeze(-1) * one).norm()) < 1e-5
+
+
+def test_dot_epilogue_matches_separate_reduction():
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph
+    x = oracle.datasets.torus(50000, seed=2)
+    oidx, oval = oracle.knn_graph(x, 12)
+    n = x.shape[0]
+    for dtype in (torch.float32, torch.float64):
+        lap = mgp.GraphLaplacianOperator(oval.to(dtype).to(DEV), oidx.to(DEV), n,
+                                         torch.tensor([[0.1]], dtype=dtype, device=DEV), "symmetric")
+        _, _, diag, a = lap._values()
+        for c in (1, 5, 16, 32):
+            X = torch.randn(n, c, dtype=dtype, device=DEV)
+            dot = torch.zeros(c, dtype=dtype, device=DEV)
+            Y = graph.lap_spmm(lap.structure, a, diag, X, dot_with=X, dot_out=dot)
+            ref = (X.double() * Y.double()).sum(0)
+            assert rel_err(dot, ref) < (1e-5 if dtype == torch.float32 else 1e-12)
+            dot2 = torch.zeros(c, dtype=dtype, device=DEV)
+            graph.lap_spmm(lap.structure, a, diag, X, dot_with=X, dot_out=dot2)
+            assert torch.equal(dot, dot2), "dot epilogue must be deterministic run to run"
+
+
+@pytest.mark.parametrize("self_loops", [True, False])
+@pytest.mark.parametrize("normalization", NORMALIZATIONS)
+def test_grad_eps_vs_reference_dense(golden_k10, normalization, self_loops):
+    """test_grad (test/_test_functions.py:59-74): d/d eps of sum(L^T v) through the CUDA backward kernels."""
+    g = golden_k10
+    tag = gtag(0.5, 1.3, 2, normalization, self_loops)
+    lap, _, e, _ = _ops(g, 0.5, 1.3, 2, normalization, self_loops, torch.float64, requires_grad=True)
+    v = torch.from_numpy(g["V"])[:, :1].to(DEV)
+    loss = lap.T.matmul(v).sum()
+    (ge,) = torch.autograd.grad(loss, e)
+    ref = float(g[f"{tag}_grad_eps_sumLtv"].reshape(-1)[0])
+    assert abs(float(ge) - ref) < 1e-8 * max(1.0, abs(ref))
+
+
+@pytest.mark.parametrize("normalization", NORMALIZATIONS)
+def test_nll_and_grads_vs_reference_dense(golden_k10, dumbbell, normalization):
+    """test_ml (test/_test_functions.py:77-104), Cholesky branch (max_cholesky >= N as in the notebooks), fp64:
+    loss and d/d(eps, kappa, outputscale, noise) against the reference's dense autograd."""
+    import math
+    import manifold_gp_b200 as mgp
+    g = golden_k10
+    tag = gtag(0.5, 1.3, 2, normalization, True)
+    lap, prec, e, kp = _ops(g, 0.5, 1.3, 2, normalization, True, torch.float64, requires_grad=True)
+    oscale = torch.tensor(1.7, dtype=torch.float64, device=DEV, requires_grad=True)
+    noise = torch.tensor(0.02, dtype=torch.float64, device=DEV, requires_grad=True)
+    op = mgp.NoiseWrapperOperator(mgp.ScaleWrapperOperator(prec, oscale, inverse_scale=True), noise)
+    y = dumbbell["train_y"].double().to(DEV)
+    with mgp.settings.max_cholesky_size(2000):
+        loss = 0.5 * sum([torch.dot(y, op.matmul(y.view(-1, 1)).squeeze()), -op.inv_quad_logdet(logdet=True)[1],
+                          y.shape[0] * math.log(2 * math.pi)])
+    grads = torch.autograd.grad(loss, [e, kp, oscale, noise])
+    ref = float(g[f"{tag}_nll"])
+    assert abs(loss.item() - ref) < 1e-8 * abs(ref)
+    for a, b in zip(grads, g[f"{tag}_nll_grads"]):
+        assert abs(a.item() - b) < 1e-6 * max(1.0, abs(b))
+
+
+def test_spmm_autograd_rhs_and_values_vs_oracle():
+    import manifold_gp_b200 as mgp
+    x = oracle.datasets.torus(4000, seed=3)
+    oidx, oval = oracle.knn_graph(x, 10)
+    n = x.shape[0]
+    for normalization in NORMALIZATIONS:
+        eo = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+        ko = torch.tensor(0.8, dtype=torch.float64, requires_grad=True)
+        vo = torch.randn(n, 3, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(n, 3, dtype=torch.float64)
+        olap = oracle.LaplacianOracle(oval.double(), oidx, n, eo, normalization, True)
+        lo = (w * oracle.precision_matmul(olap, 2, ko, vo)).sum()
+        go = torch.autograd.grad(lo, [eo, ko, vo])
+        e = torch.tensor([[0.3]], dtype=torch.float64, device=DEV, requires_grad=True)
+        kp = torch.tensor([[0.8]], dtype=torch.float64, device=DEV, requires_grad=True)
+        v = vo.detach().to(DEV).requires_grad_(True)
+        lap = mgp.GraphLaplacianOperator(oval.double().to(DEV), oidx.to(DEV), n, e, normalization)
+        prec = mgp.PrecisionMaternOperator(lap, 2, kp)
+        l = (w.to(DEV) * prec.matmul(v)).sum()
+        gg = torch.autograd.grad(l, [e, kp, v])
+        assert abs(l.item() - lo.item()) < 1e-9 * abs(lo.item())
+        assert abs(gg[0].item() - go[0].item()) < 1e-7 * max(1.0, abs(go[0].item()))
+        assert abs(gg[1].item() - go[1].item()) < 1e-7 * max(1.0, abs(go[1].item()))
+        assert rel_err(gg[2], go[2]) < 1e-9
+
+
+@pytest.mark.parametrize("normalization", NORMALIZATIONS)
+def test_out_of_sample_vs_reference_dense(golden_k10, normalization):
+    """test_outofsample (test/_test_functions.py:134-164)."""
+    g = golden_k10
+    tag = gtag(0.5, 1.3, 2, normalization, True)
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 1e-5)):
+        lap, _, _, _ = _ops(g, 0.5, 1.3, 2, normalization, True, dtype)
+        U = torch.from_numpy(g[f"{tag}_evecs"]).to(dtype).to(DEV)
+        ev = torch.from_numpy(g["oos_edge_value"]).to(dtype).to(DEV)
+        ei = torch.from_numpy(g["oos_edge_index"]).long().to(DEV)
+        ext = lap.out_of_sample(U, ev, ei)
+        assert rel_err(ext, g[f"{tag}_ext_evecs"][:, :6]) < tol
+
+
+@pytest.mark.parametrize("normalization", NORMALIZATIONS)
+def test_schur_vs_reference_dense(golden_k10, normalization):
+    import manifold_gp_b200 as mgp
+    g = golden_k10
+    tag = gtag(0.5, 1.3, 2, normalization, True)
+    _, prec, _, _ = _ops(g, 0.5, 1.3, 2, normalization, True, torch.float64)
+    mask = torch.from_numpy(g["mask"]).to(DEV)
+    V = torch.from_numpy(g["V"]).to(DEV)
+    sch = mgp.SchurComplementOperator(prec, mask)
+    assert sch.shape == (200, 200)
+    with mgp.settings.max_cholesky_size(2000):          # inner solve by dense Cholesky
+        assert rel_err(sch.matmul(V[mask]), g[f"{tag}_PschurV"]) < 1e-9
+    with mgp.settings.max_cholesky_size(0), mgp.settings.cg_tolerance(1e-6), mgp.settings.max_cg_iterations(2000):
+        assert rel_err(sch.matmul(V[mask]), g[f"{tag}_PschurV"]) < 1e-4   # inner solve by CUDA CG
