@@ -128,7 +128,7 @@ def test_nll_gradients_through_cg_slq(golden_k10, dumbbell):
     y = dumbbell["train_y"].double().to(DEV)
     torch.manual_seed(0)
     with mgp.settings.max_cholesky_size(0), mgp.settings.cg_tolerance(1e-5), mgp.settings.max_cg_iterations(2000), \
-            mgp.settings.num_trace_samples(200), mgp.settings.max_lanczos_quadrature_iterations(60):
+            mgp.settings.num_trace_samples(120), mgp.settings.max_lanczos_quadrature_iterations(60):
         lap = mgp.GraphLaplacianOperator(val, idx, n, e, "symmetric")
         prec = mgp.PrecisionMaternOperator(lap, 2, kp)
         op = mgp.NoiseWrapperOperator(mgp.ScaleWrapperOperator(prec, oscale, inverse_scale=True), noise)
