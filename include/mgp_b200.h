@@ -132,6 +132,25 @@ int mgp_lap_spmm_f64(const int32_t* rowptr, const int32_t* col, const double* a,
                      const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols,
                      const double* dot_with, double* dot_out, void* dot_ws, void* stream);
 
+/* Same product, v2 "tile-compacted" kernel: rows are processed in tiles of `tile_rows` (= 128) consecutive rows whose
+ * distinct X rows (own rows + a halo list) are staged in shared memory once per tile; per nonzero the kernel streams a
+ * 16-bit tile-local column index (lcol: own rows 0..tile_rows-1, halo rows tile_rows + position in the tile's halo list)
+ * and the value with 128-bit loads.  Built for graphs whose rows were reordered along a space-filling curve
+ * (manifold_gp_b200/graph.py); lmax = max over tiles of tile_rows + halo length, nzmax = max nonzeros of a tile.
+ * `a` and `lcol` must be readable 8 entries past nnz.  xmap / ymap (int32[n], optional) give the caller's row of
+ * structure row i for X (and dot_with) / Y, so vectors in the caller's order need no separate permutation pass.
+ * Returns MGP_EUNSUPPORTED if a tile does not fit in shared memory (use mgp_lap_spmm). */
+int mgp_lap_spmm_tiled_f32(const int32_t* rowptr, const uint16_t* lcol, const float* a, const float* diag,
+                           const int32_t* halo_ptr, const int32_t* halo_col, int32_t tile_rows, int32_t lmax, int32_t nzmax,
+                           const float* shift, const float* pre, const float* post, const int32_t* xmap,
+                           const int32_t* ymap, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n,
+                           int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws, void* stream);
+int mgp_lap_spmm_tiled_f64(const int32_t* rowptr, const uint16_t* lcol, const double* a, const double* diag,
+                           const int32_t* halo_ptr, const int32_t* halo_col, int32_t tile_rows, int32_t lmax, int32_t nzmax,
+                           const double* shift, const double* pre, const double* post, const int32_t* xmap,
+                           const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
+                           int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws, void* stream);
+
 /* ----------------------------------------------------------------------------------------------------------
  * Backward of the SpMM w.r.t. the matrix entries (what autograd through torch_sparse.spmm computes for `value`,
  * graph_laplacian_operator.py:117-119, reached via linear_operator's _bilinear_derivative):

@@ -45,6 +45,8 @@ _SIG = {
     "mgp_lap_spmm_dot_ws_bytes": (c_size_t, [c_int64, c_int32]),
     "mgp_lap_spmm_f32": (c_int32, [P, P, P, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_spmm_f64": (c_int32, [P, P, P, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_lap_spmm_tiled_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_lap_spmm_tiled_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_sddmm_f32": (c_int32, [P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P]),
     "mgp_lap_sddmm_f64": (c_int32, [P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P]),
     "mgp_cg_state_elems": (c_size_t, [c_int32]),
@@ -121,6 +123,14 @@ def call(name: str, *args) -> None:
     rc = getattr(_dll, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+
+
+MGP_EUNSUPPORTED = -4
+
+
+def call_rc(name: str, *args) -> int:
+    """Like ``call`` but returns the status code instead of raising (for calls with a defined alternative kernel)."""
+    return int(getattr(_dll, name)(*args))
 
 
 def query(name: str, *args) -> int:

@@ -52,9 +52,9 @@ def lap_values_autograd(st, d2csr, eps, self_loops):
 
 class _LapSpmmFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, diag, x, shift, pre, post, st):
-        y = graph.lap_spmm(st, a, diag, x, shift=shift, pre=pre, post=post)
-        ctx.st = st
+    def forward(ctx, a, diag, x, shift, pre, post, st, x_external, y_external):
+        y = graph.lap_spmm(st, a, diag, x, shift=shift, pre=pre, post=post, x_external=x_external, y_external=y_external)
+        ctx.st, ctx.xe, ctx.ye = st, x_external, y_external
         ctx.save_for_backward(a, diag, x, shift, pre, post, y if (post is not None and post.requires_grad) else None)
         return y
 
@@ -65,26 +65,32 @@ class _LapSpmmFn(torch.autograd.Function):
         gy = gy.contiguous()
         need = ctx.needs_input_grad
         g_a = g_diag = g_x = g_shift = g_pre = g_post = None
+        # internal-order copies for the pieces that index per-node arrays
+        gy_i = st.to_internal(gy) if ctx.ye else gy
+        x_i = st.to_internal(x) if ctx.xe else x
         if need[2] or need[4]:
-            # dL/dZ with Z = pre .* X:  M (post .* gy)
-            dz = graph.lap_spmm(st, a, diag, gy, shift=shift, pre=post, post=None)
+            # dL/dZ with Z = pre .* X:  M (post .* gy)   (M symmetric); result in X's row order
+            dz = graph.lap_spmm(st, a, diag, gy, shift=shift, pre=post, post=None, x_external=ctx.ye, y_external=False)
+            if need[4] and pre is not None:
+                g_pre = (dz * x_i).sum(1)
             if need[2]:
                 g_x = dz if pre is None else dz * pre.view(-1, 1)
-            if need[4] and pre is not None:
-                g_pre = (dz * x).sum(1)
+                if ctx.xe:
+                    g_x = st.to_external(g_x)
         if need[0] or need[1] or need[3]:
-            g_a, g_diag = graph.lap_sddmm(st, gy, x, pre=pre, post=post)
+            g_a, g_diag = graph.lap_sddmm(st, gy_i, x_i, pre=pre, post=post)
             if need[3] and shift is not None:
                 g_shift = g_diag.sum().reshape(shift.shape)
         if need[5] and post is not None:
-            g_post = (gy * y).sum(1) / post
-        return g_a, g_diag, g_x, g_shift, g_pre, g_post, None
+            y_i = st.to_internal(y) if ctx.ye else y
+            g_post = (gy_i * y_i).sum(1) / post
+        return g_a, g_diag, g_x, g_shift, g_pre, g_post, None, None, None
 
 
-def lap_spmm_apply(st, a, diag, x, shift, pre, post):
+def lap_spmm_apply(st, a, diag, x, shift, pre, post, x_external=False, y_external=False):
     """Differentiable ``Y = post .* ((diag + shift) .* (pre .* X) - A (pre .* X))`` (plain kernel call when no
-    input requires grad)."""
+    input requires grad).  ``x_external`` / ``y_external``: X / Y in the caller's row order (see graph.lap_spmm)."""
     tensors = (a, diag, x, shift, pre, post)
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        return _LapSpmmFn.apply(a, diag, x, shift, pre, post, st)
-    return graph.lap_spmm(st, a, diag, x, shift=shift, pre=pre, post=post)
+        return _LapSpmmFn.apply(a, diag, x, shift, pre, post, st, x_external, y_external)
+    return graph.lap_spmm(st, a, diag, x, shift=shift, pre=pre, post=post, x_external=x_external, y_external=y_external)

@@ -14,49 +14,9 @@
 // that own VEC consecutive right-hand-side columns each (128-bit gathers of X rows when VEC > 1).  Persistent
 // grid-stride over row blocks so the dot epilogue needs only gridDim.x partials.
 #include "common.cuh"
+#include "spmm_common.cuh"
 
 namespace mgp {
-
-template <typename T, int VEC>
-struct Vec;
-template <typename T>
-struct Vec<T, 1> {
-  T v[1];
-};
-template <>
-struct alignas(16) Vec<float, 4> {
-  float v[4];
-};
-template <>
-struct alignas(16) Vec<double, 2> {
-  double v[2];
-};
-
-template <typename T, int VEC>
-__device__ __forceinline__ Vec<T, VEC> ldg_vec(const T* p) {
-  Vec<T, VEC> r;
-  if constexpr (VEC == 1) {
-    r.v[0] = __ldg(p);
-  } else if constexpr (sizeof(T) == 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-  } else {
-    const double2 t = __ldg(reinterpret_cast<const double2*>(p));
-    r.v[0] = t.x; r.v[1] = t.y;
-  }
-  return r;
-}
-
-template <typename T, int VEC>
-__device__ __forceinline__ void st_vec(T* p, const Vec<T, VEC>& r) {
-  if constexpr (VEC == 1) {
-    *p = r.v[0];
-  } else if constexpr (sizeof(T) == 4) {
-    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-  } else {
-    *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
-  }
-}
 
 template <typename T>
 struct SpmmArgs {

@@ -19,15 +19,65 @@ def _device_scalar(v, dtype, device) -> torch.Tensor:
     return torch.tensor([float(v)], dtype=dtype, device=device)
 
 
-class GraphStructure:
-    """rowptr[n+1], col[nnz], eid[nnz] (int32) with nnz = 2M; column indices ascending inside a row."""
+def _spread21(v: torch.Tensor) -> torch.Tensor:
+    """Spread the low 21 bits of an int64 tensor so that two zero bits separate consecutive bits (3-D Morton)."""
+    v = (v | (v << 32)) & 0x1F00000000FFFF
+    v = (v | (v << 16)) & 0x1F0000FF0000FF
+    v = (v | (v << 8)) & 0x100F00F00F00F00F
+    v = (v | (v << 4)) & 0x10C30C30C30C30C3
+    v = (v | (v << 2)) & 0x1249249249249249
+    return v
 
-    def __init__(self, idx: torch.Tensor, n: int):
+
+def morton_permutation(x: torch.Tensor) -> torch.Tensor:
+    """Space-filling-curve order of the points (new position -> old index).  Legal because every operator on the path
+    is permutation-equivariant; it makes the SpMM's gathers of X rows cache-local (neighbours in space become
+    neighbours in memory) and is what keeps a row-partitioned halo small.  For d > 3 the curve runs over the three
+    leading principal directions.  Setup only (torch ops): once per graph, hyper-parameter independent."""
+    xs = x.detach().to(torch.float32)
+    if xs.shape[1] > 3:
+        xc = xs - xs.mean(0, keepdim=True)
+        _, _, v = torch.pca_lowrank(xc, q=3, center=False)
+        xs = xc @ v[:, :3]
+    d = xs.shape[1]
+    lo, hi = xs.amin(0), xs.amax(0)
+    scale = (2 ** 21 - 1) / (hi - lo).clamp_min(1e-30)
+    q = ((xs - lo) * scale).to(torch.int64).clamp_(0, 2 ** 21 - 1)
+    key = torch.zeros(xs.shape[0], dtype=torch.int64, device=xs.device)
+    for j in range(d):
+        key |= _spread21(q[:, j]) << j
+    return torch.argsort(key, stable=True)
+
+
+_PERM_ATTR = "_mgp_b200_perm"
+
+
+def attach_permutation(idx: torch.Tensor, perm: torch.Tensor) -> None:
+    """Remember a locality-improving row order on the edge-index tensor (picked up by ``structure_for``)."""
+    try:
+        setattr(idx, _PERM_ATTR, perm)
+    except Exception:  # pragma: no cover
+        pass
+
+
+class GraphStructure:
+    """rowptr[n+1], col[nnz], eid[nnz] (int32) with nnz = 2M; column indices ascending inside a row.
+
+    If ``perm`` (new position -> old index) is given, rows AND columns live in the permuted numbering: vectors must
+    be permuted (``x[perm]``) before and un-permuted (``y[inv]``) after a product; the solvers do this once per solve."""
+
+    def __init__(self, idx: torch.Tensor, n: int, perm: torch.Tensor = None):
         if not idx.is_cuda:
             raise RuntimeError("GraphStructure: edge index must be a CUDA tensor (no CPU fallback exists)")
         if idx.dim() != 2 or idx.shape[0] != 2:
             raise ValueError("edge index must be [2, M]")
         idx = idx.to(torch.int64)
+        self.perm = self.inv = None
+        if perm is not None:
+            self.perm = perm.to(device=idx.device, dtype=torch.int64).contiguous()
+            self.inv = torch.empty_like(self.perm)
+            self.inv[self.perm] = torch.arange(self.perm.numel(), device=idx.device)
+            idx = self.inv[idx]
         if idx.stride(1) != 1:
             idx = idx.contiguous()
         self.n = int(n)
@@ -45,6 +95,64 @@ class GraphStructure:
         self._d2 = {}
         self._dot_ws = None
         self._upper_pos = None
+        self.perm32 = None if self.perm is None else self.perm.to(torch.int32).contiguous()
+        self.tiles = None
+        self._tiles_tried = False
+
+    # -- tile-compacted structure for the v2 SpMM kernel (csrc/lap_spmm_tiled.cu) ----------------------------------------
+    TILE_ROWS = 128
+    TILED_SMEM_LIMIT = 200 * 1024
+
+    def build_tiles(self):
+        """Per tile of TILE_ROWS consecutive rows: the sorted list of distinct out-of-tile columns (halo) and a 16-bit
+        tile-local column index per nonzero.  Setup only (torch sort/unique), once per graph."""
+        if self._tiles_tried:
+            return self.tiles
+        self._tiles_tried = True
+        R, n, dev = self.TILE_ROWS, self.n, self.device
+        ntiles = (n + R - 1) // R
+        rowlen = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), rowlen)
+        tile = rows // R
+        col = self.col.to(torch.int64)
+        lo = tile * R
+        own = (col >= lo) & (col < lo + R)
+        lcol = torch.where(own, col - lo, torch.zeros_like(col))
+        out = ~own
+        key = (tile[out] << 32) | col[out]
+        ukey, inverse = torch.unique(key, sorted=True, return_inverse=True)
+        bounds = torch.arange(ntiles + 1, device=dev, dtype=torch.int64) << 32
+        halo_ptr = torch.searchsorted(ukey, bounds)
+        lcol[out] = R + inverse - halo_ptr[tile[out]]
+        hlen = halo_ptr[1:] - halo_ptr[:-1]
+        tstart = self.rowptr[torch.arange(0, n, R, device=dev)].to(torch.int64)
+        tend = torch.cat([tstart[1:], self.rowptr[-1:].to(torch.int64)])
+        lmax = int(R + (hlen.max() if hlen.numel() else 0))
+        nzmax = int((tend - tstart).max())
+        if lmax > 65535:
+            return None
+        lcol16 = torch.zeros(self.nnz + 8, dtype=torch.int16, device=dev)
+        lcol16[:self.nnz] = lcol.to(torch.int32).to(torch.int16)          # two's-complement wrap == uint16 bit pattern
+        self.tiles = dict(lcol=lcol16, halo_ptr=halo_ptr.to(torch.int32).contiguous(),
+                          halo_col=torch.cat([(ukey & 0xFFFFFFFF).to(torch.int32),
+                                              torch.zeros(1, dtype=torch.int32, device=dev)]).contiguous(),
+                          lmax=lmax, nzmax=nzmax, rows=R, halo_total=int(ukey.numel()))
+        return self.tiles
+
+    def tiled_ok(self, dtype, cw: int) -> bool:
+        """Does the widest pass for ``cw`` columns of ``dtype`` fit the shared-memory budget of the tiled kernel?"""
+        t = self.build_tiles()
+        if t is None:
+            return False
+        w = 4 if dtype == torch.float32 else 8
+        cwp = 1
+        while cwp < min(cw, 16):
+            cwp *= 2
+        if cw > 16:
+            cwp = 32 if (cw % (4 if w == 4 else 2)) else 16
+        lmax = (t["lmax"] + 3) & ~3
+        nzcap = (t["nzmax"] + 15) & ~7
+        return lmax * cwp * w + nzcap * (w + 2) + (t["rows"] + 1) * 4 + 16 <= self.TILED_SMEM_LIMIT
 
     # -- cached helpers -------------------------------------------------------------------------------------------
     def d2csr(self, val: torch.Tensor) -> torch.Tensor:
@@ -66,17 +174,20 @@ class GraphStructure:
         return self._dot_ws
 
     def upper_pos(self) -> torch.Tensor:
-        """Position in the CSR arrays of the (row<col) copy of every undirected edge e -- maps per-entry arrays back
-        to the reference's per-edge arrays (laplacian_triu etc.).  For a diagonal COO entry either copy is returned."""
+        """Position in the CSR arrays of one directed copy of every undirected edge e -- maps per-entry arrays back to
+        the reference's per-edge arrays (laplacian_triu etc.; the entries are symmetric so either copy serves)."""
         if self._upper_pos is None:
-            rows = torch.repeat_interleave(torch.arange(self.n, device=self.device, dtype=torch.int64),
-                                           (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64))
-            upper = rows <= self.col.to(torch.int64)
-            pos = torch.nonzero(upper).squeeze(1)
             out = torch.empty(self.m, dtype=torch.int64, device=self.device)
-            out[self.eid[pos].to(torch.int64)] = pos
+            out[self.eid.to(torch.int64)] = torch.arange(self.nnz, device=self.device)
             self._upper_pos = out
         return self._upper_pos
+
+    # vectors between the caller's order and the structure's (permuted) order
+    def to_internal(self, v: torch.Tensor) -> torch.Tensor:
+        return v if self.perm is None else v.index_select(0, self.perm)
+
+    def to_external(self, v: torch.Tensor) -> torch.Tensor:
+        return v if self.inv is None else v.index_select(0, self.inv)
 
 
 _STRUCT_ATTR = "_mgp_b200_structure"
@@ -86,7 +197,7 @@ def structure_for(idx: torch.Tensor, n: int) -> GraphStructure:
     """Build (once) and cache the GraphStructure on the edge-index tensor object."""
     st = getattr(idx, _STRUCT_ATTR, None)
     if st is None or st.n != int(n) or st.m != int(idx.shape[1]) or st.device != idx.device:
-        st = GraphStructure(idx, n)
+        st = GraphStructure(idx, n, perm=getattr(idx, _PERM_ATTR, None))
         try:
             setattr(idx, _STRUCT_ATTR, st)
         except Exception:  # pragma: no cover - tensors normally accept attributes
@@ -103,15 +214,22 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
     deg_un = torch.empty(st.n, dtype=dt, device=dev)
     deg = torch.empty(st.n, dtype=dt, device=dev)
     diag = torch.empty(st.n, dtype=dt, device=dev)
-    a = torch.empty(st.nnz, dtype=dt, device=dev)
+    a = torch.zeros(st.nnz + 8, dtype=dt, device=dev)[:st.nnz]   # 8 entries of slack: the tiled kernel streams 128-bit chunks
     _lib.call("mgp_lap_values_" + _lib.suffix(dt), ptr(st.rowptr), ptr(st.col), ptr(d2csr), c_int64(st.n), ptr(eps_t),
               c_int32(1 if self_loops else 0), ptr(deg_un), ptr(deg), ptr(diag), ptr(a), stream())
     return deg_un, deg, diag, a
 
 
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
-def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None):
-    """Y = post .* ((diag + shift) .* (pre .* X) - A (pre .* X)).  ``x``: [n, C] CUDA tensor with unit column stride."""
+SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled"  (tests force each; "auto" prefers the tiled kernel when it fits)
+
+
+def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
+             x_external=False, y_external=False):
+    """Y = post .* ((diag + shift) .* (pre .* X) - A (pre .* X)).  ``x``: [n, C] CUDA tensor with unit column stride.
+
+    ``a, diag, pre, post`` are in the structure's row order.  ``x_external`` / ``y_external``: X (and ``dot_with``) / Y are
+    in the caller's row order (only matters when the structure is internally permuted)."""
     if x.dim() != 2 or x.shape[0] != st.n:
         raise ValueError(f"lap_spmm: expected rhs of shape [{st.n}, C], got {tuple(x.shape)}")
     if x.stride(1) != 1:
@@ -120,14 +238,44 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
     if a.dtype != dt or diag.dtype != dt:
         raise TypeError(f"lap_spmm: value dtype {a.dtype} does not match rhs dtype {dt}")
     c = int(x.shape[1])
-    if out is None:
-        out = torch.empty((st.n, c), dtype=dt, device=x.device)
+    if st.perm is None:
+        x_external = y_external = False
     shift_t = None if shift is None else _device_scalar(shift, dt, x.device)
     ws = st.dot_ws() if dot_out is not None else None
-    _lib.call("mgp_lap_spmm_" + _lib.suffix(dt), ptr(st.rowptr), ptr(st.col), ptr(a), ptr(diag), ptr(shift_t),
-              ptr(pre), ptr(post), ptr(x), c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n),
+    sfx = _lib.suffix(dt)
+    slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
+    use_tiled = SPMM_KERNEL != "csr" and slack_ok and st.tiled_ok(dt, c)
+    if SPMM_KERNEL == "tiled" and not use_tiled:
+        raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
+    if use_tiled:
+        t = st.tiles
+        if out is None:
+            out = torch.empty((st.n, c), dtype=dt, device=x.device)
+        rc = _lib.call_rc("mgp_lap_spmm_tiled_" + sfx, ptr(st.rowptr), ptr(t["lcol"]), ptr(a), ptr(diag), ptr(t["halo_ptr"]),
+                          ptr(t["halo_col"]), c_int32(t["rows"]), c_int32(t["lmax"]), c_int32(t["nzmax"]), ptr(shift_t),
+                          ptr(pre), ptr(post), ptr(st.perm32 if x_external else None),
+                          ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
+                          c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())
+        if rc == 0:
+            return out
+        if rc != _lib.MGP_EUNSUPPORTED or SPMM_KERNEL == "tiled":
+            raise RuntimeError(f"mgp_lap_spmm_tiled_{sfx} failed ({rc}): {_lib.last_error()}")
+        # a pass wider than estimated (unaligned leading dimension): the CSR kernel handles it
+    # v1 CSR kernel works in the structure's order only
+    if x_external:
+        x = x.index_select(0, st.perm)
+        if dot_with is not None:
+            dot_with = dot_with.index_select(0, st.perm)
+    y = torch.empty((st.n, c), dtype=dt, device=x.device) if (out is None or y_external) else out
+    _lib.call("mgp_lap_spmm_" + sfx, ptr(st.rowptr), ptr(st.col), ptr(a), ptr(diag), ptr(shift_t),
+              ptr(pre), ptr(post), ptr(x), c_int64(x.stride(0)), ptr(y), c_int64(y.stride(0)), c_int64(st.n),
               c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())
-    return out
+    if y_external:
+        if out is None:
+            return y.index_select(0, st.inv)
+        out.copy_(y.index_select(0, st.inv))
+        return out
+    return y
 
 
 def lap_sddmm(st: GraphStructure, gy, x, pre=None, post=None):

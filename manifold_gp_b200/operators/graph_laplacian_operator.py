@@ -86,9 +86,13 @@ class GraphLaplacianOperator(LinearOperator):
     def adjacency_unnorm_mat(self) -> Tensor:
         return self._memo("W", lambda: self.x.div(-4 * self.graphbandwidth.square()).exp().squeeze())
 
+    def _ext(self, name, i):
+        """i-th value array in the caller's node order (the structure may be internally permuted)."""
+        return self._memo(name, lambda: self.structure.to_external(self._values()[i]))
+
     @property
     def degree_unnorm_mat(self) -> Tensor:
-        return self._values()[0]
+        return self._ext("Dt_ext", 0)
 
     @property
     def adjacency_mat(self) -> Tensor:
@@ -97,11 +101,11 @@ class GraphLaplacianOperator(LinearOperator):
 
     @property
     def degree_mat(self) -> Tensor:
-        return self._values()[1]
+        return self._ext("D_ext", 1)
 
     @property
     def laplacian_diag(self) -> Tensor:
-        return self._values()[2]
+        return self._ext("diag_ext", 2)
 
     def _diagonal(self) -> Tensor:
         return self.laplacian_diag
@@ -110,13 +114,14 @@ class GraphLaplacianOperator(LinearOperator):
     def laplacian_triu(self) -> Tensor:
         return self._memo("triu", lambda: self._values()[3][self.structure.upper_pos()])
 
+    # internal (structure-order) D^{+-1/2}
     @property
     def _sqrt_degree(self):
-        return self._memo("sqrtD", lambda: self.degree_mat.sqrt())
+        return self._memo("sqrtD", lambda: self._values()[1].sqrt())
 
     @property
     def _rsqrt_degree(self):
-        return self._memo("rsqrtD", lambda: self.degree_mat.pow(-0.5))
+        return self._memo("rsqrtD", lambda: self._values()[1].pow(-0.5))
 
     # ---- matvec (:108-124) -------------------------------------------------------------------------------------------
     def _pre_post(self):
@@ -134,12 +139,16 @@ class GraphLaplacianOperator(LinearOperator):
             vec = vec.to(a.dtype)
         pre, post = self._pre_post()
         from ..autograd import lap_spmm_apply
-        out = lap_spmm_apply(self.structure, a, diag, vec.contiguous(), None, pre, post)
+        st = self.structure
+        out = lap_spmm_apply(st, a, diag, vec.contiguous(), None, pre, post, x_external=True, y_external=True)
         return out.squeeze(-1) if squeeze else out
 
     # ---- fused path used by the CUDA CG / Lanczos drivers (no autograd, caller-owned buffers) ---------------------
     def _native(self) -> bool:
         return True
+
+    def _mgp_structure(self):
+        return self.structure
 
     def _mgp_matvec(self, x: Tensor, out: Tensor, tmp=None, dot_with=None, dot_out=None, ncols=None):
         if ncols is not None:
@@ -188,7 +197,7 @@ class GraphLaplacianOperator(LinearOperator):
         if not (x.is_cuda and edge_value.is_cuda and edge_idx.is_cuda):
             raise RuntimeError("out_of_sample: tensors must be CUDA tensors (no CPU fallback exists)")
         dt = x.dtype
-        deg_un, deg, _, _ = self._values()
+        deg_un, deg = self.degree_unnorm_mat, self.degree_mat
         phi = x if x.stride(1) == 1 else x.contiguous()
         ev = edge_value.to(dt).contiguous()
         ei = edge_idx.to(torch.int64).contiguous()

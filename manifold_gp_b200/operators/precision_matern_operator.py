@@ -51,11 +51,13 @@ class PrecisionMaternOperator(LinearOperator):
         shift = self._shift().to(a.dtype)
         rw = lap.normalization == "randomwalk"
         sq = lap._sqrt_degree if rw else None
+        st = lap.structure
         out = vec.contiguous()
         for s in range(self.nu):
             pre = sq if (rw and s == 0) else None
             post = sq if (rw and s == self.nu - 1) else None
-            out = lap_spmm_apply(lap.structure, a, diag, out, shift, pre, post)
+            # the caller's row order is translated on the fly by the first / last launch (no permutation passes)
+            out = lap_spmm_apply(st, a, diag, out, shift, pre, post, x_external=(s == 0), y_external=(s == self.nu - 1))
         return out.squeeze(-1) if squeeze else out
 
     # ---- fused path used by the CUDA CG / Lanczos drivers (no autograd, caller-owned buffers) -------------------------
@@ -81,6 +83,9 @@ class PrecisionMaternOperator(LinearOperator):
                                dot_with=dot_with if last else None, dot_out=dot_out if last else None)
                 src = dst
         return out
+
+    def _mgp_structure(self):
+        return self.laplacian.structure
 
     def _size(self):
         return self.laplacian._size()

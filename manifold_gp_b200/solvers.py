@@ -50,7 +50,9 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
     ws = torch.zeros(_lib.query("mgp_cg_ws_bytes", c_int64(n), c_int32(c)), dtype=torch.uint8, device=dev)
     max_hist = max(1, min(max_iter, n_tridiag_iter)) if n_tridiag else 1
     hist = torch.zeros((max_hist, 2, c), dtype=dt, device=dev) if n_tridiag else None
-    rhs_c = rhs if rhs.stride(1) == 1 else rhs.contiguous()
+    st = op._mgp_structure() if fused else None     # fused path runs in the structure's (permuted) row order
+    rhs_c = st.to_internal(rhs) if st is not None else rhs
+    rhs_c = rhs_c if rhs_c.stride(1) == 1 else rhs_c.contiguous()
 
     _lib.call("mgp_cg_init_" + sfx, ptr(rhs_c), c_int64(rhs_c.stride(0)), ptr(x), ptr(r), ptr(p), c_int64(ld), c_int64(n),
               c_int32(c), fl(tolerance), fl(eps), fl(stop_updating_after), c_int32(max_iter),
@@ -82,6 +84,8 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
             break
     out = torch.empty((n, c), dtype=dt, device=dev)
     _lib.call("mgp_cg_finalize_" + sfx, ptr(x), c_int64(ld), ptr(out), c_int64(c), c_int64(n), c_int32(c), ptr(state), stream())
+    if st is not None:
+        out = st.to_external(out)
     tail = state[scal:scal + 3].tolist()
     info = CGInfo(iterations=int(tail[K_ITER]), mean_residual=float(tail[K_MEAN]), converged=(done == 1.0),
                   residual_norm=state[S_RESID * c:(S_RESID + 1) * c].clone())
@@ -194,6 +198,9 @@ def lanczos_tridiag(op, max_iter, init_vec=None, tol=1e-5, generator=None):
     betas = torch.zeros(num_iter, dtype=dt, device=dev)
     fused = hasattr(op, "_mgp_matvec") and getattr(op, "_native", lambda: True)()
     tmp = torch.empty((n, 1), dtype=dt, device=dev) if fused else None
+    st = op._mgp_structure() if fused else None     # fused path: Lanczos vectors live in the structure's row order
+    if st is not None:
+        r = st.to_internal(r).contiguous()
 
     _lib.call("mgp_lanczos_reorth_" + sfx, None, c_int64(n), c_int32(0), ptr(r), c_int64(n), ptr(c), ptr(nrm2), ptr(ws), stream())
     _lib.call("mgp_lanczos_normalize_" + sfx, ptr(r), c_int64(n), ptr(nrm2), ptr(q[0]), None, stream())
@@ -227,7 +234,10 @@ def lanczos_tridiag(op, max_iter, init_vec=None, tol=1e-5, generator=None):
     if steps > 1:
         off = betas[:steps - 1]
         t = t + torch.diag(off, 1) + torch.diag(off, -1)
-    return q[:steps], t
+    qm = q[:steps]
+    if st is not None and st.inv is not None:
+        qm = qm.index_select(1, st.inv)
+    return qm, t
 
 
 def lanczos_tridiag_to_diag(t_mat):

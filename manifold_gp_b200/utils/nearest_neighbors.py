@@ -65,7 +65,11 @@ class NearestNeighbors():
         _lib.call("mgp_graph_symmetrize_f32", ptr(v32), ptr(idx), c_int64(n), c_int32(k), c_int32(drop), ptr(eidx),
                   ptr(ev), c_int64(cap), ptr(m_out), ptr(ws), c_size_t(ws.numel()), stream())
         m = int(m_out.item())          # one host read per graph build (output size is data dependent)
-        return eidx[:, :m].contiguous(), ev[:m].to(self.x.dtype).contiguous()
+        out_idx = eidx[:, :m].contiguous()
+        # hint for the operators: a space-filling-curve order of the points (the reference's outputs are unchanged)
+        from .. import graph
+        graph.attach_permutation(out_idx, graph.morton_permutation(self.x))
+        return out_idx, ev[:m].to(self.x.dtype).contiguous()
 
     @property
     def min_ivf(self):

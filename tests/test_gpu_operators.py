@@ -236,3 +236,35 @@ def test_schur_vs_reference_dense(golden_k10, normalization):
         assert rel_err(sch.matmul(V[mask]), g[f"{tag}_PschurV"]) < 1e-9
     with mgp.settings.max_cholesky_size(0), mgp.settings.cg_tolerance(1e-6), mgp.settings.max_cg_iterations(2000):
         assert rel_err(sch.matmul(V[mask]), g[f"{tag}_PschurV"]) < 1e-4   # inner solve by CUDA CG
+
+
+def test_morton_permutation_equivalence():
+    """The internal space-filling-curve reordering (attached by NearestNeighbors.graph) must not change any result:
+    same operator built with and without the hint, Laplacian + precision + CG + per-node arrays."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph, solvers
+    x = oracle.datasets.torus(40000, seed=8).to(DEV)
+    idx, val = mgp.NearestNeighbors(x).graph(12)
+    assert getattr(idx, graph._PERM_ATTR, None) is not None
+    perm = getattr(idx, graph._PERM_ATTR)
+    assert torch.equal(torch.sort(perm).values, torch.arange(x.shape[0], device=DEV))
+    idx_plain = idx.clone()                       # no hint -> identity order
+    n = x.shape[0]
+    for normalization in NORMALIZATIONS:
+        eps = torch.tensor([[0.1]], device=DEV)
+        kap = torch.tensor([[0.6]], device=DEV)
+        la = mgp.GraphLaplacianOperator(val, idx, n, eps, normalization)
+        lb = mgp.GraphLaplacianOperator(val, idx_plain, n, eps, normalization)
+        assert la.structure.perm is not None and lb.structure.perm is None
+        V = torch.randn(n, 8, device=DEV)
+        assert rel_err(la.matmul(V), lb.matmul(V)) < 1e-6
+        assert rel_err(la.T.matmul(V), lb.T.matmul(V)) < 1e-6
+        assert rel_err(la.degree_mat, lb.degree_mat) < 1e-6
+        assert rel_err(la.laplacian_diag, lb.laplacian_diag) < 1e-6
+        assert rel_err(la.laplacian_triu, lb.laplacian_triu) < 1e-6
+        pa = mgp.PrecisionMaternOperator(la, 2, kap)
+        pb = mgp.PrecisionMaternOperator(lb, 2, kap)
+        assert rel_err(pa.matmul(V), pb.matmul(V)) < 1e-6
+        xa = solvers.linear_cg(pa, V, tolerance=1e-4, max_iter=500)
+        xb = solvers.linear_cg(pb, V, tolerance=1e-4, max_iter=500)
+        assert rel_err(xa, xb) < 1e-3
