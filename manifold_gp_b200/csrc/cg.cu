@@ -316,6 +316,140 @@ cg_update_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, 
   }
 }
 
+// ---- vectorised fast paths (ld a power of two <= 128: every thread keeps the same columns across the grid stride) -----
+template <typename T> struct V16;
+template <> struct V16<float> { using type = float4; static constexpr int N = 4; };
+template <> struct V16<double> { using type = double2; static constexpr int N = 2; };
+
+template <typename T>
+__device__ __forceinline__ void v16_unpack(const typename V16<T>::type& v, T* o);
+template <> __device__ __forceinline__ void v16_unpack<float>(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+template <> __device__ __forceinline__ void v16_unpack<double>(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+template <typename T>
+__device__ __forceinline__ typename V16<T>::type v16_pack(const T* o);
+template <> __device__ __forceinline__ float4 v16_pack<float>(const float* o) { return make_float4(o[0], o[1], o[2], o[3]); }
+template <> __device__ __forceinline__ double2 v16_pack<double>(const double* o) { return make_double2(o[0], o[1]); }
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_update_vec_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ v, int ld,
+                     int64_t n, int ncols, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws) {
+  using V = typename V16<T>::type;
+  constexpr int N = V16<T>::N;
+  T* k = state + S_NARR * ncols;
+  if (k[K_DONE] != T(0)) return;
+  CgWs<T> w = cg_ws<T>(ws);
+  __shared__ T al[kCgMaxCols];
+  __shared__ T sm[kCgBlock][N];
+  const int tid = threadIdx.x;
+  const T eps = k[K_EPS];
+  for (int c = tid; c < ld; c += kCgBlock) al[c] = c < ncols ? cg_alpha_of<T>(state, ncols, c, eps) : T(0);
+  __syncthreads();
+  const int c0 = (tid * N) % ld;          // this thread's columns: constant because (blockDim * N) % ld == 0
+  T a[N], acc[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) { a[u] = al[c0 + u]; acc[u] = T(0); }
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* x4 = reinterpret_cast<V*>(x);
+  V* r4 = reinterpret_cast<V*>(r);
+  const V* p4 = reinterpret_cast<const V*>(p);
+  const V* v4 = reinterpret_cast<const V*>(v);
+#pragma unroll 2
+  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + tid; e < total; e += stride) {
+    T pv[N], vv[N], xv[N], rv[N];
+    v16_unpack<T>(p4[e], pv); v16_unpack<T>(v4[e], vv); v16_unpack<T>(x4[e], xv); v16_unpack<T>(r4[e], rv);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      rv[u] = fma(-a[u], vv[u], rv[u]);
+      xv[u] = fma(a[u], pv[u], xv[u]);
+      acc[u] = fma(rv[u], rv[u], acc[u]);
+    }
+    r4[e] = v16_pack<T>(rv);
+    x4[e] = v16_pack<T>(xv);
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) sm[tid][u] = acc[u];
+  __syncthreads();
+  if (tid < ncols) {
+    // threads t with (t*N) % ld == (tid / N) * N hold column tid in slot tid % N; fixed summation order
+    const int groups = ld / N;
+    T s = T(0);
+    for (int t = tid / N; t < kCgBlock; t += groups) s += sm[t][tid % N];
+    w.partials[(int64_t)blockIdx.x * ncols + tid] = s;
+  }
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    __shared__ T msum[kCgBlock];
+    const int it = (int)k[K_ITER];
+    const T stop = k[K_STOP];
+    T local = T(0);
+    for (int c = tid; c < ncols; c += kCgBlock) {
+      const T aa = cg_alpha_of<T>(state, ncols, c, eps);
+      const T rz_old = state[S_RZ * ncols + c];
+      const T rz_new = tot[c];
+      const bool bz = rz_old < eps;
+      const T beta = bz ? T(0) : rz_new / rz_old;
+      T rn = dev_sqrt<T>(rz_new);
+      if (state[S_RHSZERO * ncols + c] != T(0)) rn = T(0);
+      state[S_ALPHA * ncols + c] = aa;
+      state[S_BETA * ncols + c] = beta;
+      state[S_RZ * ncols + c] = rz_new;
+      state[S_RESID * ncols + c] = rn;
+      state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
+      if (hist && it < max_hist) {
+        hist[((int64_t)it * 2 + 0) * ncols + c] = aa;
+        hist[((int64_t)it * 2 + 1) * ncols + c] = beta;
+      }
+      local += rn;
+    }
+    msum[tid] = local;
+    __syncthreads();
+    if (tid == 0) {
+      T s = T(0);
+      for (int i = 0; i < kCgBlock; ++i) s += msum[i];
+      const T mean = s / T(ncols);
+      k[K_MEAN] = mean;
+      k[K_ITER] = T(it + 1);
+      const bool tri_pending = (k[K_NTRIMIN] > T(0)) && (T(it) < k[K_NTRIMIN]);
+      if (T(it) >= k[K_MINITER] && mean < k[K_TOL] && !tri_pending) k[K_DONE] = T(1);
+      else if (T(it + 1) >= k[K_MAXITER]) k[K_DONE] = T(2);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_pupdate_vec_kernel(T* __restrict__ p, const T* __restrict__ r, int ld, int64_t n, int ncols, const T* __restrict__ state) {
+  using V = typename V16<T>::type;
+  constexpr int N = V16<T>::N;
+  const int c0 = (threadIdx.x * N) % ld;
+  T b[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) b[u] = (c0 + u) < ncols ? state[S_BETA * ncols + c0 + u] : T(0);
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* p4 = reinterpret_cast<V*>(p);
+  const V* r4 = reinterpret_cast<const V*>(r);
+#pragma unroll 4
+  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + threadIdx.x; e < total; e += stride) {
+    T pv[N], rv[N];
+    v16_unpack<T>(p4[e], pv); v16_unpack<T>(r4[e], rv);
+#pragma unroll
+    for (int u = 0; u < N; ++u) pv[u] = fma(b[u], pv[u], rv[u]);
+    p4[e] = v16_pack<T>(pv);
+  }
+}
+
+template <typename T>
+static inline bool cg_vec_ok(int64_t ld, const void* a, const void* b, const void* c, const void* d) {
+  constexpr int N = V16<T>::N;
+  if (ld < N || ld > kCgMaxCols || (ld & (ld - 1)) != 0) return false;
+  auto al = [](const void* q) { return q == nullptr || (((uintptr_t)q) % 16) == 0; };
+  return al(a) && al(b) && al(c) && al(d);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kCgBlock)
 cg_pupdate_kernel(T* __restrict__ p, const T* __restrict__ r, int64_t ld, int64_t n, int ncols,
@@ -381,6 +515,15 @@ static int cg_update(T* x, T* r, const T* p, const T* v, int64_t ld, int64_t n, 
   int rc = cg_check<T>(n, ncols, ld);
   if (rc) return rc;
   MGP_CHECK_ARG(x && r && p && v && state && ws, "cg_update: null pointer");
+  if (cg_vec_ok<T>(ld, x, r, p, v)) {
+    int64_t g = ceil_div(n * ld / V16<T>::N, (int64_t)kCgBlock * 4);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    cg_update_vec_kernel<T><<<(unsigned)g, kCgBlock, 0, st>>>(x, r, p, v, (int)ld, n, ncols, state, hist, max_hist, ws);
+    MGP_LAUNCH_CHECK();
+    return MGP_OK;
+  }
   const int CP = col_lanes(ncols);
   cg_update_kernel<T><<<cg_grid(n, kCgBlock / CP), kCgBlock, 0, st>>>(x, r, p, v, ld, n, ncols, CP, state, hist, max_hist, ws);
   MGP_LAUNCH_CHECK();
@@ -429,6 +572,12 @@ int mgp_cg_update_f64(double* x, double* r, const double* p, const double* v, in
 int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream) {
   MGP_CHECK_ARG(p && r && state && n > 0 && ncols > 0 && ld >= ncols, "cg_pupdate: bad arguments");
   const int64_t total = n * ld;
+  if (cg_vec_ok<float>(ld, p, r, nullptr, nullptr)) {
+    int64_t gv = ceil_div(total / V16<float>::N, (int64_t)kCgBlock * 4); if (gv > kNumSMs * 8) gv = kNumSMs * 8; if (gv < 1) gv = 1;
+    cg_pupdate_vec_kernel<float><<<(unsigned)gv, kCgBlock, 0, (cudaStream_t)stream>>>(p, r, (int)ld, n, ncols, state);
+    MGP_LAUNCH_CHECK();
+    return MGP_OK;
+  }
   int64_t g = ceil_div(total, kCgBlock); if (g > kNumSMs * 16) g = kNumSMs * 16;
   cg_pupdate_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(p, r, ld, n, ncols, state);
   MGP_LAUNCH_CHECK();
@@ -437,6 +586,12 @@ int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t 
 int mgp_cg_pupdate_f64(double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream) {
   MGP_CHECK_ARG(p && r && state && n > 0 && ncols > 0 && ld >= ncols, "cg_pupdate: bad arguments");
   const int64_t total = n * ld;
+  if (cg_vec_ok<double>(ld, p, r, nullptr, nullptr)) {
+    int64_t gv = ceil_div(total / V16<double>::N, (int64_t)kCgBlock * 4); if (gv > kNumSMs * 8) gv = kNumSMs * 8; if (gv < 1) gv = 1;
+    cg_pupdate_vec_kernel<double><<<(unsigned)gv, kCgBlock, 0, (cudaStream_t)stream>>>(p, r, (int)ld, n, ncols, state);
+    MGP_LAUNCH_CHECK();
+    return MGP_OK;
+  }
   int64_t g = ceil_div(total, kCgBlock); if (g > kNumSMs * 16) g = kNumSMs * 16;
   cg_pupdate_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(p, r, ld, n, ncols, state);
   MGP_LAUNCH_CHECK();
