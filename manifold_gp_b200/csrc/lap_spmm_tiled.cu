@@ -17,6 +17,8 @@
 // Structure (built once per graph by the host, see graph.py::TileStructure): rowptr (CSR of the reordered graph),
 // lcol[nnz] uint16 (local index: own rows 0..R-1, halo rows R..R+H-1), halo_ptr[T+1], halo_col[sum H].
 // `xmap` / `ymap` (optional) translate the structure's row ids to the caller's row order for X / Y.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "spmm_common.cuh"
 
@@ -50,6 +52,8 @@ struct TiledArgs {
   T* dot_out;
   T* partials;
   unsigned int* counter;
+  int dot_is_x;  // dot_with == x and no pre scaling: the row is already in shared memory
+  int debug;     // development only: 1 = skip phase B, 3 = phase A only once per CTA
 };
 
 template <typename T, int VEC, int LPN, int LPR, int R>
@@ -63,7 +67,9 @@ lap_spmm_tiled_kernel(const TiledArgs<T> g) {
   T* xs = reinterpret_cast<T*>(smem_raw);                                   // [lmax][CW]
   T* vs = xs + (size_t)g.lmax * CW;                                         // [nzcap]
   unsigned short* cs = reinterpret_cast<unsigned short*>(vs + g.nzcap);     // [nzcap]
-  int* rp = reinterpret_cast<int*>(cs + g.nzcap);                           // [R + 1]
+  int* rp = reinterpret_cast<int*>(cs + g.nzcap);                           // [R + 4]
+  T* dgs = reinterpret_cast<T*>(rp + R + 4);                                // [R]  diag + shift of the tile's rows
+  T* pss = dgs + R;                                                         // [R]  post scaling of the tile's rows
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -89,6 +95,7 @@ lap_spmm_tiled_kernel(const TiledArgs<T> g) {
     const int nh = __ldg(g.halo_ptr + tile + 1) - h0;
 
     // ---- phase A: stage indices + values (128-bit streaming loads), row offsets, and the X tile ------------------
+    if (g.debug != 3 || tile == (int)blockIdx.x) {   // debug 3: phase A only for the first tile (stale but valid indices)
     for (int i = tid * 8; i < cnt; i += kTiledBlock * 8) {
       const int4 c8 = ld_stream_v4(reinterpret_cast<const int4*>(g.lcol + base + i));
       *reinterpret_cast<int4*>(cs + i) = c8;
@@ -106,37 +113,76 @@ lap_spmm_tiled_kernel(const TiledArgs<T> g) {
       }
     }
     for (int i = tid; i <= nrows; i += kTiledBlock) rp[i] = __ldg(g.rowptr + row0 + i) - base;
-    for (int it = tid; it < (R + nh) * LPN; it += kTiledBlock) {
-      const int lr = it / LPN;
-      const int c = it % LPN;
-      int id;
-      if (lr < R) {
-        if (lr >= nrows) continue;
-        id = (int)row0 + lr;
-      } else {
-        id = __ldg(g.halo_col + h0 + lr - R);
-      }
-      if (VEC == 1 && c >= g.cw) continue;
-      const int64_t src = g.xmap ? (int64_t)__ldg(g.xmap + id) : (int64_t)id;
-      Vec<T, VEC> v = ldg_vec<T, VEC>(g.x + src * g.ldx + g.c0 + c * VEC);
-      if (g.pre) {
-        const T pj = __ldg(g.pre + id);
+    for (int i = tid; i < nrows; i += kTiledBlock) {
+      dgs[i] = __ldg(g.diag + row0 + i) + shift;
+      pss[i] = g.post ? __ldg(g.post + row0 + i) : T(1);
+    }
+    // X tile: ids first, then all gathers of the batch in flight together, then the shared-memory stores
+    {
+      constexpr int UNR = 4;
+      const int nitems = (R + nh) * LPN;
+      for (int it0 = tid; it0 < nitems; it0 += kTiledBlock * UNR) {
+        int id[UNR], lr[UNR], cc[UNR];
+        bool ok[UNR];
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) v.v[u] *= pj;
+        for (int u = 0; u < UNR; ++u) {
+          const int it = it0 + u * kTiledBlock;
+          ok[u] = it < nitems;
+          lr[u] = it / LPN;
+          cc[u] = it % LPN;
+          id[u] = 0;
+          if (ok[u]) {
+            if (lr[u] < R) {
+              ok[u] = lr[u] < nrows;
+              id[u] = (int)row0 + lr[u];
+            } else {
+              id[u] = __ldg(g.halo_col + h0 + lr[u] - R);
+            }
+            if (VEC == 1 && cc[u] >= g.cw) ok[u] = false;
+          }
+        }
+        int64_t src[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) src[u] = (ok[u] && g.xmap) ? (int64_t)__ldg(g.xmap + id[u]) : (int64_t)id[u];
+        Vec<T, VEC> v[UNR];
+        T pj[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (ok[u]) {
+            v[u] = ldg_vec<T, VEC>(g.x + src[u] * g.ldx + g.c0 + cc[u] * VEC);
+            pj[u] = g.pre ? __ldg(g.pre + id[u]) : T(1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (ok[u]) {
+            if (g.pre) {
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) v[u].v[e] *= pj[u];
+            }
+            if constexpr (VEC == 1) xs[lr[u] * CW + cc[u]] = v[u].v[0];
+            else *reinterpret_cast<Vec<T, VEC>*>(xs + lr[u] * CW + cc[u] * VEC) = v[u];
+          }
+        }
       }
-      if constexpr (VEC == 1) {
-        xs[lr * CW + c] = v.v[0];
-      } else {
-        *reinterpret_cast<Vec<T, VEC>*>(xs + lr * CW + c * VEC) = v;
-      }
+    }
     }
     __syncthreads();
 
     // ---- phase B + C ---------------------------------------------------------------------------------------------
-    for (int rb = 0; rb < R; rb += ROWS_PER_ROUND) {       // block-uniform trip count (shuffles below need full warps)
+    for (int rb = 0; rb < (g.debug == 1 ? 0 : R); rb += ROWS_PER_ROUND) {       // block-uniform trip count (shuffles below need full warps)
       const int r = rb + tid / LPR;
+      const bool writer = (slot == 0) && (r < nrows) && col_ok;
       int q0 = 0, q1 = 0;
       if (r < nrows) { q0 = rp[r]; q1 = rp[r + 1]; }
+      const int64_t row = row0 + r;
+      Vec<T, VEC> dw;
+      if (g.dot_out && !g.dot_is_x && writer) {              // issue early: the latency hides behind the row loop
+        const int64_t drow = g.xmap ? (int64_t)__ldg(g.xmap + row) : row;
+        dw = ldg_vec<T, VEC>(g.dot_with + drow * g.ldx + cbase);
+      }
+      int64_t yrow = row;
+      if (g.ymap && writer) yrow = (int64_t)__ldg(g.ymap + row);
       T acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = T(0);
@@ -154,23 +200,22 @@ lap_spmm_tiled_kernel(const TiledArgs<T> g) {
           }
         }
       }
+      if constexpr (SPR > 1) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = subwarp_sum(acc[v], LPN, LPR);
-      if (slot == 0 && r < nrows && col_ok) {
-        const int64_t row = row0 + r;
+        for (int v = 0; v < VEC; ++v) acc[v] = subwarp_sum(acc[v], LPN, LPR);
+      }
+      if (writer) {
         Vec<T, VEC> xi;
         if constexpr (VEC == 1) xi.v[0] = xs[r * CW + cl];
         else xi = *reinterpret_cast<const Vec<T, VEC>*>(xs + r * CW + cl * VEC);   // already scaled by pre
-        const T d = __ldg(g.diag + row) + shift;
-        const T po = g.post ? __ldg(g.post + row) : T(1);
+        const T d = dgs[r];
+        const T po = pss[r];
         Vec<T, VEC> out;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) out.v[v] = po * (d * xi.v[v] - acc[v]);
-        const int64_t yrow = g.ymap ? (int64_t)__ldg(g.ymap + row) : row;
         st_vec<T, VEC>(g.y + yrow * g.ldy + cbase, out);
         if (g.dot_out) {
-          const int64_t drow = g.xmap ? (int64_t)__ldg(g.xmap + row) : row;
-          const Vec<T, VEC> dw = ldg_vec<T, VEC>(g.dot_with + drow * g.ldx + cbase);
+          if (g.dot_is_x) dw = xi;
 #pragma unroll
           for (int v = 0; v < VEC; ++v) dsum[v] = fma(dw.v[v], out.v[v], dsum[v]);
         }
@@ -184,7 +229,7 @@ lap_spmm_tiled_kernel(const TiledArgs<T> g) {
 
 template <typename T, int VEC, int LPN, int LPR, int R>
 static size_t tiled_smem_bytes(int lmax, int nzcap) {
-  return (size_t)lmax * LPN * VEC * sizeof(T) + (size_t)nzcap * (sizeof(T) + 2) + (size_t)(R + 1) * 4 + 16;
+  return (size_t)lmax * LPN * VEC * sizeof(T) + (size_t)nzcap * (sizeof(T) + 2) + (size_t)(R + 4) * 4 + (size_t)2 * R * sizeof(T) + 16;
 }
 
 constexpr size_t kTiledSmemLimit = 200 * 1024;
@@ -213,6 +258,13 @@ static int launch_tiled(const TiledArgs<T>& g, cudaStream_t st) {
   return MGP_OK;
 }
 
+// v3 pipelined pass (lap_spmm_pipe.cu)
+template <typename T>
+int lap_spmm_pipe_pass(const int* rowptr, const unsigned short* lcol, const T* a, const T* diag, const int* halo_ptr,
+                       const int* halo_col, int lmax, int nzcap, const T* shift, const T* post, const int* xmap,
+                       const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int c0, int cw,
+                       const T* dot_with, T* dot_out, T* partials, unsigned int* counter, int dot_is_x, cudaStream_t st);
+
 template <typename T>
 static int lap_spmm_tiled(const int* rowptr, const unsigned short* lcol, const T* a, const T* diag, const int* halo_ptr,
                           const int* halo_col, int tile_rows, int lmax, int nzmax, const T* shift, const T* pre,
@@ -235,16 +287,29 @@ static int lap_spmm_tiled(const int* rowptr, const unsigned short* lcol, const T
   g.dot_with = dot_out ? dot_with : nullptr; g.dot_out = dot_out;
   g.counter = dot_out ? reinterpret_cast<unsigned int*>(dot_ws) : nullptr;
   g.partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
+  g.dot_is_x = (dot_out && dot_with == x && pre == nullptr) ? 1 : 0;
+  { const char* dbg = getenv("MGP_TILED_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
+  bool use_pipe = true;
+  { const char* e = getenv("MGP_SPMM_PIPE"); if (e && e[0] == '0') use_pipe = false; }
   int c0 = 0;
   while (c0 < ncols) {
     const int rem = ncols - c0;
     int rc;
     g.c0 = c0;
+    if (aligned && c0 % VECW == 0 && rem >= VECW && pre == nullptr && use_pipe) {
+      // v3: warp-specialised TMA pipeline (falls through to v2 when two stages do not fit in shared memory)
+      int cw = VECW;
+      while (cw * 2 <= rem && cw * 2 <= 16) cw *= 2;
+      rc = lap_spmm_pipe_pass<T>(rowptr, lcol, a, diag, halo_ptr, halo_col, g.lmax, g.nzcap, shift, post, xmap, ymap, x, ldx,
+                                 y, ldy, n, c0, cw, g.dot_with, dot_out, g.partials, g.counter, g.dot_is_x, st);
+      if (rc == MGP_OK) { c0 += cw; continue; }
+      if (rc != MGP_EUNSUPPORTED) return rc;
+    }
     if (aligned && c0 % VECW == 0 && rem >= VECW) {
       if constexpr (sizeof(T) == 4) {
-        if (rem >= 16) { g.cw = 16; rc = launch_tiled<T, 4, 4, 16, R>(g, st); }
-        else if (rem >= 8) { g.cw = 8; rc = launch_tiled<T, 4, 2, 8, R>(g, st); }
-        else { g.cw = 4; rc = launch_tiled<T, 4, 1, 8, R>(g, st); }
+        if (rem >= 16) { g.cw = 16; rc = launch_tiled<T, 4, 4, 4, R>(g, st); }
+        else if (rem >= 8) { g.cw = 8; rc = launch_tiled<T, 4, 2, 4, R>(g, st); }
+        else { g.cw = 4; rc = launch_tiled<T, 4, 1, 4, R>(g, st); }
       } else {
         if (rem >= 16) { g.cw = 16; rc = launch_tiled<T, 2, 8, 32, R>(g, st); }
         else if (rem >= 8) { g.cw = 8; rc = launch_tiled<T, 2, 4, 16, R>(g, st); }
@@ -254,8 +319,8 @@ static int lap_spmm_tiled(const int* rowptr, const unsigned short* lcol, const T
     } else {
       const int cw = rem > 32 ? 32 : rem;
       g.cw = cw;
-      if (cw == 1) rc = launch_tiled<T, 1, 1, 8, R>(g, st);
-      else if (cw == 2) rc = launch_tiled<T, 1, 2, 8, R>(g, st);
+      if (cw == 1) rc = launch_tiled<T, 1, 1, 4, R>(g, st);
+      else if (cw == 2) rc = launch_tiled<T, 1, 2, 4, R>(g, st);
       else if (cw <= 4) rc = launch_tiled<T, 1, 4, 16, R>(g, st);
       else if (cw <= 8) rc = launch_tiled<T, 1, 8, 32, R>(g, st);
       else if (cw <= 16) rc = launch_tiled<T, 1, 16, 32, R>(g, st);

@@ -74,7 +74,14 @@ class GraphStructure:
         idx = idx.to(torch.int64)
         self.perm = self.inv = None
         if perm is not None:
-            self.perm = perm.to(device=idx.device, dtype=torch.int64).contiguous()
+            perm = perm.to(device=idx.device, dtype=torch.int64)
+            # balance the tiled kernel's sub-warps: inside every tile of TILE_ROWS consecutive rows, order the rows by
+            # their number of nonzeros (descending), so rows processed together have (nearly) equal length
+            deg = torch.bincount(idx.reshape(-1), minlength=int(n))
+            tile_id = torch.arange(perm.numel(), device=idx.device, dtype=torch.int64) // self.TILE_ROWS
+            key = (tile_id << 20) | ((1 << 20) - 1 - deg[perm].clamp_max((1 << 20) - 1))
+            perm = perm[torch.argsort(key, stable=True)]
+            self.perm = perm.contiguous()
             self.inv = torch.empty_like(self.perm)
             self.inv[self.perm] = torch.arange(self.perm.numel(), device=idx.device)
             idx = self.inv[idx]
@@ -98,6 +105,7 @@ class GraphStructure:
         self.perm32 = None if self.perm is None else self.perm.to(torch.int32).contiguous()
         self.tiles = None
         self._tiles_tried = False
+        self.build_tiles()   # now: it may reorder the entries inside rows, which must happen before any value build
 
     # -- tile-compacted structure for the v2 SpMM kernel (csrc/lap_spmm_tiled.cu) ----------------------------------------
     TILE_ROWS = 128
@@ -124,6 +132,17 @@ class GraphStructure:
         bounds = torch.arange(ntiles + 1, device=dev, dtype=torch.int64) << 32
         halo_ptr = torch.searchsorted(ukey, bounds)
         lcol[out] = R + inverse - halo_ptr[tile[out]]
+        # bank-conflict control for 64-byte X rows in shared memory: two nonzeros handled by the same quarter-warp hit
+        # different bank halves iff their local indices have different parity.  Rows in even sub-warp slots list their
+        # even-parity entries first, rows in odd slots their odd-parity entries first (entry order inside a row is free).
+        flip = ((lcol & 1) ^ (rows & 1)).to(torch.int64)
+        order = torch.argsort((rows << 1) | flip, stable=True)
+        if not bool((order[1:] > order[:-1]).all()):
+            self.col = self.col[order].contiguous()
+            self.eid = self.eid[order].contiguous()
+            lcol = lcol[order]
+            self._d2 = {}
+            self._upper_pos = None
         hlen = halo_ptr[1:] - halo_ptr[:-1]
         tstart = self.rowptr[torch.arange(0, n, R, device=dev)].to(torch.int64)
         tend = torch.cat([tstart[1:], self.rowptr[-1:].to(torch.int64)])
@@ -152,7 +171,7 @@ class GraphStructure:
             cwp = 32 if (cw % (4 if w == 4 else 2)) else 16
         lmax = (t["lmax"] + 3) & ~3
         nzcap = (t["nzmax"] + 15) & ~7
-        return lmax * cwp * w + nzcap * (w + 2) + (t["rows"] + 1) * 4 + 16 <= self.TILED_SMEM_LIMIT
+        return lmax * cwp * w + nzcap * (w + 2) + (t["rows"] + 4) * 4 + 2 * t["rows"] * w + 16 <= self.TILED_SMEM_LIMIT
 
     # -- cached helpers -------------------------------------------------------------------------------------------
     def d2csr(self, val: torch.Tensor) -> torch.Tensor:
@@ -244,7 +263,9 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
     ws = st.dot_ws() if dot_out is not None else None
     sfx = _lib.suffix(dt)
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
-    use_tiled = SPMM_KERNEL != "csr" and slack_ok and st.tiled_ok(dt, c)
+    # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
+    # kernel (X served from L1/L2) is faster
+    use_tiled = SPMM_KERNEL != "csr" and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL == "tiled")
     if SPMM_KERNEL == "tiled" and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
