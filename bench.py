@@ -34,7 +34,10 @@ CFG = dict(workload="torus_R3_N1M_k32_nu2_cg16rhs", n=1_000_000, k=32, nu=2, kap
            max_iter=4000, normalization="symmetric", self_loops=True, seed=0, rhs_seed=1)
 # CG iterations the GPU solve of exactly this configuration needs (deterministic; measured on B200, see profiles/).
 # Used only by the CPU arms to scale their bounded sample (a few iterations) to a full solve.
-CG_ITERS_FULL_SOLVE = None
+CG_ITERS_FULL_SOLVE = 1696
+# dram__bytes_read.sum + dram__bytes_write.sum of one lap_spmm_pipe_kernel launch (C=16, cfg-C) from the ncu --set full
+# capture committed as profiles/r01_ncu_spmm_pipe_c16.txt (281.8 MB read + 51.5 MB written)
+NCU_DRAM_BYTES_PER_SPMM16 = 333_309_440
 
 
 def spmm_algorithmic_bytes(n, nnz, c, w=4):
@@ -233,9 +236,9 @@ def run_ours(args):
         "cg_true_relative_residual": true_rel,
         "e2e": {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": Bh.numel() * 4, "d2h_bytes_per_step": Xh.numel() * 4},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "lap_spmm_csr_kernel (C=16 SpMM of the precision operator)",
+        "roofline": {"bound": "hbm", "kernel": "lap_spmm_pipe_kernel<float,4,4,128> (C=16 SpMM step of the Matern precision operator)",
                      "achieved": round(ach16, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach16 / hbm_peak, 4),
-                     "frac_of_nominal_8000": round(ach16 / 8000.0, 4), "traffic": None, "peak_source": peak_src,
+                     "frac_of_nominal_8000": round(ach16 / 8000.0, 4), "traffic": NCU_DRAM_BYTES_PER_SPMM16, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": b16, "us_per_launch": round(spmm16_us, 2),
                      "spmm_share_of_step": round(2 * iters * spmm16_us * 1e-3 / ms_step, 3)},
         "spmv_c1": {"us_per_launch": round(spmv1_us, 2), "achieved_gbs": round(ach1, 1), "frac": round(ach1 / hbm_peak, 4),
