@@ -199,6 +199,27 @@ int mgp_cg_update_f32(float* x, float* r, const float* p, const float* v, int64_
                       float* state, float* hist, int32_t max_hist, void* ws, void* stream);
 int mgp_cg_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
                       double* state, double* hist, int32_t max_hist, void* ws, void* stream);
+/* Multi-GPU split of the two reductions (rows partitioned across ranks): the kernels export their LOCAL column sums to
+ * rbuf[ncols]; the host all-reduces rbuf (NCCL) and mgp_cg_dist_scalars finishes the scalar bookkeeping on every rank
+ * (what = 0: right-hand-side norms, 1: initial residual / state, 2: one iteration's beta, norms, flags, done).
+ * Per iteration: [halo exchange + SpMM chain, last launch with the p^T A p epilogue into state.pAp] -> all-reduce(pAp)
+ * -> mgp_cg_dist_update -> all-reduce(rbuf) -> mgp_cg_dist_scalars(what=2) -> mgp_cg_pupdate. */
+int mgp_cg_dist_norm2_f32(const float* b, int64_t ldb, int64_t n, int32_t ncols, float* state, float* rbuf, void* ws, void* stream);
+int mgp_cg_dist_norm2_f64(const double* b, int64_t ldb, int64_t n, int32_t ncols, double* state, double* rbuf, void* ws, void* stream);
+int mgp_cg_dist_init_f32(const float* b, int64_t ldb, float* x, float* r, float* p, int64_t ld, int64_t n, int32_t ncols,
+                         float* state, float* rbuf, void* ws, void* stream);
+int mgp_cg_dist_init_f64(const double* b, int64_t ldb, double* x, double* r, double* p, int64_t ld, int64_t n, int32_t ncols,
+                         double* state, double* rbuf, void* ws, void* stream);
+int mgp_cg_dist_update_f32(float* x, float* r, const float* p, const float* v, int64_t ld, int64_t n, int32_t ncols,
+                           float* state, float* rbuf, void* ws, void* stream);
+int mgp_cg_dist_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
+                           double* state, double* rbuf, void* ws, void* stream);
+int mgp_cg_dist_scalars_f32(float* state, const float* rbuf, int32_t ncols, int32_t what, float tolerance, float eps,
+                            float stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, float* hist, int32_t max_hist,
+                            void* stream);
+int mgp_cg_dist_scalars_f64(double* state, const double* rbuf, int32_t ncols, int32_t what, double tolerance, double eps,
+                            double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, double* hist, int32_t max_hist,
+                            void* stream);
 /* p = r + beta p */
 int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream);
 int mgp_cg_pupdate_f64(double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream);

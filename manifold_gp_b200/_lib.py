@@ -57,6 +57,14 @@ _SIG = {
     "mgp_cg_alpha_f64": (c_int32, [P, P, c_int64, c_int64, c_int32, c_int32, P, P, P]),
     "mgp_cg_update_f32": (c_int32, [P, P, P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P]),
     "mgp_cg_update_f64": (c_int32, [P, P, P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P]),
+    "mgp_cg_dist_norm2_f32": (c_int32, [P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_cg_dist_norm2_f64": (c_int32, [P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_cg_dist_init_f32": (c_int32, [P, c_int64, P, P, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_cg_dist_init_f64": (c_int32, [P, c_int64, P, P, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_cg_dist_update_f32": (c_int32, [P, P, P, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_cg_dist_update_f64": (c_int32, [P, P, P, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_cg_dist_scalars_f32": (c_int32, [P, P, c_int32, c_int32, c_float, c_float, c_float, c_int32, c_int32, P, c_int32, P]),
+    "mgp_cg_dist_scalars_f64": (c_int32, [P, P, c_int32, c_int32, c_double, c_double, c_double, c_int32, c_int32, P, c_int32, P]),
     "mgp_cg_pupdate_f32": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P]),
     "mgp_cg_pupdate_f64": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P]),
     "mgp_cg_finalize_f32": (c_int32, [P, c_int64, P, c_int64, c_int64, c_int32, P, P]),

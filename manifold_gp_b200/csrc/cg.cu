@@ -93,11 +93,113 @@ __host__ __device__ inline CgWs<T> cg_ws(void* ws) {
   return w;
 }
 
+// ---- scalar bookkeeping shared by the single-GPU kernels (run by the last block) and the multi-GPU split kernels (run
+//      by a one-block kernel after the all-reduce of the column sums).  `tot` is in shared memory, whole block calls. ----
+template <typename T>
+__device__ __forceinline__ void cg_finish_norm(T* state, const T* tot, int ncols, T eps) {
+  for (int c = threadIdx.x; c < ncols; c += kCgBlock) {
+    T nrm = dev_sqrt<T>(tot[c]);
+    const bool zero = nrm < eps;
+    state[S_RHSZERO * ncols + c] = zero ? T(1) : T(0);
+    state[S_RHSNORM * ncols + c] = zero ? T(1) : nrm;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void cg_finish_init(T* state, const T* tot, int ncols, T tol, T eps, T stop, int max_iter,
+                                               int n_tridiag_iter) {
+  __shared__ T msum_i[kCgBlock];
+  const int tid = threadIdx.x;
+  T local = T(0);
+  int all_conv = 1;
+  for (int c = tid; c < ncols; c += kCgBlock) {
+    const T rn = dev_sqrt<T>(tot[c]);
+    state[S_RZ * ncols + c] = tot[c];
+    state[S_RESID * ncols + c] = rn;
+    state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
+    state[S_PAP * ncols + c] = T(0);
+    state[S_ALPHA * ncols + c] = T(0);
+    state[S_BETA * ncols + c] = T(0);
+    local += rn;
+    if (!(rn < stop)) all_conv = 0;
+  }
+  msum_i[tid] = local;
+  const int any_unconv = __syncthreads_or(!all_conv);
+  if (tid == 0) {
+    T s = T(0);
+    for (int i = 0; i < kCgBlock; ++i) s += msum_i[i];
+    T* k = state + S_NARR * ncols;
+    k[K_MEAN] = s / T(ncols);
+    // published: "if has_converged.all() and not n_tridiag: n_iter = 0"
+    k[K_DONE] = (!any_unconv && n_tridiag_iter == 0) ? T(1) : T(0);
+    k[K_ITER] = T(0);
+    k[K_TOL] = tol;
+    k[K_EPS] = eps;
+    k[K_STOP] = stop;
+    k[K_MINITER] = T(min(10, max_iter - 1));
+    k[K_NTRIMIN] = T(n_tridiag_iter > 0 ? min(n_tridiag_iter, max_iter - 1) : 0);
+    k[K_MAXITER] = T(max_iter);
+    if (max_iter <= 0) k[K_DONE] = T(2);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T cg_alpha_of(const T* state, int ncols, int c, T eps);
+
+template <typename T>
+__device__ __forceinline__ void cg_finish_update(T* state, const T* tot, int ncols, T* hist, int max_hist) {
+  __shared__ T msum_u[kCgBlock];
+  const int tid = threadIdx.x;
+  T* k = state + S_NARR * ncols;
+  const T eps = k[K_EPS];
+  const int it = (int)k[K_ITER];
+  const T stop = k[K_STOP];
+  T local = T(0);
+  for (int c = tid; c < ncols; c += kCgBlock) {
+    const T aa = cg_alpha_of<T>(state, ncols, c, eps);
+    const T rz_old = state[S_RZ * ncols + c];
+    const T rz_new = tot[c];
+    const bool bz = rz_old < eps;
+    const T beta = bz ? T(0) : rz_new / rz_old;
+    T rn = dev_sqrt<T>(rz_new);
+    if (state[S_RHSZERO * ncols + c] != T(0)) rn = T(0);
+    state[S_ALPHA * ncols + c] = aa;
+    state[S_BETA * ncols + c] = beta;
+    state[S_RZ * ncols + c] = rz_new;
+    state[S_RESID * ncols + c] = rn;
+    state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
+    if (hist && it < max_hist) {
+      hist[((int64_t)it * 2 + 0) * ncols + c] = aa;
+      hist[((int64_t)it * 2 + 1) * ncols + c] = beta;
+    }
+    local += rn;
+  }
+  msum_u[tid] = local;
+  __syncthreads();
+  if (tid == 0) {
+    T s = T(0);
+    for (int i = 0; i < kCgBlock; ++i) s += msum_u[i];
+    const T mean = s / T(ncols);
+    k[K_MEAN] = mean;
+    k[K_ITER] = T(it + 1);
+    // published stopping rule: k >= min(10, max_iter-1) and mean residual < tol and the tridiagonal has enough rows
+    const bool tri_pending = (k[K_NTRIMIN] > T(0)) && (T(it) < k[K_NTRIMIN]);
+    if (T(it) >= k[K_MINITER] && mean < k[K_TOL] && !tri_pending) k[K_DONE] = T(1);
+    else if (T(it + 1) >= k[K_MAXITER]) k[K_DONE] = T(2);
+  }
+}
+
+// tot (shared) -> rbuf (global): the multi-GPU path all-reduces rbuf before the scalars are finished
+template <typename T>
+__device__ __forceinline__ void cg_export_tot(const T* tot, T* rbuf, int ncols) {
+  for (int c = threadIdx.x; c < ncols; c += kCgBlock) rbuf[c] = tot[c];
+}
+
 // ---- init pass 1: column norms of b ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kCgBlock)
 cg_norm_kernel(const T* __restrict__ b, int64_t ldb, int64_t n, int ncols, int CP, T eps, T* __restrict__ state,
-               void* ws) {
+               void* ws, T* __restrict__ rbuf) {
   CgWs<T> w = cg_ws<T>(ws);
   const int tid = threadIdx.x;
   const int cl = tid % CP, rl = tid / CP, rpb = kCgBlock / CP;
@@ -119,12 +221,8 @@ cg_norm_kernel(const T* __restrict__ b, int64_t ldb, int64_t n, int ncols, int C
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);
-    for (int c = tid; c < ncols; c += kCgBlock) {
-      T nrm = dev_sqrt<T>(tot[c]);
-      const bool zero = nrm < eps;
-      state[S_RHSZERO * ncols + c] = zero ? T(1) : T(0);
-      state[S_RHSNORM * ncols + c] = zero ? T(1) : nrm;
-    }
+    if (rbuf) cg_export_tot<T>(tot, rbuf, ncols);
+    else cg_finish_norm<T>(state, tot, ncols, eps);
   }
 }
 
@@ -133,7 +231,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCgBlock)
 cg_init_kernel(const T* __restrict__ b, int64_t ldb, T* __restrict__ x, T* __restrict__ r, T* __restrict__ p,
                int64_t ld, int64_t n, int ncols, int CP, T tol, T eps, T stop, int max_iter, int n_tridiag_iter,
-               T* __restrict__ state, void* ws) {
+               T* __restrict__ state, void* ws, T* __restrict__ rbuf) {
   CgWs<T> w = cg_ws<T>(ws);
   const int tid = threadIdx.x;
   const int cl = tid % CP, rl = tid / CP, rpb = kCgBlock / CP;
@@ -166,38 +264,8 @@ cg_init_kernel(const T* __restrict__ b, int64_t ldb, T* __restrict__ x, T* __res
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);
-    __shared__ T msum[kCgBlock];
-    T local = T(0);
-    int all_conv = 1;
-    for (int c = tid; c < ncols; c += kCgBlock) {
-      const T rn = dev_sqrt<T>(tot[c]);
-      state[S_RZ * ncols + c] = tot[c];
-      state[S_RESID * ncols + c] = rn;
-      state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
-      state[S_PAP * ncols + c] = T(0);
-      state[S_ALPHA * ncols + c] = T(0);
-      state[S_BETA * ncols + c] = T(0);
-      local += rn;
-      if (!(rn < stop)) all_conv = 0;
-    }
-    msum[tid] = local;
-    const int any_unconv = __syncthreads_or(!all_conv);
-    if (tid == 0) {
-      T s = T(0);
-      for (int i = 0; i < kCgBlock; ++i) s += msum[i];
-      T* k = state + S_NARR * ncols;
-      k[K_MEAN] = s / T(ncols);
-      // published: "if has_converged.all() and not n_tridiag: n_iter = 0"
-      k[K_DONE] = (!any_unconv && n_tridiag_iter == 0) ? T(1) : T(0);
-      k[K_ITER] = T(0);
-      k[K_TOL] = tol;
-      k[K_EPS] = eps;
-      k[K_STOP] = stop;
-      k[K_MINITER] = T(min(10, max_iter - 1));
-      k[K_NTRIMIN] = T(n_tridiag_iter > 0 ? min(n_tridiag_iter, max_iter - 1) : 0);
-      k[K_MAXITER] = T(max_iter);
-      if (max_iter <= 0) k[K_DONE] = T(2);
-    }
+    if (rbuf) cg_export_tot<T>(tot, rbuf, ncols);
+    else cg_finish_init<T>(state, tot, ncols, tol, eps, stop, max_iter, n_tridiag_iter);
   }
 }
 
@@ -244,7 +312,8 @@ __device__ __forceinline__ T cg_alpha_of(const T* state, int ncols, int c, T eps
 template <typename T>
 __global__ void __launch_bounds__(kCgBlock)
 cg_update_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ v, int64_t ld,
-                 int64_t n, int ncols, int CP, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws) {
+                 int64_t n, int ncols, int CP, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws,
+                 T* __restrict__ rbuf) {
   T* k = state + S_NARR * ncols;
   if (k[K_DONE] != T(0)) return;
   CgWs<T> w = cg_ws<T>(ws);
@@ -277,42 +346,8 @@ cg_update_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, 
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);
-    __shared__ T msum[kCgBlock];
-    const int it = (int)k[K_ITER];
-    const T stop = k[K_STOP];
-    T local = T(0);
-    for (int c = tid; c < ncols; c += kCgBlock) {
-      const T a = cg_alpha_of<T>(state, ncols, c, eps);
-      const T rz_old = state[S_RZ * ncols + c];
-      const T rz_new = tot[c];
-      const bool bz = rz_old < eps;
-      const T beta = bz ? T(0) : rz_new / rz_old;
-      T rn = dev_sqrt<T>(rz_new);
-      if (state[S_RHSZERO * ncols + c] != T(0)) rn = T(0);
-      state[S_ALPHA * ncols + c] = a;
-      state[S_BETA * ncols + c] = beta;
-      state[S_RZ * ncols + c] = rz_new;
-      state[S_RESID * ncols + c] = rn;
-      state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
-      if (hist && it < max_hist) {
-        hist[((int64_t)it * 2 + 0) * ncols + c] = a;
-        hist[((int64_t)it * 2 + 1) * ncols + c] = beta;
-      }
-      local += rn;
-    }
-    msum[tid] = local;
-    __syncthreads();
-    if (tid == 0) {
-      T s = T(0);
-      for (int i = 0; i < kCgBlock; ++i) s += msum[i];
-      const T mean = s / T(ncols);
-      k[K_MEAN] = mean;
-      k[K_ITER] = T(it + 1);
-      // published stopping rule: k >= min(10, max_iter-1) and mean residual < tol and the tridiagonal has enough rows
-      const bool tri_pending = (k[K_NTRIMIN] > T(0)) && (T(it) < k[K_NTRIMIN]);
-      if (T(it) >= k[K_MINITER] && mean < k[K_TOL] && !tri_pending) k[K_DONE] = T(1);
-      else if (T(it + 1) >= k[K_MAXITER]) k[K_DONE] = T(2);
-    }
+    if (rbuf) cg_export_tot<T>(tot, rbuf, ncols);
+    else cg_finish_update<T>(state, tot, ncols, hist, max_hist);
   }
 }
 
@@ -333,7 +368,8 @@ template <> __device__ __forceinline__ double2 v16_pack<double>(const double* o)
 template <typename T>
 __global__ void __launch_bounds__(kCgBlock)
 cg_update_vec_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ v, int ld,
-                     int64_t n, int ncols, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws) {
+                     int64_t n, int ncols, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws,
+                     T* __restrict__ rbuf) {
   using V = typename V16<T>::type;
   constexpr int N = V16<T>::N;
   T* k = state + S_NARR * ncols;
@@ -381,42 +417,23 @@ cg_update_vec_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);
-    __shared__ T msum[kCgBlock];
-    const int it = (int)k[K_ITER];
-    const T stop = k[K_STOP];
-    T local = T(0);
-    for (int c = tid; c < ncols; c += kCgBlock) {
-      const T aa = cg_alpha_of<T>(state, ncols, c, eps);
-      const T rz_old = state[S_RZ * ncols + c];
-      const T rz_new = tot[c];
-      const bool bz = rz_old < eps;
-      const T beta = bz ? T(0) : rz_new / rz_old;
-      T rn = dev_sqrt<T>(rz_new);
-      if (state[S_RHSZERO * ncols + c] != T(0)) rn = T(0);
-      state[S_ALPHA * ncols + c] = aa;
-      state[S_BETA * ncols + c] = beta;
-      state[S_RZ * ncols + c] = rz_new;
-      state[S_RESID * ncols + c] = rn;
-      state[S_CONV * ncols + c] = (rn < stop) ? T(1) : T(0);
-      if (hist && it < max_hist) {
-        hist[((int64_t)it * 2 + 0) * ncols + c] = aa;
-        hist[((int64_t)it * 2 + 1) * ncols + c] = beta;
-      }
-      local += rn;
-    }
-    msum[tid] = local;
-    __syncthreads();
-    if (tid == 0) {
-      T s = T(0);
-      for (int i = 0; i < kCgBlock; ++i) s += msum[i];
-      const T mean = s / T(ncols);
-      k[K_MEAN] = mean;
-      k[K_ITER] = T(it + 1);
-      const bool tri_pending = (k[K_NTRIMIN] > T(0)) && (T(it) < k[K_NTRIMIN]);
-      if (T(it) >= k[K_MINITER] && mean < k[K_TOL] && !tri_pending) k[K_DONE] = T(1);
-      else if (T(it + 1) >= k[K_MAXITER]) k[K_DONE] = T(2);
-    }
+    if (rbuf) cg_export_tot<T>(tot, rbuf, ncols);
+    else cg_finish_update<T>(state, tot, ncols, hist, max_hist);
   }
+}
+
+// ---- one-block scalar kernels of the multi-GPU path: finish the bookkeeping from all-reduced column sums ----------------
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_scalars_kernel(T* __restrict__ state, const T* __restrict__ rbuf, int ncols, int what, T tol, T eps, T stop, int max_iter,
+                  int n_tridiag_iter, T* __restrict__ hist, int max_hist) {
+  __shared__ T tot[kCgMaxCols];
+  if (what == 2 && state[S_NARR * ncols + K_DONE] != T(0)) return;
+  for (int c = threadIdx.x; c < ncols; c += kCgBlock) tot[c] = rbuf[c];
+  __syncthreads();
+  if (what == 0) cg_finish_norm<T>(state, tot, ncols, eps);
+  else if (what == 1) cg_finish_init<T>(state, tot, ncols, tol, eps, stop, max_iter, n_tridiag_iter);
+  else cg_finish_update<T>(state, tot, ncols, hist, max_hist);
 }
 
 template <typename T>
@@ -483,16 +500,21 @@ static int cg_check(int64_t n, int ncols, int64_t ld) {
 
 template <typename T>
 static int cg_init(const T* b, int64_t ldb, T* x, T* r, T* p, int64_t ld, int64_t n, int ncols, T tol, T eps, T stop,
-                   int max_iter, int n_tridiag_iter, T* state, void* ws, cudaStream_t st) {
+                   int max_iter, int n_tridiag_iter, T* state, void* ws, cudaStream_t st, int phase = 0, T* rbuf = nullptr) {
   int rc = cg_check<T>(n, ncols, ld);
   if (rc) return rc;
   MGP_CHECK_ARG(b && x && r && p && state && ws && ldb >= ncols, "cg_init: bad arguments");
   const int CP = col_lanes(ncols);
   const int grid = cg_grid(n, kCgBlock / CP);
-  cg_norm_kernel<T><<<grid, kCgBlock, 0, st>>>(b, ldb, n, ncols, CP, eps, state, ws);
-  MGP_LAUNCH_CHECK();
-  cg_init_kernel<T><<<grid, kCgBlock, 0, st>>>(b, ldb, x, r, p, ld, n, ncols, CP, tol, eps, stop, max_iter, n_tridiag_iter, state, ws);
-  MGP_LAUNCH_CHECK();
+  // phase 0: both passes (single GPU); phase 1 / 2: one pass each, column sums exported to rbuf (multi-GPU)
+  if (phase == 0 || phase == 1) {
+    cg_norm_kernel<T><<<grid, kCgBlock, 0, st>>>(b, ldb, n, ncols, CP, eps, state, ws, rbuf);
+    MGP_LAUNCH_CHECK();
+  }
+  if (phase == 0 || phase == 2) {
+    cg_init_kernel<T><<<grid, kCgBlock, 0, st>>>(b, ldb, x, r, p, ld, n, ncols, CP, tol, eps, stop, max_iter, n_tridiag_iter, state, ws, rbuf);
+    MGP_LAUNCH_CHECK();
+  }
   return MGP_OK;
 }
 
@@ -511,7 +533,7 @@ static int cg_alpha(const T* p, const T* v, int64_t ld, int64_t n, int ncols, in
 
 template <typename T>
 static int cg_update(T* x, T* r, const T* p, const T* v, int64_t ld, int64_t n, int ncols, T* state, T* hist,
-                     int max_hist, void* ws, cudaStream_t st) {
+                     int max_hist, void* ws, cudaStream_t st, T* rbuf = nullptr) {
   int rc = cg_check<T>(n, ncols, ld);
   if (rc) return rc;
   MGP_CHECK_ARG(x && r && p && v && state && ws, "cg_update: null pointer");
@@ -520,12 +542,12 @@ static int cg_update(T* x, T* r, const T* p, const T* v, int64_t ld, int64_t n, 
     const int64_t cap = (int64_t)kNumSMs * 8;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    cg_update_vec_kernel<T><<<(unsigned)g, kCgBlock, 0, st>>>(x, r, p, v, (int)ld, n, ncols, state, hist, max_hist, ws);
+    cg_update_vec_kernel<T><<<(unsigned)g, kCgBlock, 0, st>>>(x, r, p, v, (int)ld, n, ncols, state, hist, max_hist, ws, rbuf);
     MGP_LAUNCH_CHECK();
     return MGP_OK;
   }
   const int CP = col_lanes(ncols);
-  cg_update_kernel<T><<<cg_grid(n, kCgBlock / CP), kCgBlock, 0, st>>>(x, r, p, v, ld, n, ncols, CP, state, hist, max_hist, ws);
+  cg_update_kernel<T><<<cg_grid(n, kCgBlock / CP), kCgBlock, 0, st>>>(x, r, p, v, ld, n, ncols, CP, state, hist, max_hist, ws, rbuf);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }
@@ -568,6 +590,51 @@ int mgp_cg_update_f32(float* x, float* r, const float* p, const float* v, int64_
 int mgp_cg_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
                       double* state, double* hist, int32_t max_hist, void* ws, void* stream) {
   return cg_update<double>(x, r, p, v, ld, n, ncols, state, hist, max_hist, ws, (cudaStream_t)stream);
+}
+// ---- multi-GPU split entry points (column sums exported to rbuf, finished by mgp_cg_dist_scalars after the all-reduce) ----
+int mgp_cg_dist_norm2_f32(const float* b, int64_t ldb, int64_t n, int32_t ncols, float* state, float* rbuf, void* ws, void* stream) {
+  MGP_CHECK_ARG(rbuf != nullptr, "cg_dist_norm2: rbuf is null");
+  return cg_init<float>(b, ldb, (float*)b, (float*)b, (float*)b, ncols > ldb ? ldb : ldb, n, ncols, 0.f, 0.f, 0.f, 1, 0, state, ws, (cudaStream_t)stream, 1, rbuf);
+}
+int mgp_cg_dist_norm2_f64(const double* b, int64_t ldb, int64_t n, int32_t ncols, double* state, double* rbuf, void* ws, void* stream) {
+  MGP_CHECK_ARG(rbuf != nullptr, "cg_dist_norm2: rbuf is null");
+  return cg_init<double>(b, ldb, (double*)b, (double*)b, (double*)b, ldb, n, ncols, 0., 0., 0., 1, 0, state, ws, (cudaStream_t)stream, 1, rbuf);
+}
+int mgp_cg_dist_init_f32(const float* b, int64_t ldb, float* x, float* r, float* p, int64_t ld, int64_t n, int32_t ncols,
+                         float* state, float* rbuf, void* ws, void* stream) {
+  MGP_CHECK_ARG(rbuf != nullptr, "cg_dist_init: rbuf is null");
+  return cg_init<float>(b, ldb, x, r, p, ld, n, ncols, 0.f, 0.f, 0.f, 1, 0, state, ws, (cudaStream_t)stream, 2, rbuf);
+}
+int mgp_cg_dist_init_f64(const double* b, int64_t ldb, double* x, double* r, double* p, int64_t ld, int64_t n, int32_t ncols,
+                         double* state, double* rbuf, void* ws, void* stream) {
+  MGP_CHECK_ARG(rbuf != nullptr, "cg_dist_init: rbuf is null");
+  return cg_init<double>(b, ldb, x, r, p, ld, n, ncols, 0., 0., 0., 1, 0, state, ws, (cudaStream_t)stream, 2, rbuf);
+}
+int mgp_cg_dist_update_f32(float* x, float* r, const float* p, const float* v, int64_t ld, int64_t n, int32_t ncols,
+                           float* state, float* rbuf, void* ws, void* stream) {
+  MGP_CHECK_ARG(rbuf != nullptr, "cg_dist_update: rbuf is null");
+  return cg_update<float>(x, r, p, v, ld, n, ncols, state, nullptr, 0, ws, (cudaStream_t)stream, rbuf);
+}
+int mgp_cg_dist_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
+                           double* state, double* rbuf, void* ws, void* stream) {
+  MGP_CHECK_ARG(rbuf != nullptr, "cg_dist_update: rbuf is null");
+  return cg_update<double>(x, r, p, v, ld, n, ncols, state, nullptr, 0, ws, (cudaStream_t)stream, rbuf);
+}
+int mgp_cg_dist_scalars_f32(float* state, const float* rbuf, int32_t ncols, int32_t what, float tolerance, float eps,
+                            float stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, float* hist, int32_t max_hist,
+                            void* stream) {
+  MGP_CHECK_ARG(state && rbuf && ncols > 0 && ncols <= kCgMaxCols && what >= 0 && what <= 2, "cg_dist_scalars: bad arguments");
+  cg_scalars_kernel<float><<<1, kCgBlock, 0, (cudaStream_t)stream>>>(state, rbuf, ncols, what, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter, hist, max_hist);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_dist_scalars_f64(double* state, const double* rbuf, int32_t ncols, int32_t what, double tolerance, double eps,
+                            double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, double* hist, int32_t max_hist,
+                            void* stream) {
+  MGP_CHECK_ARG(state && rbuf && ncols > 0 && ncols <= kCgMaxCols && what >= 0 && what <= 2, "cg_dist_scalars: bad arguments");
+  cg_scalars_kernel<double><<<1, kCgBlock, 0, (cudaStream_t)stream>>>(state, rbuf, ncols, what, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter, hist, max_hist);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
 }
 int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream) {
   MGP_CHECK_ARG(p && r && state && n > 0 && ncols > 0 && ld >= ncols, "cg_pupdate: bad arguments");

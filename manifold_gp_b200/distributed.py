@@ -1,0 +1,320 @@
+"""Row-partitioned multi-GPU execution of the Matern-precision CG solve.
+
+The reference has no distributed code; this is new design.  One process per GPU (torchrun), ``torch.distributed`` (NCCL
+over NVLink/NVSwitch; gloo in the CPU tests) for the plumbing:
+
+* rows are partitioned into contiguous, 128-aligned blocks of the space-filling-curve order, so a rank's neighbours are
+  almost all its own rows and the halo is the thin boundary of a 2-D patch;
+* every matvec exchanges ONLY halo rows of the vector (``all_to_all_single`` with precomputed send lists; the receive
+  buffer is the halo region of the local vector, ordered by owner so each peer's rows land contiguously);
+* every CG inner product is an all-reduce of ``C`` floats (p^T A p comes out of the SpMM epilogue, r^T r out of the fused
+  update kernel; ``mgp_cg_dist_scalars`` finishes alpha/beta/flags on every rank identically);
+* graph construction is replicated in round 1 (kNN queries are sharded and all-gathered; the O(nnz) structure / value
+  builds run on every rank): only the solve is partitioned.
+
+The local operator is a *view* of the global tile-compacted structure (no index rebasing: row pointers keep global
+positions so the TMA copies stay 16-byte aligned) with the halo column ids translated to local vector rows.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+import warnings
+
+import torch
+import torch.distributed as dist
+
+
+class RowPartition:
+    """Contiguous row blocks, aligned to ``align`` rows (the SpMM tile height) except for the last block."""
+
+    def __init__(self, n: int, world: int, align: int = 128):
+        self.n, self.world = int(n), int(world)
+        per = (n + world - 1) // world
+        per = (per + align - 1) // align * align
+        self.bounds = [min(r * per, n) for r in range(world + 1)]
+        self.bounds[-1] = n
+
+    def range(self, rank: int):
+        return self.bounds[rank], self.bounds[rank + 1]
+
+    def owner(self, ids: torch.Tensor) -> torch.Tensor:
+        b = torch.tensor(self.bounds[1:], device=ids.device, dtype=ids.dtype)
+        return torch.searchsorted(b, ids, right=True)
+
+
+class HaloPlan:
+    """Which rows each rank sends to / receives from every peer for one matvec.
+
+    ``halo_ids``  -- sorted global ids of the out-of-range columns my rows reference (grouped by owner because owners are
+                     contiguous ranges); vector row ``n_loc + i`` holds the value of global row ``halo_ids[i]``.
+    ``send_idx``  -- local row indices to pack for the peers, concatenated in peer order.
+    """
+
+    def __init__(self, part: RowPartition, rank: int, cols_of_my_rows: torch.Tensor, group=None):
+        lo, hi = part.range(rank)
+        dev = cols_of_my_rows.device
+        outside = (cols_of_my_rows < lo) | (cols_of_my_rows >= hi)
+        self.halo_ids = torch.unique(cols_of_my_rows[outside].to(torch.int64), sorted=True)
+        self.n_loc = hi - lo
+        self.lo, self.hi = lo, hi
+        owners = part.owner(self.halo_ids)
+        self.recv_counts = torch.bincount(owners, minlength=part.world).tolist()
+        # tell every peer which of its rows I need
+        send_counts_t = torch.zeros(part.world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(send_counts_t, torch.tensor(self.recv_counts, dtype=torch.int64, device=dev), group=group)
+        self.send_counts = send_counts_t.tolist()
+        req = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(req, self.halo_ids, self.send_counts, self.recv_counts, group=group)
+        self.send_idx = (req - lo).contiguous()          # local row index of every row I must send
+        assert self.send_idx.numel() == 0 or (int(self.send_idx.min()) >= 0 and int(self.send_idx.max()) < self.n_loc)
+        self.group = group
+
+    def to_local(self, ids: torch.Tensor) -> torch.Tensor:
+        """global (permuted) row id -> row of the local vector [own rows | halo rows]."""
+        ids = ids.to(torch.int64)
+        inside = (ids >= self.lo) & (ids < self.hi)
+        pos = torch.searchsorted(self.halo_ids, ids.clamp(min=0))
+        pos = pos.clamp(max=max(self.halo_ids.numel() - 1, 0))
+        return torch.where(inside, ids - self.lo, self.n_loc + pos)
+
+    def exchange(self, x: torch.Tensor, ncols: int = None) -> None:
+        """Fill rows [n_loc, n_loc + H) of ``x`` ([n_loc + H, ld]) with the peers' current values."""
+        if self.halo_ids.numel() == 0 and self.send_idx.numel() == 0:
+            return
+        send = x.index_select(0, self.send_idx)
+        dist.all_to_all_single(x[self.n_loc:self.n_loc + self.halo_ids.numel()], send, self.recv_counts, self.send_counts,
+                               group=self.group)
+
+
+class LocalStructure:
+    """Duck-types ``graph.GraphStructure`` for the rows of one rank (views of the global arrays + remapped column ids)."""
+
+    def __init__(self, gst, plan: HaloPlan):
+        from . import graph
+        self.n = plan.n_loc
+        self.nnz = gst.nnz
+        self.m = gst.m
+        self.device = gst.device
+        self.perm = self.inv = self.perm32 = None
+        lo, hi = plan.lo, plan.hi
+        self.rowptr = gst.rowptr[lo:hi + 1]                      # global positions: a / lcol are passed unsliced
+        self.col = plan.to_local(gst.col).to(torch.int32).contiguous()
+        self._dot_ws = None
+        self.tiles = None
+        t = gst.tiles
+        if t is not None and lo % t["rows"] == 0:
+            t0, t1 = lo // t["rows"], (hi + t["rows"] - 1) // t["rows"]
+            self.tiles = dict(lcol=t["lcol"], halo_ptr=t["halo_ptr"][t0:t1 + 1],
+                              halo_col=plan.to_local(t["halo_col"]).to(torch.int32).contiguous(),
+                              lmax=t["lmax"], nzmax=t["nzmax"], rows=t["rows"], halo_total=t["halo_total"])
+        self._gst = gst
+        self.TILED_SMEM_LIMIT = gst.TILED_SMEM_LIMIT
+
+    def build_tiles(self):
+        return self.tiles
+
+    def tiled_ok(self, dtype, cw):
+        return self.tiles is not None and self._gst.tiled_ok(dtype, cw)
+
+    def dot_ws(self):
+        if self._dot_ws is None:
+            self._dot_ws = torch.zeros_like(self._gst.dot_ws())
+        return self._dot_ws
+
+
+class DistPrecision:
+    """(2nu/kappa^2 + L_sym)^nu on the rows of this rank.  ``values`` = (diag[n], a[nnz]) of the GLOBAL structure."""
+
+    def __init__(self, gst, diag, a, shift, nu: int, part: RowPartition, rank: int, group=None):
+        lo, hi = part.range(rank)
+        p0, p1 = int(gst.rowptr[lo]), int(gst.rowptr[hi])
+        self.plan = HaloPlan(part, rank, gst.col[p0:p1], group=group)
+        self.st = LocalStructure(gst, self.plan)
+        self.diag = diag[lo:hi]
+        self.a = a
+        self.shift = shift
+        self.nu = nu
+        self.n_loc = hi - lo
+        self.n_ext = self.n_loc + int(self.plan.halo_ids.numel())
+
+    def matvec(self, p, out, tmp, ncols, dot_out=None):
+        """out[:n_loc, :ncols] <- P p  (p, tmp: [n_ext, ld] with halo rows; out: [>= n_loc, ld])."""
+        from . import graph
+        src = p
+        for s in range(self.nu):
+            last = s == self.nu - 1
+            dst = out if last else tmp
+            self.plan.exchange(src)
+            graph.lap_spmm(self.st, self.a, self.diag, src[:, :ncols], shift=self.shift, out=dst[:self.n_loc, :ncols],
+                           dot_with=p if last else None, dot_out=dot_out if last else None)
+            src = dst
+        return out
+
+
+def dist_cg(op: DistPrecision, b_loc: torch.Tensor, tolerance=1e-6, eps=1e-10, stop_updating_after=1e-10, max_iter=1000,
+            check_interval=16, group=None):
+    """mBCG on row-partitioned vectors.  ``b_loc`` [n_loc, C] is this rank's block of the right-hand sides (structure
+    order).  Returns (x_loc [n_loc, C], info).  Same stopping rules as ``solvers.linear_cg``."""
+    from . import _lib, solvers
+    from ._lib import c_double, c_float, c_int32, c_int64, ptr, stream
+    n_loc, c = b_loc.shape
+    dt, dev = b_loc.dtype, b_loc.device
+    sfx = _lib.suffix(dt)
+    fl = c_float if dt == torch.float32 else c_double
+    ld = solvers._pad_ld(c, dt)
+    x = torch.zeros((n_loc, ld), dtype=dt, device=dev)
+    r = torch.zeros((n_loc, ld), dtype=dt, device=dev)
+    p = torch.zeros((op.n_ext, ld), dtype=dt, device=dev)
+    tmp = torch.zeros((op.n_ext, ld), dtype=dt, device=dev)
+    v = torch.zeros((n_loc, ld), dtype=dt, device=dev)
+    state = torch.zeros(_lib.query("mgp_cg_state_elems", c_int32(c)), dtype=dt, device=dev)
+    ws = torch.zeros(_lib.query("mgp_cg_ws_bytes", c_int64(n_loc), c_int32(c)), dtype=torch.uint8, device=dev)
+    rbuf = torch.zeros(c, dtype=dt, device=dev)
+    pap = state[solvers.S_PAP * c:(solvers.S_PAP + 1) * c]
+    b = b_loc if b_loc.stride(1) == 1 else b_loc.contiguous()
+
+    def scalars(what):
+        _lib.call("mgp_cg_dist_scalars_" + sfx, ptr(state), ptr(rbuf), c_int32(c), c_int32(what), fl(tolerance), fl(eps),
+                  fl(stop_updating_after), c_int32(max_iter), c_int32(0), None, c_int32(0), stream())
+
+    _lib.call("mgp_cg_dist_norm2_" + sfx, ptr(b), c_int64(b.stride(0)), c_int64(n_loc), c_int32(c), ptr(state), ptr(rbuf),
+              ptr(ws), stream())
+    dist.all_reduce(rbuf, group=group)
+    scalars(0)
+    _lib.call("mgp_cg_dist_init_" + sfx, ptr(b), c_int64(b.stride(0)), ptr(x), ptr(r), ptr(p), c_int64(ld), c_int64(n_loc),
+              c_int32(c), ptr(state), ptr(rbuf), ptr(ws), stream())
+    dist.all_reduce(rbuf, group=group)
+    scalars(1)
+    k, done = 0, 0.0
+    scal = solvers.S_NARR * c
+    while k < max_iter:
+        steps = min(check_interval, max_iter - k)
+        for _ in range(steps):
+            op.matvec(p, v, tmp, c, dot_out=pap)
+            dist.all_reduce(pap, group=group)
+            _lib.call("mgp_cg_dist_update_" + sfx, ptr(x), ptr(r), ptr(p), ptr(v), c_int64(ld), c_int64(n_loc), c_int32(c),
+                      ptr(state), ptr(rbuf), ptr(ws), stream())
+            dist.all_reduce(rbuf, group=group)
+            scalars(2)
+            _lib.call("mgp_cg_pupdate_" + sfx, ptr(p), ptr(r), c_int64(ld), c_int64(n_loc), c_int32(c), ptr(state), stream())
+        k += steps
+        done = float(state[scal + solvers.K_DONE].item())
+        if done != 0.0:
+            break
+    out = torch.empty((n_loc, c), dtype=dt, device=dev)
+    _lib.call("mgp_cg_finalize_" + sfx, ptr(x), c_int64(ld), ptr(out), c_int64(c), c_int64(n_loc), c_int32(c), ptr(state), stream())
+    tail = state[scal:scal + 3].tolist()
+    info = dict(iterations=int(tail[solvers.K_ITER]), mean_residual=float(tail[solvers.K_MEAN]), converged=(done == 1.0))
+    return out, info
+
+
+def sharded_knn(x: torch.Tensor, k: int, part_queries: RowPartition, rank: int, group=None):
+    """kNN with the database replicated and the queries sharded; returns the full (dist2, idx) on every rank."""
+    from .utils import NearestNeighbors
+    lo, hi = part_queries.range(rank)
+    knn = NearestNeighbors(x)
+    d_loc, i_loc = knn.search(x[lo:hi].contiguous(), k)
+    world = part_queries.world
+    sizes = [part_queries.range(r)[1] - part_queries.range(r)[0] for r in range(world)]
+    d_all = [torch.empty((s, k), dtype=d_loc.dtype, device=x.device) for s in sizes]
+    i_all = [torch.empty((s, k), dtype=i_loc.dtype, device=x.device) for s in sizes]
+    dist.all_gather(d_all, d_loc.contiguous(), group=group)
+    dist.all_gather(i_all, i_loc.contiguous(), group=group)
+    return torch.cat(d_all), torch.cat(i_all), knn
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# bench entry (called by bench.py under torchrun)
+# ---------------------------------------------------------------------------------------------------------------------------
+def bench_main(args, CFG):
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import _lib, graph
+    from manifold_gp_b200.utils import synthetic
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    warnings.simplefilter("ignore")
+    n, k, c = args.n, CFG["k"], CFG["rhs"]
+    x = synthetic.torus(n, seed=CFG["seed"], device=dev)
+    # ---- graph: queries sharded, everything after replicated ------------------------------------------------------------
+    qpart = RowPartition(n, world, align=64)
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    d2, nbr, knn = sharded_knn(x, k, qpart, rank)
+    torch.cuda.synchronize(); dist.barrier(); t_knn = time.perf_counter() - t0
+    eps = float(d2[:, k - 1].sqrt().median())
+    # symmetrise on every rank (deterministic, identical results)
+    from ._lib import c_int32, c_int64, c_size_t, ptr, stream
+    cap = n * (k - 1)
+    eidx = torch.empty((2, cap), dtype=torch.int64, device=dev)
+    ev = torch.empty(cap, dtype=torch.float32, device=dev)
+    m_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    wsb = _lib.workspace(_lib.query("mgp_graph_symmetrize_ws_bytes", c_int64(n), c_int32(k)), dev)
+    _lib.call("mgp_graph_symmetrize_f32", ptr(d2.contiguous()), ptr(nbr.contiguous()), c_int64(n), c_int32(k), c_int32(1),
+              ptr(eidx), ptr(ev), c_int64(cap), ptr(m_out), ptr(wsb), c_size_t(wsb.numel()), stream())
+    m = int(m_out.item())
+    idx, val = eidx[:, :m].contiguous(), ev[:m].contiguous()
+    del eidx, ev, wsb
+    graph.attach_permutation(idx, graph.morton_permutation(x))
+    lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[eps]], device=dev), CFG["normalization"], CFG["self_loops"])
+    prec = mgp.PrecisionMaternOperator(lap, CFG["nu"], torch.tensor([[CFG["kappa"]]], device=dev))
+    gst = lap.structure
+    _, _, diag, a = lap._values()
+    part = RowPartition(n, world, align=gst.TILE_ROWS)
+    op = DistPrecision(gst, diag, a, prec._shift(), CFG["nu"], part, rank)
+    lo, hi = part.range(rank)
+    g = torch.Generator(device=dev).manual_seed(CFG["rhs_seed"])
+    B = torch.randn(n, c, device=dev, generator=g)           # identical on every rank (same seed)
+    b_loc = gst.to_internal(B)[lo:hi].contiguous()
+
+    def solve():
+        return dist_cg(op, b_loc, tolerance=CFG["tol"], max_iter=CFG["max_iter"])
+
+    for _ in range(args.warmup):
+        xs, info = solve()
+    torch.cuda.synchronize(); dist.barrier()
+    _lib.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        xs, info = solve()
+    ev1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = _lib.launch_count()
+    # check against the global residual
+    x_all = [torch.empty((part.range(r)[1] - part.range(r)[0], c), device=dev) for r in range(world)]
+    dist.all_gather(x_all, xs.contiguous())
+    sol = gst.to_external(torch.cat(x_all))
+    true_rel = float(((prec.matmul(sol) - B).double().norm(dim=0) / B.double().norm(dim=0)).mean())
+    # e2e: host buffers in, host result out (each rank moves its own block)
+    Bh = b_loc.cpu().pin_memory(); Xh = torch.empty_like(Bh).pin_memory()
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 2))):
+        bl = Bh.to(dev, non_blocking=True)
+        xs2, _ = dist_cg(op, bl, tolerance=CFG["tol"], max_iter=CFG["max_iter"])
+        Xh.copy_(xs2, non_blocking=True)
+        torch.cuda.synchronize()
+    dist.barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, min(args.steps, 2))
+    if rank == 0:
+        out = {"metric": "precision_cg_solve_time", "value": round(float(ms), 3), "unit": "ms", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(ms), 3), "higher_is_better": False,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": CFG["workload"], "n": n, "k": k, "edges_M": m, "nu": CFG["nu"], "kappa": CFG["kappa"],
+                          "eps": round(eps, 6), "rhs": c, "tol": CFG["tol"], "partition": "contiguous row blocks of the Morton order",
+                          "halo_rows_rank0": int(op.plan.halo_ids.numel()), "rows_rank0": int(op.n_loc),
+                          "l2": "inputs larger than L2 at 1-2 GPUs; at 8 GPUs a rank's share (~50 MB) is L2 resident (strong scaling)"},
+               "cg_iterations": info["iterations"], "cg_converged": bool(info["converged"]),
+               "cg_true_relative_residual": true_rel, "knn_build_s": round(t_knn, 4),
+               "e2e": {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": int(Bh.numel() * 4 * world),
+                       "d2h_bytes_per_step": int(Xh.numel() * 4 * world)},
+               "gpu_launches": int(launches),
+               "collectives_per_iteration": {"halo_all_to_all": CFG["nu"], "all_reduce": 2}}
+        print(json.dumps(out))
+    dist.barrier()
+    return None

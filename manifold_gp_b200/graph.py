@@ -249,7 +249,7 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
 
     ``a, diag, pre, post`` are in the structure's row order.  ``x_external`` / ``y_external``: X (and ``dot_with``) / Y are
     in the caller's row order (only matters when the structure is internally permuted)."""
-    if x.dim() != 2 or x.shape[0] != st.n:
+    if x.dim() != 2 or x.shape[0] < st.n:   # a row-partitioned structure reads [own rows | halo rows]: more rows than it writes
         raise ValueError(f"lap_spmm: expected rhs of shape [{st.n}, C], got {tuple(x.shape)}")
     if x.stride(1) != 1:
         x = x.contiguous()
