@@ -41,6 +41,8 @@ const char* mgp_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches claim). */
 int64_t mgp_launch_count(void);
 void mgp_reset_launch_count(void);
+/* Account for launches replayed from a captured CUDA graph (the host calls above only run at capture time). */
+void mgp_add_launch_count(int64_t n);
 
 /* ----------------------------------------------------------------------------------------------------------
  * (a2) Exact brute-force kNN, squared L2, ascending.  Replaces faiss Index{Flat,IVFFlat(nlist=1)}.search

@@ -29,6 +29,7 @@ _SIG = {
     "mgp_version": (c_char_p, []),
     "mgp_launch_count": (c_int64, []),
     "mgp_reset_launch_count": (None, []),
+    "mgp_add_launch_count": (None, [c_int64]),
     "mgp_knn_search_ws_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
     "mgp_knn_search_f32": (c_int32, [P, c_int64, P, c_int64, c_int32, c_int32, P, P, P, c_size_t, P]),
     "mgp_graph_symmetrize_ws_bytes": (c_size_t, [c_int64, c_int32]),

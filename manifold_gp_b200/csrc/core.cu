@@ -31,4 +31,6 @@ int64_t mgp_launch_count(void) { return mgp::g_launches.load(std::memory_order_r
 
 void mgp_reset_launch_count(void) { mgp::g_launches.store(0, std::memory_order_relaxed); }
 
+void mgp_add_launch_count(int64_t n) { mgp::g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 }  // extern "C"
