@@ -15,5 +15,8 @@ from .operators import (  # noqa: F401
     SchurComplementOperator,
 )
 from .utils import NearestNeighbors, bump_function  # noqa: F401
+from .kernels import RiemannKernel, RiemannMaternKernel  # noqa: F401
+from .models import RiemannGP  # noqa: F401
+from ._compat.gp import GaussianLikelihood, ScaleKernel  # noqa: F401  (stand-ins; use gpytorch's when it is installed)
 
 __version__ = "0.1.0"

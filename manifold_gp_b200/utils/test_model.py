@@ -1,0 +1,27 @@
+"""``test_model`` -- manifold_gp/utils/test_model.py:10-30: RMSE and NLL of the posterior on held-out points."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import settings
+
+
+def test_model(model, input, output, noisy_test=False, base_model=None, max_cholesky=800, cg_tolerance=1e-2, cg_iterations=1000):
+    with torch.no_grad(), settings.fast_pred_var(), settings.max_cholesky_size(max_cholesky), \
+            settings.cg_tolerance(cg_tolerance), settings.max_cg_iterations(cg_iterations):
+        model.likelihood.eval()
+        model.eval()
+        if base_model is not None:
+            model.posterior(input, noisy_posterior=noisy_test, base_model=base_model)
+        else:
+            model.posterior(input, noisy_posterior=noisy_test)
+        error = output - model.posterior_mean
+        rmse = (error.square().mean()).sqrt()
+        inv_quad, logdet = model.posterior_covar.inv_quad_logdet(inv_quad_rhs=error.unsqueeze(-1), logdet=True)
+        nll = 0.5 * sum([inv_quad, logdet, error.size(-1) * math.log(2 * math.pi)]) / error.size(-1)
+        return rmse, nll
+
+
+test_model.__test__ = False   # not a pytest test
