@@ -153,6 +153,51 @@ int mgp_lap_spmm_tiled_f64(const int32_t* rowptr, const uint16_t* lcol, const do
                            const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
                            int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws, void* stream);
 
+/* Same product, v4 "pipelined" kernel (lap_spmm_pipe.cu): the tile structure of mgp_lap_spmm_tiled with PADDED entry
+ * streams -- prowptr[n+1] addresses a stream in which every row holds a multiple of 4 entries (padding entries: plcol =
+ * the row's own tile-local index, value 0) and every tile of 128 rows starts at a multiple of 8 entries; plcol and ap
+ * must be readable 8 entries past prowptr[n].  pnzmax = max padded entries of a tile (multiple of 8).  No `pre` scaling.
+ * mgp_lap_pad_values copies a CSR-ordered value array `a` (per bandwidth) into the padded layout.
+ * Replaces the two torch_sparse.spmm calls + diagonal of graph_laplacian_operator.py:117-119 and one step of
+ * precision_matern_operator.py:28-32.  Returns MGP_EUNSUPPORTED (nothing launched) when ncols / alignment / shared
+ * memory do not qualify: the caller then uses mgp_lap_spmm_tiled or mgp_lap_spmm. */
+int mgp_lap_pad_values_f32(const int32_t* rowptr, const int32_t* prowptr, const float* a, int64_t n, float* ap, void* stream);
+int mgp_lap_pad_values_f64(const int32_t* rowptr, const int32_t* prowptr, const double* a, int64_t n, double* ap, void* stream);
+int mgp_lap_spmm_pipe_f32(const int32_t* prowptr, const uint16_t* plcol, const float* ap, const float* diag,
+                          const int32_t* halo_ptr, const int32_t* halo_col, int32_t tile_rows, int32_t lmax, int32_t pnzmax,
+                          const float* shift, const float* post, const int32_t* xmap, const int32_t* ymap, const float* x,
+                          int64_t ldx, float* y, int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out,
+                          void* dot_ws, void* stream);
+int mgp_lap_spmm_pipe_f64(const int32_t* prowptr, const uint16_t* plcol, const double* ap, const double* diag,
+                          const int32_t* halo_ptr, const int32_t* halo_col, int32_t tile_rows, int32_t lmax, int32_t pnzmax,
+                          const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
+                          int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with,
+                          double* dot_out, void* dot_ws, void* stream);
+
+/* Same product, v5 "warp-interleaved" kernel (lap_spmm_wi.cu) for 64-byte rows of X (ncols a multiple of 16 fp32 / 8 fp64
+ * columns).  Tiles of 128 rows as above; the entry streams are laid out in consumption order: warp block b = 16 * tile + w
+ * owns positions [wptr[b], wptr[b+1]) (whole 32-entry steps) and position wptr[b] + 32 t + lane holds nonzero
+ * 4t + (lane & 3) of row 128 tile + 8 w + (lane >> 2); padding entries have value 0.  wcol / aw must be readable 64
+ * entries past wptr[16 ntiles]; wnzmax = max entries of a tile.  Halo lists: hcol[hptr[t] .. hptr[t+1]) = the out-of-tile
+ * rows of X tile t reads (tile-local column 128 + position), every list padded to a multiple of 4 ids; hmax = longest
+ * padded list; lmax >= 128 + hmax.  The kernel bulk-copies its metadata in chunks of 32 tiles, so wptr must be readable
+ * up to index 512 ceil(ntiles/32) + 4 and hptr up to 32 ceil(ntiles/32) + 4, and wptr / hptr / hcol / wcol / aw must be
+ * 16-byte aligned.  mgp_lap_wi_values copies a CSR-ordered value array into the stream layout.
+ * Replaces graph_laplacian_operator.py:117-119 / precision_matern_operator.py:28-32 like the kernels above.
+ * Returns MGP_EUNSUPPORTED (nothing launched) when the call does not qualify. */
+int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const float* a, int64_t n, float* aw, void* stream);
+int mgp_lap_wi_values_f64(const int32_t* rowptr, const int32_t* wptr, const double* a, int64_t n, double* aw, void* stream);
+int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
+                        const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
+                        const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
+                        int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
+                        void* stream);
+int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag,
+                        const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax,
+                        const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
+                        int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
+                        void* dot_ws, void* stream);
+
 /* ----------------------------------------------------------------------------------------------------------
  * Backward of the SpMM w.r.t. the matrix entries (what autograd through torch_sparse.spmm computes for `value`,
  * graph_laplacian_operator.py:117-119, reached via linear_operator's _bilinear_derivative):

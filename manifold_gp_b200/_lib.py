@@ -48,6 +48,14 @@ _SIG = {
     "mgp_lap_spmm_f64": (c_int32, [P, P, P, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_spmm_tiled_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_spmm_tiled_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_lap_pad_values_f32": (c_int32, [P, P, P, c_int64, P, P]),
+    "mgp_lap_pad_values_f64": (c_int32, [P, P, P, c_int64, P, P]),
+    "mgp_lap_spmm_pipe_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_lap_spmm_pipe_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_lap_wi_values_f32": (c_int32, [P, P, P, c_int64, P, P]),
+    "mgp_lap_wi_values_f64": (c_int32, [P, P, P, c_int64, P, P]),
+    "mgp_lap_spmm_wi_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
+    "mgp_lap_spmm_wi_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_sddmm_f32": (c_int32, [P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P]),
     "mgp_lap_sddmm_f64": (c_int32, [P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P]),
     "mgp_cg_state_elems": (c_size_t, [c_int32]),

@@ -1,4 +1,9 @@
-// v3 SpMM: the tile-compacted kernel of lap_spmm_tiled.cu as a warp-specialised, double-buffered TMA pipeline.
+// v3/v4 SpMM: the tile-compacted kernel of lap_spmm_tiled.cu as a warp-specialised, multi-stage TMA pipeline.
+//
+// v4 (this file): the (index, value) streams are stored PADDED -- every row holds a multiple of 4 entries (padding entries
+// point at the row itself with weight 0) and every tile starts at a multiple of 8 entries -- so a row slot fetches 4
+// indices with one 64-bit and 4 values with one 128-bit shared-memory load instead of 8 scalar loads: per 4 nonzeros
+// the load/store pipe sees 2 + 16 wavefronts instead of 8 + 16 and the issue slots ~34 instead of ~56 instructions.
 //
 //   Y = post .* ( (diag + shift) .* X  -  A X )            (no `pre` scaling on this path; the host routes `pre` to v2)
 //
@@ -13,6 +18,7 @@
 //   consumers (16 warps): wait full[s] -> rows (one 4-lane slot per row for 16 fp32 columns) -> Y stores -> arrive empty[s]
 #include "common.cuh"
 #include "spmm_common.cuh"
+#include "pipe_common.cuh"
 
 namespace mgp {
 
@@ -51,46 +57,18 @@ struct PipeArgs {
   int stages;   // 2 or 3 shared-memory stages (as many as fit)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("{ .reg .b64 st; mbarrier.arrive.release.cta.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-// Bounded wait: a logic error traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && spins > (1u << 24)) __trap();
+// 4 consecutive values of the (padded, 16-byte aligned) value stream: unit u = entries [4u, 4u + 4)
+template <typename T>
+__device__ __forceinline__ void load_vals4(const T* vs, int u, T (&w)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 t = reinterpret_cast<const float4*>(vs)[u];
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+  } else {
+    const double2 t0 = reinterpret_cast<const double2*>(vs)[2 * u];
+    const double2 t1 = reinterpret_cast<const double2*>(vs)[2 * u + 1];
+    w[0] = t0.x; w[1] = t0.y; w[2] = t1.x; w[3] = t1.y;
   }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-// the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <typename T, int CW, int R>
 __host__ __device__ inline size_t pipe_stage_bytes(int lmax, int nzcap) {
@@ -276,33 +254,56 @@ lap_spmm_pipe_kernel(const PipeArgs<T> g) {
         T acc[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v] = T(0);
-        // Bank schedule for the (index, value) streams.  The 8 (= 32 / LPN) row slots of a warp advance in lockstep, so
-        // slot i reads entry q0_i + t at step t; rows of equal length L start L entries apart, i.e. in the same bank when
-        // L % 32 == 0.  Each slot therefore starts its row at a rotated offset (wrapping around at the end of the row):
-        // slot pairs (2q, 2q+1) -- which share a quarter-warp and rely on the even/odd entry ordering for conflict-free
-        // X-row loads -- keep a common rotation (shifted by one entry only if their rows are a multiple of 32 apart),
-        // and pair q is moved to banks 8q beyond slot 0.
-        const int len = q1 - q0;
-        int rot = 0;
+        // Entries are consumed 4 at a time (rows are padded to multiples of 4 entries): one 64-bit load brings 4 tile-local
+        // indices, one 128-bit load (two for fp64) the 4 values.  The row slots of a warp advance in lockstep, so slot i
+        // reads unit u_i + t at step t; rows of equal length start a fixed number of units apart and can sit in the same
+        // banks.  Each slot therefore starts at a rotated unit (wrapping around at the end of the row): slot pairs
+        // (2q, 2q+1) -- which share a quarter-warp and rely on the even/odd entry ordering for conflict-free X-row
+        // loads -- keep a common rotation (one extra unit only if their rows are a multiple of 8 units apart), and the
+        // leader of pair q starts 2q units (mod 8) beyond slot 0.
+        const int ulen = (q1 - q0) >> 2;
+        const int ubeg = q0 >> 2, uend = q1 >> 2;
+        int rotu = 0;
         if constexpr (ROWS_PER_WARP >= 2) {
-          const int b = q0 & 31;
-          const int b0 = __shfl_sync(0xffffffffu, b, 0);
+          const int u0 = __shfl_sync(0xffffffffu, ubeg, 0);
           const int lead_lane = (rg & ~1) * LPR;
-          const int bl = __shfl_sync(0xffffffffu, b, lead_lane);
-          const int len_l = __shfl_sync(0xffffffffu, len, lead_lane);
-          rot = (8 * (rg >> 1) + b0 - bl) & 31;
-          if ((rg & 1) && (len_l & 31) == 0) rot += 1;
-          if (rot >= len) rot = 0;
+          const int ul = __shfl_sync(0xffffffffu, ubeg, lead_lane);
+          const int ulen_l = __shfl_sync(0xffffffffu, ulen, lead_lane);
+          rotu = (2 * (rg >> 1) + u0 - ul) & 7;
+          if ((rg & 1) && (ulen_l & 7) == 0) rotu += 1;
+          if (rotu >= ulen) rotu = 0;
         }
-#pragma unroll 4
-        for (int t = 0; t < len; ++t) {
-          int p = q0 + t + rot;
-          if (p >= q1) p -= len;
-          const int j = cs[p];
-          const T w = vs[p];
-          const Vec<T, VEC> xv = *reinterpret_cast<const Vec<T, VEC>*>(xs + j * CW + cl * VEC);
+        const uint2* cs2 = reinterpret_cast<const uint2*>(cs);
+        const unsigned char* xb = reinterpret_cast<const unsigned char*>(xs) + cl * VEC * sizeof(T);
+        int u = ubeg + rotu;
+        uint2 jj = cs2[u];
+        T w4[4];
+        load_vals4<T>(vs, u, w4);
+#pragma unroll 2
+        for (int t = 0; t < ulen; ++t) {
+          int un = u + 1;
+          if (un == uend) un = ubeg;
+          const uint2 jn = cs2[un];                   // next unit in flight while this one is consumed
+          T wn[4];
+          load_vals4<T>(vs, un, wn);
+          const uint32_t o0 = (jj.x & 0xffffu) * ROW_BYTES, o1 = (jj.x >> 16) * ROW_BYTES;
+          const uint32_t o2 = (jj.y & 0xffffu) * ROW_BYTES, o3 = (jj.y >> 16) * ROW_BYTES;
+          const Vec<T, VEC> x0 = *reinterpret_cast<const Vec<T, VEC>*>(xb + o0);
+          const Vec<T, VEC> x1 = *reinterpret_cast<const Vec<T, VEC>*>(xb + o1);
+          const Vec<T, VEC> x2 = *reinterpret_cast<const Vec<T, VEC>*>(xb + o2);
+          const Vec<T, VEC> x3 = *reinterpret_cast<const Vec<T, VEC>*>(xb + o3);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] = fma(w, xv.v[v], acc[v]);
+          for (int v = 0; v < VEC; ++v) acc[v] = fma(w4[0], x0.v[v], acc[v]);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] = fma(w4[1], x1.v[v], acc[v]);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] = fma(w4[2], x2.v[v], acc[v]);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] = fma(w4[3], x3.v[v], acc[v]);
+          jj = jn;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w4[e] = wn[e];
+          u = un;
         }
         if (active) {
           const Vec<T, VEC> xi = *reinterpret_cast<const Vec<T, VEC>*>(xs + r * CW + cl * VEC);
@@ -355,7 +356,7 @@ static int launch_pipe(const PipeArgs<T>& g, cudaStream_t st) {
 // One column pass of the pipelined kernel; returns MGP_EUNSUPPORTED when the pass does not qualify (caller falls back
 // to the v2 kernel): needs VEC-wide aligned columns and two stages that fit in shared memory.
 template <typename T>
-int lap_spmm_pipe_pass(const int* rowptr, const unsigned short* lcol, const T* a, const T* diag, const int* halo_ptr,
+static int lap_spmm_pipe_pass(const int* rowptr, const unsigned short* lcol, const T* a, const T* diag, const int* halo_ptr,
                        const int* halo_col, int lmax, int nzcap, const T* shift, const T* post, const int* xmap,
                        const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int c0, int cw,
                        const T* dot_with, T* dot_out, T* partials, unsigned int* counter, int dot_is_x, cudaStream_t st) {
@@ -378,13 +379,96 @@ int lap_spmm_pipe_pass(const int* rowptr, const unsigned short* lcol, const T* a
   return MGP_EUNSUPPORTED;
 }
 
-template int lap_spmm_pipe_pass<float>(const int*, const unsigned short*, const float*, const float*, const int*, const int*,
-                                       int, int, const float*, const float*, const int*, const int*, const float*, int64_t,
-                                       float*, int64_t, int64_t, int, int, const float*, float*, float*, unsigned int*, int,
-                                       cudaStream_t);
-template int lap_spmm_pipe_pass<double>(const int*, const unsigned short*, const double*, const double*, const int*,
-                                        const int*, int, int, const double*, const double*, const int*, const int*,
-                                        const double*, int64_t, double*, int64_t, int64_t, int, int, const double*, double*,
-                                        double*, unsigned int*, int, cudaStream_t);
+// ---- padded value stream: a_p[prowptr[r] + t] = a[rowptr[r] + t] for t < len(r), 0 for the padding entries -------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+lap_pad_values_kernel(const int* __restrict__ rowptr, const int* __restrict__ prowptr, const T* __restrict__ a, int64_t n,
+                      T* __restrict__ ap) {
+  constexpr int L = 8;   // lanes per row
+  const int l = threadIdx.x & (L - 1);
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  if (row >= n) return;
+  const int p0 = rowptr[row], len = rowptr[row + 1] - p0;
+  const int q0 = prowptr[row], plen = prowptr[row + 1] - q0;
+  for (int t = l; t < plen; t += L) ap[q0 + t] = t < len ? ld_stream(a + p0 + t) : T(0);
+}
+
+template <typename T>
+static int lap_pad_values(const int* rowptr, const int* prowptr, const T* a, int64_t n, T* ap, cudaStream_t st) {
+  MGP_CHECK_ARG(rowptr && prowptr && a && ap && n > 0, "lap_pad_values: bad arguments");
+  const int64_t threads = n * 8;
+  lap_pad_values_kernel<T><<<(unsigned)ceil_div(threads, (int64_t)256), 256, 0, st>>>(rowptr, prowptr, a, n, ap);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+template <typename T>
+static int lap_spmm_pipe(const int* prowptr, const unsigned short* plcol, const T* ap, const T* diag, const int* halo_ptr,
+                         const int* halo_col, int tile_rows, int lmax, int pnzmax, const T* shift, const T* post,
+                         const int* xmap, const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int ncols,
+                         const T* dot_with, T* dot_out, void* dot_ws, cudaStream_t st) {
+  constexpr int R = 128;
+  constexpr int VECW = sizeof(T) == 4 ? 4 : 2;
+  MGP_CHECK_ARG(prowptr && plcol && ap && diag && halo_ptr && halo_col && x && y, "lap_spmm_pipe: null pointer");
+  MGP_CHECK_ARG(tile_rows == R, "lap_spmm_pipe: this build supports tile_rows == %d (got %d)", R, tile_rows);
+  MGP_CHECK_ARG(n > 0 && ncols > 0 && ldx >= ncols && ldy >= ncols, "lap_spmm_pipe: bad shape");
+  MGP_CHECK_ARG(x != y, "lap_spmm_pipe: X and Y must not alias");
+  MGP_CHECK_ARG((dot_out == nullptr) || (dot_with && dot_ws), "lap_spmm_pipe: dot epilogue needs dot_with and dot_ws");
+  MGP_CHECK_ARG(lmax >= R && lmax <= 65535 && pnzmax > 0 && pnzmax % 8 == 0, "lap_spmm_pipe: bad tile statistics lmax=%d pnzmax=%d",
+                lmax, pnzmax);
+  const bool aligned = (ldx % VECW == 0) && (ldy % VECW == 0) && (((uintptr_t)x) % 16 == 0) && (((uintptr_t)y) % 16 == 0) &&
+                       (dot_with == nullptr || ((uintptr_t)dot_with) % 16 == 0) && (ncols % VECW == 0);
+  if (!aligned) return MGP_EUNSUPPORTED;
+  const int lmax4 = (lmax + 3) & ~3;
+  {  // the widest pass must fit two stages, otherwise nothing is launched and the caller uses the v2 kernel
+    int cw = VECW;
+    while (cw * 2 <= ncols && cw * 2 <= 16) cw *= 2;
+    const size_t one = (size_t)lmax4 * cw * sizeof(T) + (size_t)pnzmax * (sizeof(T) + 2) + (size_t)R * sizeof(T) + (size_t)(R + 4) * 4;
+    if (2 * one > kPipeSmemLimit) return MGP_EUNSUPPORTED;
+  }
+  T* partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
+  unsigned int* counter = dot_out ? reinterpret_cast<unsigned int*>(dot_ws) : nullptr;
+  const int dot_is_x = (dot_out && dot_with == x) ? 1 : 0;
+  int c0 = 0;
+  while (c0 < ncols) {
+    const int rem = ncols - c0;
+    int cw = VECW;
+    while (cw * 2 <= rem && cw * 2 <= 16) cw *= 2;
+    const int rc = lap_spmm_pipe_pass<T>(prowptr, plcol, ap, diag, halo_ptr, halo_col, lmax4, pnzmax, shift, post, xmap, ymap, x,
+                                         ldx, y, ldy, n, c0, cw, dot_out ? dot_with : nullptr, dot_out, partials, counter,
+                                         dot_is_x, st);
+    if (rc != MGP_OK) return rc;
+    c0 += cw;
+  }
+  return MGP_OK;
+}
 
 }  // namespace mgp
+
+extern "C" {
+
+int mgp_lap_pad_values_f32(const int32_t* rowptr, const int32_t* prowptr, const float* a, int64_t n, float* ap, void* stream) {
+  return mgp::lap_pad_values<float>(rowptr, prowptr, a, n, ap, (cudaStream_t)stream);
+}
+int mgp_lap_pad_values_f64(const int32_t* rowptr, const int32_t* prowptr, const double* a, int64_t n, double* ap, void* stream) {
+  return mgp::lap_pad_values<double>(rowptr, prowptr, a, n, ap, (cudaStream_t)stream);
+}
+
+int mgp_lap_spmm_pipe_f32(const int32_t* prowptr, const uint16_t* plcol, const float* ap, const float* diag,
+                          const int32_t* halo_ptr, const int32_t* halo_col, int32_t tile_rows, int32_t lmax, int32_t pnzmax,
+                          const float* shift, const float* post, const int32_t* xmap, const int32_t* ymap, const float* x,
+                          int64_t ldx, float* y, int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out,
+                          void* dot_ws, void* stream) {
+  return mgp::lap_spmm_pipe<float>(prowptr, plcol, ap, diag, halo_ptr, halo_col, tile_rows, lmax, pnzmax, shift, post, xmap,
+                                   ymap, x, ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
+}
+int mgp_lap_spmm_pipe_f64(const int32_t* prowptr, const uint16_t* plcol, const double* ap, const double* diag,
+                          const int32_t* halo_ptr, const int32_t* halo_col, int32_t tile_rows, int32_t lmax, int32_t pnzmax,
+                          const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
+                          int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with,
+                          double* dot_out, void* dot_ws, void* stream) {
+  return mgp::lap_spmm_pipe<double>(prowptr, plcol, ap, diag, halo_ptr, halo_col, tile_rows, lmax, pnzmax, shift, post, xmap,
+                                    ymap, x, ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

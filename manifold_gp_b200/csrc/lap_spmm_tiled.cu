@@ -258,13 +258,6 @@ static int launch_tiled(const TiledArgs<T>& g, cudaStream_t st) {
   return MGP_OK;
 }
 
-// v3 pipelined pass (lap_spmm_pipe.cu)
-template <typename T>
-int lap_spmm_pipe_pass(const int* rowptr, const unsigned short* lcol, const T* a, const T* diag, const int* halo_ptr,
-                       const int* halo_col, int lmax, int nzcap, const T* shift, const T* post, const int* xmap,
-                       const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int c0, int cw,
-                       const T* dot_with, T* dot_out, T* partials, unsigned int* counter, int dot_is_x, cudaStream_t st);
-
 template <typename T>
 static int lap_spmm_tiled(const int* rowptr, const unsigned short* lcol, const T* a, const T* diag, const int* halo_ptr,
                           const int* halo_col, int tile_rows, int lmax, int nzmax, const T* shift, const T* pre,
@@ -289,22 +282,11 @@ static int lap_spmm_tiled(const int* rowptr, const unsigned short* lcol, const T
   g.partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
   g.dot_is_x = (dot_out && dot_with == x && pre == nullptr) ? 1 : 0;
   { const char* dbg = getenv("MGP_TILED_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
-  bool use_pipe = true;
-  { const char* e = getenv("MGP_SPMM_PIPE"); if (e && e[0] == '0') use_pipe = false; }
   int c0 = 0;
   while (c0 < ncols) {
     const int rem = ncols - c0;
     int rc;
     g.c0 = c0;
-    if (aligned && c0 % VECW == 0 && rem >= VECW && pre == nullptr && use_pipe) {
-      // v3: warp-specialised TMA pipeline (falls through to v2 when two stages do not fit in shared memory)
-      int cw = VECW;
-      while (cw * 2 <= rem && cw * 2 <= 16) cw *= 2;
-      rc = lap_spmm_pipe_pass<T>(rowptr, lcol, a, diag, halo_ptr, halo_col, g.lmax, g.nzcap, shift, post, xmap, ymap, x, ldx,
-                                 y, ldy, n, c0, cw, g.dot_with, dot_out, g.partials, g.counter, g.dot_is_x, st);
-      if (rc == MGP_OK) { c0 += cw; continue; }
-      if (rc != MGP_EUNSUPPORTED) return rc;
-    }
     if (aligned && c0 % VECW == 0 && rem >= VECW) {
       if constexpr (sizeof(T) == 4) {
         if (rem >= 16) { g.cw = 16; rc = launch_tiled<T, 4, 4, 4, R>(g, st); }

@@ -1,0 +1,442 @@
+// v5 SpMM ("warp-interleaved"): the pipelined tile kernel of lap_spmm_pipe.cu with the row work split the other way.
+//
+//   Y = post .* ( (diag + shift) .* X  -  A X )        for 64-byte rows of X (16 fp32 or 8 fp64 columns per pass)
+//
+// Why: ncu on v3/v4 (profiles/) shows the kernel bound by shared-memory wavefronts (LSU data pipe ~70 % busy): per 32
+// nonzeros 16 wavefronts of X-row loads (64 B per nonzero -- irreducible) plus 6-8 wavefronts of (index, value) loads,
+// because the 4 lanes that share a row all load the same index and value (a broadcast still costs one wavefront per
+// 32-bit slice per phase).  Here the 4 lanes of a row slot take DIFFERENT nonzeros of the row and each accumulates all
+// 16 columns; the slot's partial sums are combined once per row with 12 shuffles.  The (index, value) streams are stored
+// in exactly the order the lanes consume them -- for warp w of a tile, step t, lane l: position wptr[16*tile + w] + 32 t + l
+// holds nonzero 4t + (l & 3) of row 8w + (l >> 2) -- so every step is ONE 64-byte and ONE 128-byte fully coalesced
+// shared load per warp: 2 wavefronts per 32 nonzeros instead of 6-8, and 29 instead of 36 (v4) / ~90 (v3) instructions.
+//
+// Bank conflicts of the X-row loads: lane l reads 16-byte chunk (c + l) mod 4 of its nonzero's row in load c, so the 4
+// lanes of a slot cover 4 different chunks; the two slots of a quarter-warp stay in different 64-byte halves of the
+// bank space as long as their rows' tile-local indices have opposite parity, which the entry order arranges (even rows
+// list even indices first, odd rows odd indices first -- graph.py).  Padding entries (weight 0) carry an index of the
+// parity their position expects.
+//
+// Pipeline (unchanged from v3): 4 producer warps fill one of up to 3 shared-memory stages per tile -- bulk copies (TMA,
+// UBLKCP) for the index stream, the value stream and the tile's own X rows, 16-byte cp.async for the scattered halo rows,
+// all completing on an mbarrier -- while 16 consumer warps walk the rows of a ready stage.
+#include "common.cuh"
+#include "pipe_common.cuh"
+#include "spmm_common.cuh"
+
+namespace mgp {
+
+constexpr int kWiMaxStages = 3;
+constexpr int kWiProducerWarps = 4;
+constexpr int kWiProducerThreads = kWiProducerWarps * 32;
+constexpr int kWiConsumerWarps = 16;
+constexpr int kWiThreads = (kWiConsumerWarps + kWiProducerWarps) * 32;
+constexpr int kWiRows = 128;                       // rows per tile = 16 consumer warps x 8 row slots
+constexpr int kWiIdSlots = 4;                      // halo-id ring: ids are requested this many tiles ahead
+constexpr int kWiChunk = 32;                       // tiles per metadata chunk
+constexpr int kWiMetaW = 16 * kWiChunk + 4;        // ints of wptr per chunk (513 used)
+constexpr int kWiMetaH = kWiChunk + 4;             // ints of hptr per chunk (33 used)
+constexpr int kWiMetaBytes = (kWiMetaW + kWiMetaH) * 4;
+constexpr size_t kWiSmemLimit = 232448 - 8192;    // dynamic; static shared memory (dot epilogue, barriers) stays < 8 KB
+
+template <typename T>
+struct WiArgs {
+  const int* wptr;               // [16 * ntiles + 1] stream offsets of the per-warp blocks (multiples of 32 entries); padded, see header
+  const unsigned short* wcol;    // tile-local column per stream entry
+  const T* aw;                   // value per stream entry (0 for padding)
+  const T* diag;
+  const int* hptr;               // [ntiles + 1] halo list offsets (multiples of 4); padded, see header
+  const int* hcol;               // halo row ids, every tile's list padded to a multiple of 4 with valid ids
+  const T* shift;
+  const T* post;
+  const int* xmap;
+  const int* ymap;
+  const T* x;
+  int64_t ldx;
+  T* y;
+  int64_t ldy;
+  int64_t n;
+  int ntiles;
+  int lmax;      // max rows of X a tile stages (own + padded halo), multiple of 4
+  int nzcap;     // max stream entries of a tile + 32 (multiple of 32)
+  int hmax;      // max padded halo length (multiple of 4)
+  int c0;
+  const T* dot_with;
+  T* dot_out;
+  T* partials;
+  unsigned int* counter;
+  int dot_is_x;
+  int stages;
+  int debug;     // timing experiments only (MGP_WI_DEBUG bit mask): 1 = consumers skip the row walk, 2 = producers skip the halo rows
+                 // (same-process A/B on B200, cfg-C: 150 us full, 104 without halo copies, 90 without the walk, 62 with neither)
+};
+
+template <typename T>
+__host__ __device__ inline size_t wi_stage_bytes(int lmax, int nzcap) {
+  // xs [lmax] x 64 B | vs [nzcap] T | cs [nzcap] u16 | rp [20] int       (every piece a multiple of 16 bytes)
+  return (size_t)lmax * 64 + (size_t)nzcap * (sizeof(T) + 2) + 20 * 4;
+}
+__host__ __device__ inline size_t wi_ring_bytes(int hmax) { return 2 * (size_t)kWiMetaBytes + (size_t)kWiIdSlots * hmax * 4; }
+
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWiProducerThreads) : "memory"); }
+
+// Design notes (what three rounds of ncu / timing experiments on B200 established, profiles/):
+//  * consumers are bound by shared-memory wavefronts: 16 per 32 nonzeros for the 64-byte X rows; the warp-interleaved
+//    streams bring the (index, value) part down from 6-8 to 2;
+//  * the PRODUCER decides whether they ever get there.  With the tile's metadata, row offsets, diagonal and halo ids
+//    loaded from global memory into registers (v3-v5a) each producer warp ran ~500 dependent instructions per tile and
+//    waited on global-load latency every iteration (register rings do not help: a scoreboard wait covers every load in
+//    flight on that scoreboard); the kernel took the same ~105 us with the consumers' row walk switched off.  A bare
+//    TMA ring with the same barrier protocol streams at 7 TB/s (profiles/micro/tma_stream.cu), so the fix is to keep
+//    long-latency loads out of the producer altogether:
+//      - a block owns a CONTIGUOUS range of tiles, so its metadata is contiguous: chunks of 32 tiles of (wptr, hptr) are
+//        bulk-copied into a 2-slot shared-memory ring one chunk ahead;
+//      - each tile's halo id list is bulk-copied into a 4-slot ring 4 tiles ahead;
+//      - the producers then only read shared memory (tens of cycles) and issue copies: thread 0 the three bulk copies of
+//        the stage, thread 32 the ring refills, all 128 the 16-byte cp.async of the halo rows (4 lanes per row);
+//      - the diagonal is read by the consumers themselves (issued before the row walk, used after it).
+template <typename T>
+__global__ void __launch_bounds__(kWiThreads, 1)
+lap_spmm_wi_kernel(const WiArgs<T> g) {
+  constexpr int R = kWiRows;
+  constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte chunk
+  constexpr int CW = 4 * VEC;                  // columns per pass: 64-byte rows
+  constexpr uint32_t ROW_BYTES = 64;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kWiMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWiMaxStages];
+  __shared__ __align__(8) uint64_t meta_bar[2];
+  __shared__ __align__(8) uint64_t ids_bar[kWiIdSlots];
+  const int nstages = g.stages;
+  const size_t stage_bytes = wi_stage_bytes<T>(g.lmax, g.nzcap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* const ring = smem_raw + (size_t)nstages * stage_bytes;
+  int* const ids_ring = reinterpret_cast<int*>(ring + 2 * kWiMetaBytes);
+
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 2 * kWiProducerThreads);   // per producer thread: one plain arrive (thread 0: expect_tx) + one cp.async arrive
+      mbar_init(&empty_bar[s], 16);                      // one arrival per warp block of the tile
+    }
+    mbar_init(&meta_bar[0], 1);
+    mbar_init(&meta_bar[1], 1);
+    for (int s = 0; s < kWiIdSlots; ++s) mbar_init(&ids_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // contiguous tile range of this block
+  const int t0 = (int)(((int64_t)blockIdx.x * g.ntiles) / gridDim.x);
+  const int t1 = (int)(((int64_t)(blockIdx.x + 1) * g.ntiles) / gridDim.x);
+
+  T dsum[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) dsum[v] = T(0);
+
+  if (warp < kWiProducerWarps) {
+    // =================================================== producer ===================================================
+    const int pw = warp, sub = lane >> 2, ch = lane & 3;          // producer warp / row of a pass / 16-byte chunk
+    const int ch0 = t0 >> 5, ch_last = (t1 - 1) >> 5;             // metadata chunks this block touches
+    const bool own_contig = (g.xmap == nullptr) && (g.ldx == CW);
+    const unsigned char* const xbase = reinterpret_cast<const unsigned char*>(g.x + g.c0) + ch * 16;
+    const int64_t ldxb = g.ldx * (int64_t)sizeof(T);
+    auto meta_w = [&](int c) { return reinterpret_cast<const int*>(ring + (size_t)((c - ch0) & 1) * kWiMetaBytes); };
+    auto meta_h = [&](int c) { return meta_w(c) + kWiMetaW; };
+    auto request_meta = [&](int c) {                               // one thread
+      uint64_t* bar = &meta_bar[(c - ch0) & 1];
+      mbar_arrive_expect_tx(bar, (uint32_t)kWiMetaBytes);
+      bulk_g2s(const_cast<int*>(meta_w(c)), g.wptr + (size_t)c * 16 * kWiChunk, kWiMetaW * 4, bar);
+      bulk_g2s(const_cast<int*>(meta_h(c)), g.hptr + (size_t)c * kWiChunk, kWiMetaH * 4, bar);
+    };
+    auto wait_meta = [&](int c) { mbar_wait(&meta_bar[(c - ch0) & 1], (uint32_t)(((c - ch0) >> 1) & 1)); };
+    auto request_ids = [&](int t) {                                // one thread; the chunk of tile t must have landed
+      const int i = t - t0;
+      const int* hp = meta_h(t >> 5) + (t & 31);
+      const int h0 = hp[0], nh = hp[1] - h0;
+      uint64_t* bar = &ids_bar[i % kWiIdSlots];
+      mbar_arrive_expect_tx(bar, (uint32_t)nh * 4u);
+      if (nh > 0) bulk_g2s(ids_ring + (size_t)(i % kWiIdSlots) * g.hmax, g.hcol + h0, (uint32_t)nh * 4u, bar);
+    };
+    if (tid == 32 && t0 < t1) {                                    // prologue of the two rings
+      request_meta(ch0);
+      if (ch0 < ch_last) request_meta(ch0 + 1);
+      wait_meta(ch0);
+      for (int t = t0; t < t1 && t < t0 + kWiIdSlots; ++t) {
+        if ((t >> 5) != ch0) wait_meta(t >> 5);
+        request_ids(t);
+      }
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0;
+      unsigned char* const sb = smem_raw + (size_t)s * stage_bytes;
+      unsigned char* const xs = sb;
+      T* const vs = reinterpret_cast<T*>(sb + (size_t)g.lmax * ROW_BYTES);
+      unsigned short* const cs = reinterpret_cast<unsigned short*>(vs + g.nzcap);
+      int* const rp = reinterpret_cast<int*>(cs + g.nzcap);
+      const int c = t >> 5;
+      wait_meta(c);                                                // passes at once except on the first tile of a chunk
+      const int* wp = meta_w(c) + 16 * (t & 31);
+      const int* hp = meta_h(c) + (t & 31);
+      const int base = wp[0];
+      const int cnt = wp[16] - base;                               // multiple of 32 entries
+      const int nh = hp[1] - hp[0];
+      const int64_t row0 = (int64_t)t * R;
+      const int nrows = (int)min((int64_t)R, g.n - row0);
+      const int nown = own_contig ? 0 : nrows;
+      const int nscat = (g.debug & 2) ? 0 : nown + nh;
+      const int* ids = ids_ring + (size_t)(i % kWiIdSlots) * g.hmax;
+      mbar_wait(&ids_bar[i % kWiIdSlots], (uint32_t)((i / kWiIdSlots) & 1));
+      mbar_wait(&empty_bar[s], ph ^ 1);                            // fresh barrier: parity 1 passes immediately
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)cnt * (2 + (uint32_t)sizeof(T)) + (own_contig ? (uint32_t)nrows * ROW_BYTES : 0u);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        if (cnt > 0) {
+          bulk_g2s(cs, g.wcol + base, (uint32_t)cnt * 2, &full_bar[s]);
+          bulk_g2s(vs, g.aw + base, (uint32_t)cnt * (uint32_t)sizeof(T), &full_bar[s]);
+        }
+        if (own_contig) bulk_g2s(xs, g.x + row0 * g.ldx + g.c0, (uint32_t)nrows * ROW_BYTES, &full_bar[s]);
+      }
+      // scattered X rows: 4 consecutive lanes copy the four 16-byte chunks of one row (8 whole rows per warp instruction)
+      for (int rr = 8 * pw + sub; rr < nscat; rr += 32) {
+        int sr = rr < nown ? (int)(row0 + rr) : ids[rr - nown];
+        if (g.xmap) sr = __ldg(g.xmap + sr);
+        const int dstrow = rr < nown ? rr : R + (rr - nown);
+        cp_async16(xs + (size_t)dstrow * ROW_BYTES + ch * 16, xbase + (int64_t)sr * ldxb);
+      }
+      cp_async_arrive_noinc(&full_bar[s]);
+      if (tid <= 16) rp[tid] = wp[tid] - base;
+      if (tid != 0) mbar_arrive(&full_bar[s]);
+      producers_sync();                                            // everyone is done with this tile's id slot and metadata
+      if (tid == 32) {
+        const int tn = t + kWiIdSlots;
+        if (tn < t1) {
+          if ((tn >> 5) != c) wait_meta(tn >> 5);
+          request_ids(tn);
+        }
+        // last tile of a chunk done: its ring slot is free -> fetch the chunk after the next one into it
+        if (((t + 1) & 31) == 0 && c + 2 <= ch_last) request_meta(c + 2);
+      }
+      if (++s == nstages) { s = 0; ph ^= 1; }
+    }
+  } else {
+    // =================================================== consumers ==================================================
+    const int slot = lane >> 2;                      // row slot inside the warp
+    const int l = lane & 3;                          // which nonzeros of the row (4t + l) / which output chunk
+    const int cbase = g.c0 + l * VEC;
+    const T shift = g.shift ? *g.shift : T(0);
+    // byte offset of the chunk this lane reads in load c: chunk (c + l) mod 4
+    const uint32_t o0 = (uint32_t)(((0 + l) & 3) * 16), o1 = (uint32_t)(((1 + l) & 3) * 16);
+    const uint32_t o2 = (uint32_t)(((2 + l) & 3) * 16), o3 = (uint32_t)(((3 + l) & 3) * 16);
+    // Fixed warp <-> block map: warp w walks rows 8w .. 8w+7 of every tile.  (Handing the 16 blocks of a tile out
+    // dynamically -- shared-memory ticket counter -- was measured in the same process: 150.3 vs 149.6 us, no gain.)
+    for (unsigned int tk = (unsigned int)(warp - kWiProducerWarps);; tk += 16) {
+      const int ti = (int)(tk >> 4);
+      if (ti >= t1 - t0) break;
+      const int w = (int)(tk & 15u);                 // warp block of the tile: rows 8w .. 8w+7
+      const int tile = t0 + ti;
+      const int r = w * 8 + slot;                    // row inside the tile
+      int s;
+      uint32_t ph;
+      if (nstages == 3) { s = ti % 3; ph = (uint32_t)(ti / 3) & 1u; } else { s = ti & 1; ph = (uint32_t)(ti >> 1) & 1u; }
+      unsigned char* const sb = smem_raw + (size_t)s * stage_bytes;
+      unsigned char* const xs = sb;
+      const T* const vs = reinterpret_cast<const T*>(sb + (size_t)g.lmax * ROW_BYTES);
+      const unsigned short* const cs = reinterpret_cast<const unsigned short*>(vs + g.nzcap);
+      const int* const rp = reinterpret_cast<const int*>(cs + g.nzcap);
+      const int64_t row0 = (int64_t)tile * R;
+      const int nrows = (int)min((int64_t)R, g.n - row0);
+      const bool active = r < nrows;
+      const int64_t row = row0 + r;
+      // operands of the epilogue that live in global memory: in flight while the stage is awaited and walked
+      Vec<T, VEC> dw;
+      if (g.dot_out && !g.dot_is_x && active) {
+        const int64_t drow = g.xmap ? (int64_t)__ldg(g.xmap + row) : row;
+        dw = ldg_vec<T, VEC>(g.dot_with + drow * g.ldx + cbase);
+      }
+      int64_t yrow = row;
+      if (g.ymap && active) yrow = (int64_t)__ldg(g.ymap + row);
+      const T po = (g.post && active) ? __ldg(g.post + row) : T(1);
+      const T dgv = active ? __ldg(g.diag + row) : T(0);
+      mbar_wait(&full_bar[s], ph);
+      const int ofs = rp[w];
+      const int steps = (g.debug & 1) ? 0 : (rp[w + 1] - ofs) >> 5;
+      const unsigned short* cp = cs + ofs + lane;
+      const T* vp = vs + ofs + lane;
+      T acc[4][VEC];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[c][v] = T(0);
+      uint32_t j = cp[0];
+      T wv = vp[0];
+#pragma unroll 2
+      for (int t = 0; t < steps; ++t) {
+        const uint32_t jn = cp[32];                  // next step in flight (the last one reads into the next block: unused)
+        const T wn = vp[32];
+        cp += 32;
+        vp += 32;
+        const unsigned char* xr = xs + j * ROW_BYTES;
+        const Vec<T, VEC> x0 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o0);
+        const Vec<T, VEC> x1 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o1);
+        const Vec<T, VEC> x2 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o2);
+        const Vec<T, VEC> x3 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o3);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          acc[0][v] = fma(wv, x0.v[v], acc[0][v]);
+          acc[1][v] = fma(wv, x1.v[v], acc[1][v]);
+          acc[2][v] = fma(wv, x2.v[v], acc[2][v]);
+          acc[3][v] = fma(wv, x3.v[v], acc[3][v]);
+        }
+        j = jn;
+        wv = wn;
+      }
+      // acc[c] of lane l holds chunk (c + l) mod 4 of the slot's partial sums; lane l ends up with chunk l complete:
+      // its own acc[0] plus acc[4 - d] of the lane d places further (mod 4) in the slot, d = 1..3
+      T res[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) res[v] = acc[0][v];
+#pragma unroll
+      for (int d = 1; d < 4; ++d) {
+        const int src = (lane & ~3) | ((l + d) & 3);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) res[v] += __shfl_sync(0xffffffffu, acc[4 - d][v], src);
+      }
+      if (active) {
+        const Vec<T, VEC> xi = *reinterpret_cast<const Vec<T, VEC>*>(xs + (size_t)r * ROW_BYTES + l * 16);
+        const T d = dgv + shift;
+        Vec<T, VEC> out;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) out.v[v] = po * (d * xi.v[v] - res[v]);
+        st_vec<T, VEC>(g.y + yrow * g.ldy + cbase, out);
+        if (g.dot_out) {
+          if (g.dot_is_x) dw = xi;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) dsum[v] = fma(dw.v[v], out.v[v], dsum[v]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);      // this block of stage s is done (16 arrivals free the stage)
+    }
+  }
+
+  if (g.dot_out) {
+    __syncthreads();
+    spmm_dot_epilogue<T, VEC, 4, CW, kWiThreads>(dsum, CW, g.c0, g.partials, g.counter, g.dot_out);
+  }
+}
+
+// ---- value stream in the warp-interleaved layout: aw[wptr[blk] + 32 t + lane] = a[rowptr[row] + 4t + (lane & 3)] or 0 ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+lap_wi_values_kernel(const int* __restrict__ rowptr, const int* __restrict__ wptr, const T* __restrict__ a, int64_t n,
+                     int64_t nblocks, T* __restrict__ aw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blk >= nblocks) return;
+  const int64_t row = (blk >> 4) * kWiRows + (blk & 15) * 8 + (lane >> 2);
+  int p0 = 0, len = 0;
+  if (row < n) { p0 = rowptr[row]; len = rowptr[row + 1] - p0; }
+  const int o = wptr[blk];
+  const int steps = (wptr[blk + 1] - o) >> 5;
+  for (int t = 0; t < steps; ++t) {
+    const int e = 4 * t + (lane & 3);
+    aw[(int64_t)o + 32 * t + lane] = e < len ? ld_stream(a + p0 + e) : T(0);
+  }
+}
+
+template <typename T>
+static int lap_wi_values(const int* rowptr, const int* wptr, const T* a, int64_t n, T* aw, cudaStream_t st) {
+  MGP_CHECK_ARG(rowptr && wptr && a && aw && n > 0, "lap_wi_values: bad arguments");
+  const int64_t nblocks = ceil_div(n, (int64_t)kWiRows) * 16;
+  lap_wi_values_kernel<T><<<(unsigned)ceil_div(nblocks, (int64_t)8), 256, 0, st>>>(rowptr, wptr, a, n, nblocks, aw);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+template <typename T>
+static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw, const T* diag, const int* hptr,
+                       const int* hcol, int tile_rows, int lmax, int wnzmax, int hmax, const T* shift, const T* post, const int* xmap,
+                       const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int ncols, const T* dot_with,
+                       T* dot_out, void* dot_ws, cudaStream_t st) {
+  constexpr int R = kWiRows;
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int CW = 4 * VEC;
+  MGP_CHECK_ARG(wptr && wcol && aw && diag && hptr && hcol && x && y, "lap_spmm_wi: null pointer");
+  MGP_CHECK_ARG(((uintptr_t)wptr) % 16 == 0 && ((uintptr_t)hptr) % 16 == 0 && ((uintptr_t)hcol) % 16 == 0 && ((uintptr_t)wcol) % 16 == 0 &&
+                    ((uintptr_t)aw) % 16 == 0,
+                "lap_spmm_wi: wptr / hptr / hcol / wcol / aw must be 16-byte aligned (bulk copies)");
+  MGP_CHECK_ARG(hmax >= 0 && hmax % 4 == 0 && lmax >= tile_rows + hmax, "lap_spmm_wi: bad halo statistics hmax=%d lmax=%d", hmax, lmax);
+  MGP_CHECK_ARG(tile_rows == R, "lap_spmm_wi: this build supports tile_rows == %d (got %d)", R, tile_rows);
+  MGP_CHECK_ARG(n > 0 && ncols > 0 && ldx >= ncols && ldy >= ncols, "lap_spmm_wi: bad shape");
+  MGP_CHECK_ARG(x != y, "lap_spmm_wi: X and Y must not alias");
+  MGP_CHECK_ARG((dot_out == nullptr) || (dot_with && dot_ws), "lap_spmm_wi: dot epilogue needs dot_with and dot_ws");
+  MGP_CHECK_ARG(lmax >= R && lmax <= 65535 && wnzmax >= 0 && wnzmax % 32 == 0, "lap_spmm_wi: bad tile statistics lmax=%d wnzmax=%d",
+                lmax, wnzmax);
+  const bool ok = (ncols % CW == 0) && (ldx % VEC == 0) && (ldy % VEC == 0) && (((uintptr_t)x) % 16 == 0) &&
+                  (((uintptr_t)y) % 16 == 0) && (dot_with == nullptr || ((uintptr_t)dot_with) % 16 == 0);
+  if (!ok) return MGP_EUNSUPPORTED;
+  WiArgs<T> g;
+  g.wptr = wptr; g.wcol = wcol; g.aw = aw; g.diag = diag; g.hptr = hptr; g.hcol = hcol; g.shift = shift;
+  g.post = post; g.xmap = xmap; g.ymap = ymap; g.x = x; g.ldx = ldx; g.y = y; g.ldy = ldy; g.n = n;
+  g.ntiles = (int)ceil_div(n, (int64_t)R);
+  g.lmax = (lmax + 3) & ~3;
+  g.nzcap = wnzmax + 32;                       // the consumers' look-ahead loads read one step past a warp block
+  g.hmax = hmax > 0 ? hmax : 4;
+  const size_t one = wi_stage_bytes<T>(g.lmax, g.nzcap);
+  const size_t rings = wi_ring_bytes(g.hmax);
+  g.stages = (3 * one + rings <= kWiSmemLimit) ? 3 : 2;
+  const size_t smem = g.stages * one + rings;
+  if (smem > kWiSmemLimit) return MGP_EUNSUPPORTED;
+  g.dot_with = dot_out ? dot_with : nullptr;
+  g.dot_out = dot_out;
+  g.counter = dot_out ? reinterpret_cast<unsigned int*>(dot_ws) : nullptr;
+  g.partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
+  g.dot_is_x = (dot_out && dot_with == x) ? 1 : 0;
+  { const char* dbg = getenv("MGP_WI_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
+  auto kern = lap_spmm_wi_kernel<T>;
+  static size_t configured = 0;   // per instantiation
+  if (smem > configured) {
+    MGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int64_t blocks = kNumSMs;
+  if (blocks > g.ntiles) blocks = g.ntiles;
+  for (int c0 = 0; c0 < ncols; c0 += CW) {
+    g.c0 = c0;
+    kern<<<(unsigned)blocks, kWiThreads, smem, st>>>(g);
+    MGP_LAUNCH_CHECK();
+  }
+  return MGP_OK;
+}
+
+}  // namespace mgp
+
+extern "C" {
+
+int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const float* a, int64_t n, float* aw, void* stream) {
+  return mgp::lap_wi_values<float>(rowptr, wptr, a, n, aw, (cudaStream_t)stream);
+}
+int mgp_lap_wi_values_f64(const int32_t* rowptr, const int32_t* wptr, const double* a, int64_t n, double* aw, void* stream) {
+  return mgp::lap_wi_values<double>(rowptr, wptr, a, n, aw, (cudaStream_t)stream);
+}
+
+int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
+                        const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
+                        const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
+                        int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
+                        void* stream) {
+  return mgp::lap_spmm_wi<float>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
+                                 ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
+}
+int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag,
+                        const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax,
+                        const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
+                        int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
+                        void* dot_ws, void* stream) {
+  return mgp::lap_spmm_wi<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
+                                  ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

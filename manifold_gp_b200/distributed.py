@@ -109,6 +109,17 @@ class LocalStructure:
             self.tiles = dict(lcol=t["lcol"], halo_ptr=t["halo_ptr"][t0:t1 + 1],
                               halo_col=plan.to_local(t["halo_col"]).to(torch.int32).contiguous(),
                               lmax=t["lmax"], nzmax=t["nzmax"], rows=t["rows"], halo_total=t["halo_total"])
+            if "prowptr" in t:   # padded streams of the pipelined kernel: global positions again, arrays unsliced
+                self.tiles.update(prowptr=t["prowptr"][lo:hi + 1], plcol=t["plcol"], nnzp=t["nnzp"], pnzmax=t["pnzmax"])
+            if "wptr" in t:      # warp-interleaved streams (v5): 16 blocks per tile, global stream positions, streams unsliced;
+                # the metadata arrays are copied (the kernel bulk-copies them in 32-tile chunks: alignment + padding)
+                nt = t1 - t0
+                wloc = torch.full((512 * ((nt + 31) // 32) + 4,), int(t["wptr"][16 * t1]), dtype=torch.int32, device=self.device)
+                wloc[:16 * nt + 1] = t["wptr"][16 * t0:16 * t1 + 1]
+                hloc = torch.full((32 * ((nt + 31) // 32) + 4,), int(t["hptr"][t1]), dtype=torch.int32, device=self.device)
+                hloc[:nt + 1] = t["hptr"][t0:t1 + 1]
+                self.tiles.update(wptr=wloc, wcol=t["wcol"], nnzw=t["nnzw"], wnzmax=t["wnzmax"], hptr=hloc,
+                                  hcol=plan.to_local(t["hcol"]).to(torch.int32).contiguous(), hmax=t["hmax"])
         self._gst = gst
         self.TILED_SMEM_LIMIT = gst.TILED_SMEM_LIMIT
 
@@ -122,6 +133,12 @@ class LocalStructure:
         if self._dot_ws is None:
             self._dot_ws = torch.zeros_like(self._gst.dot_ws())
         return self._dot_ws
+
+    def padded_values(self, a):
+        return self._gst.padded_values(a)
+
+    def wi_values(self, a):
+        return self._gst.wi_values(a)    # built from the GLOBAL rowptr / wptr: stream positions are global
 
 
 class DistPrecision:

@@ -60,6 +60,102 @@ def attach_permutation(idx: torch.Tensor, perm: torch.Tensor) -> None:
         pass
 
 
+def padded_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int):
+    """Padded entry streams for the pipelined kernel (csrc/lap_spmm_pipe.cu): every row holds a multiple of 4 entries, every
+    tile of ``R`` rows starts at a multiple of 8 (the last row of a tile absorbs the tile's slack); padding entries carry
+    the row's own tile-local index (their value is 0 in the padded value array).  Pure index plumbing (any device)."""
+    dev = rowptr.device
+    ntiles = (n + R - 1) // R
+    rp = rowptr.to(torch.int64)
+    rowlen = rp[1:] - rp[:-1]
+    nnz = int(rp[-1])
+    plen = (rowlen + 3) & ~3
+    rid = torch.arange(n, device=dev, dtype=torch.int64)
+    tsum = torch.zeros(ntiles, dtype=torch.int64, device=dev)
+    tsum.index_add_(0, rid // R, plen)
+    slack = ((tsum + 7) & ~7) - tsum
+    last_row = torch.clamp(torch.arange(1, ntiles + 1, device=dev, dtype=torch.int64) * R, max=n) - 1
+    plen[last_row] += slack
+    prowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(plen, 0, out=prowptr[1:])
+    nnzp = int(prowptr[-1])
+    if nnzp >= 2 ** 31 - 16:
+        return None
+    plcol = torch.zeros(nnzp + 8, dtype=torch.int16, device=dev)
+    plcol[:nnzp] = torch.repeat_interleave((rid % R).to(torch.int16), plen)
+    rows = torch.repeat_interleave(rid, rowlen)
+    dst = prowptr[:-1][rows] + (torch.arange(nnz, device=dev, dtype=torch.int64) - rp[:-1][rows])
+    plcol[dst] = lcol16
+    ptile = prowptr[torch.arange(0, n + R, R, device=dev).clamp_max(n)]
+    return dict(prowptr=prowptr.to(torch.int32).contiguous(), plcol=plcol, nnzp=nnzp, pnzmax=int((ptile[1:] - ptile[:-1]).max()))
+
+
+def wi_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 128):
+    """Warp-interleaved entry streams of the v5 SpMM kernel (csrc/lap_spmm_wi.cu).  A tile of R = 128 rows is walked by 16
+    warps of 8 row slots x 4 lanes; warp block b = 16 * tile + w owns stream positions [wptr[b], wptr[b+1]) and position
+    wptr[b] + 32 t + lane holds nonzero 4t + (lane & 3) of row 128 tile + 8 w + (lane >> 2) -- exactly the order in which
+    the lanes consume them.  Every block is padded to a whole number of 32-entry steps (the longest row of the block,
+    rounded up to 4 entries); padding entries have value 0 and a tile-local index of the parity their position expects
+    (the row's neighbour r ^ 1), so they cause no extra bank conflicts.  Pure index plumbing (any device)."""
+    assert R == 128
+    dev = rowptr.device
+    ntiles = (n + R - 1) // R
+    nblk = ntiles * 16
+    rp = rowptr.to(torch.int64)
+    rowlen = torch.zeros(ntiles * R, dtype=torch.int64, device=dev)
+    rowlen[:n] = rp[1:] - rp[:-1]
+    steps = ((rowlen + 3) >> 2).view(nblk, 8).amax(1)                         # 32-entry steps per warp block
+    wptr = torch.zeros(nblk + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(steps * 32, 0, out=wptr[1:])
+    nnzw = int(wptr[-1])
+    if nnzw >= 2 ** 31 - 64:
+        return None
+    # padding index per position: neighbour row of the slot's row (valid and of opposite parity), 0 for rows beyond n
+    blk = torch.repeat_interleave(torch.arange(nblk, device=dev, dtype=torch.int64), steps * 32)
+    pos = torch.arange(nnzw, device=dev, dtype=torch.int64)
+    lane = (pos - wptr[blk]) & 31
+    rloc = (blk & 15) * 8 + (lane >> 2)
+    row = (blk >> 4) * R + rloc
+    nb = rloc ^ 1
+    pad = torch.where((blk >> 4) * R + nb < n, nb, rloc)
+    pad = torch.where(row < n, pad, torch.zeros_like(pad))
+    wcol = torch.zeros(nnzw + 64, dtype=torch.int16, device=dev)
+    wcol[:nnzw] = pad.to(torch.int16)
+    del blk, pos, lane, rloc, row, nb, pad
+    nnz = int(rp[-1])
+    rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), rowlen[:n])
+    e = torch.arange(nnz, device=dev, dtype=torch.int64) - rp[:-1][rows]
+    b = (rows // R) * 16 + (rows % R) // 8
+    dst = wptr[b] + (e >> 2) * 32 + (rows & 7) * 4 + (e & 3)
+    wcol[dst] = lcol16
+    tile_tot = wptr[16::16] - wptr[:-1:16]
+    # the kernel bulk-copies metadata in chunks of 32 tiles: pad so every chunk copy (516 ints) stays in bounds
+    wpad = torch.full((512 * ((ntiles + 31) // 32) + 4,), nnzw, dtype=torch.int32, device=dev)
+    wpad[:nblk + 1] = wptr.to(torch.int32)
+    return dict(wptr=wpad, wcol=wcol, nnzw=nnzw, wnzmax=int(tile_tot.max()))
+
+
+def wi_halo_lists(halo_ptr: torch.Tensor, halo_col: torch.Tensor, ntiles: int):
+    """Halo id lists for the v5 kernel: every tile's list padded to a multiple of 4 ids (16-byte bulk copies) by repeating
+    its last id (a valid row; 0 for empty lists is never read), offsets array padded to whole 32-tile chunks + 4."""
+    dev = halo_ptr.device
+    hp = halo_ptr.to(torch.int64)
+    hlen = hp[1:] - hp[:-1]
+    hlen4 = (hlen + 3) & ~3
+    hptr4 = torch.zeros(ntiles + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(hlen4, 0, out=hptr4[1:])
+    total4 = int(hptr4[-1])
+    tile = torch.repeat_interleave(torch.arange(ntiles, device=dev, dtype=torch.int64), hlen4)
+    k = torch.arange(total4, device=dev, dtype=torch.int64) - hptr4[tile]
+    src = hp[tile] + torch.minimum(k, (hlen[tile] - 1).clamp_min(0))
+    hcol4 = torch.zeros(total4 + 4, dtype=torch.int32, device=dev)
+    if total4:
+        hcol4[:total4] = halo_col[src].to(torch.int32)
+    hpad = torch.full((32 * ((ntiles + 31) // 32) + 4,), total4, dtype=torch.int32, device=dev)
+    hpad[:ntiles + 1] = hptr4.to(torch.int32)
+    return dict(hptr=hpad, hcol=hcol4, hmax=int(hlen4.max()) if ntiles else 0)
+
+
 class GraphStructure:
     """rowptr[n+1], col[nnz], eid[nnz] (int32) with nnz = 2M; column indices ascending inside a row.
 
@@ -156,7 +252,42 @@ class GraphStructure:
                           halo_col=torch.cat([(ukey & 0xFFFFFFFF).to(torch.int32),
                                               torch.zeros(1, dtype=torch.int32, device=dev)]).contiguous(),
                           lmax=lmax, nzmax=nzmax, rows=R, halo_total=int(ukey.numel()))
+        padded = padded_streams(self.rowptr, lcol16[:self.nnz], n, R)
+        if padded is not None:
+            self.tiles.update(padded)
+        wi = wi_streams(self.rowptr, lcol16[:self.nnz], n, R)
+        if wi is not None:
+            self.tiles.update(wi)
+            self.tiles.update(wi_halo_lists(self.tiles["halo_ptr"], self.tiles["halo_col"], ntiles))
         return self.tiles
+
+    def _value_layout(self, a: torch.Tensor, kind: str) -> torch.Tensor:
+        """``a`` (CSR entry order, one bandwidth) in the stream layout of a pipelined kernel (``kind``: "pad" = v4 padded
+        rows, "wi" = v5 warp-interleaved).  Cached per value array: the cache holds a reference to ``a`` itself (so its
+        address cannot be recycled while the entry lives) and matches on (address, version), which ``a.detach()`` shares."""
+        cache = self.__dict__.setdefault("_layout_cache", [])
+        for k, ref, ver, out in cache:
+            if k == kind and ref.data_ptr() == a.data_ptr() and ver == a._version and ref.dtype == a.dtype and ref.numel() == a.numel():
+                return out
+        t = self.tiles
+        sfx = _lib.suffix(a.dtype)
+        if kind == "pad":
+            out = torch.empty(t["nnzp"] + 8, dtype=a.dtype, device=a.device)
+            out[t["nnzp"]:].zero_()
+            _lib.call("mgp_lap_pad_values_" + sfx, ptr(self.rowptr), ptr(t["prowptr"]), ptr(a), c_int64(self.n), ptr(out), stream())
+        else:
+            out = torch.empty(t["nnzw"] + 64, dtype=a.dtype, device=a.device)
+            out[t["nnzw"]:].zero_()
+            _lib.call("mgp_lap_wi_values_" + sfx, ptr(self.rowptr), ptr(t["wptr"]), ptr(a), c_int64(self.n), ptr(out), stream())
+        cache.append((kind, a.detach(), a._version, out))
+        del cache[:-4]
+        return out
+
+    def padded_values(self, a: torch.Tensor) -> torch.Tensor:
+        return self._value_layout(a, "pad")
+
+    def wi_values(self, a: torch.Tensor) -> torch.Tensor:
+        return self._value_layout(a, "wi")
 
     def tiled_ok(self, dtype, cw: int) -> bool:
         """Does the widest pass for ``cw`` columns of ``dtype`` fit the shared-memory budget of the tiled kernel?"""
@@ -240,7 +371,7 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 
 
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
-SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled"  (tests force each; "auto" prefers the tiled kernel when it fits)
+SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi"  (tests force each; "auto": wi, else pipe, else tiled, else csr)
 
 
 def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
@@ -265,13 +396,42 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
     # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
     # kernel (X served from L1/L2) is faster
-    use_tiled = SPMM_KERNEL != "csr" and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL == "tiled")
-    if SPMM_KERNEL == "tiled" and not use_tiled:
+    use_tiled = SPMM_KERNEL != "csr" and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi"))
+    if SPMM_KERNEL in ("tiled", "pipe", "wi") and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
         t = st.tiles
         if out is None:
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
+        if pre is None and "wptr" in t and SPMM_KERNEL in ("auto", "wi"):
+            aw = st.wi_values(a)
+            rc = _lib.call_rc("mgp_lap_spmm_wi_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag),
+                              ptr(t["hptr"]), ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
+                              c_int32(t["wnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
+                              ptr(st.perm32 if x_external else None),
+                              ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
+                              c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())
+            if rc == 0:
+                return out
+            if rc != _lib.MGP_EUNSUPPORTED:
+                raise RuntimeError(f"mgp_lap_spmm_wi_{sfx} failed ({rc}): {_lib.last_error()}")
+        if SPMM_KERNEL == "wi":
+            raise RuntimeError("lap_spmm: warp-interleaved kernel requested but this call does not qualify (pre scaling, "
+                               "column count not a multiple of one 64-byte row, alignment or shared memory)")
+        if pre is None and "prowptr" in t and SPMM_KERNEL in ("auto", "pipe"):
+            ap = st.padded_values(a)
+            rc = _lib.call_rc("mgp_lap_spmm_pipe_" + sfx, ptr(t["prowptr"]), ptr(t["plcol"]), ptr(ap), ptr(diag),
+                              ptr(t["halo_ptr"]), ptr(t["halo_col"]), c_int32(t["rows"]), c_int32(t["lmax"]),
+                              c_int32(t["pnzmax"]), ptr(shift_t), ptr(post), ptr(st.perm32 if x_external else None),
+                              ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
+                              c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())
+            if rc == 0:
+                return out
+            if rc != _lib.MGP_EUNSUPPORTED:
+                raise RuntimeError(f"mgp_lap_spmm_pipe_{sfx} failed ({rc}): {_lib.last_error()}")
+        if SPMM_KERNEL == "pipe":
+            raise RuntimeError("lap_spmm: pipelined kernel requested but this call does not qualify (pre scaling, column "
+                               "count / alignment or shared memory)")
         rc = _lib.call_rc("mgp_lap_spmm_tiled_" + sfx, ptr(st.rowptr), ptr(t["lcol"]), ptr(a), ptr(diag), ptr(t["halo_ptr"]),
                           ptr(t["halo_col"]), c_int32(t["rows"]), c_int32(t["lmax"]), c_int32(t["nzmax"]), ptr(shift_t),
                           ptr(pre), ptr(post), ptr(st.perm32 if x_external else None),

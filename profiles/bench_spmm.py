@@ -32,23 +32,36 @@ def timeit(fn, reps=30, warm=5):
     return ev0.elapsed_time(ev1) * 1e3 / reps
 
 
-res = {}
+ONLY = os.environ.get("BENCH_KERNELS", "").split(",") if os.environ.get("BENCH_KERNELS") else None
+t = st.tiles
+res = {"tiles": {k: t[k] for k in ("lmax", "nzmax", "pnzmax", "wnzmax", "nnzp", "nnzw", "halo_total") if k in t}, "nnz": nnz}
 shift = prec._shift()
+MODES = [int(m) for m in os.environ.get("WI_MODES", "").split(",") if m]
+if MODES:   # A/B of the v5 kernel's experiment switches inside ONE process (same box, same clocks)
+    P = torch.randn(n, 16, device=dev); V = torch.empty_like(P)
+    graph.SPMM_KERNEL = "wi"
+    for rep in range(2):
+        for m in MODES:
+            os.environ["MGP_WI_DEBUG"] = str(m)
+            res[f"wi_mode{m}_rep{rep}"] = round(timeit(lambda: graph.lap_spmm(st, a, diag, P, shift=shift, out=V)), 1)
+    print(json.dumps(res)); sys.exit(0)
 for c in (1, 4, 8, 16):
     P = torch.randn(n, c, device=dev); V = torch.empty_like(P)
     dot = torch.zeros(c, device=dev)
     alg = nnz * 8 + n * (2 * c * 4 + 4)
-    for kern in ("csr", "tiled", "pipe"):
-        graph.SPMM_KERNEL = "tiled" if kern == "pipe" else kern
-        os.environ["MGP_SPMM_PIPE"] = "1" if kern == "pipe" else "0"
+    for kern in ("csr", "tiled", "pipe", "wi"):
+        if (kern == "pipe" and c % 4) or (kern == "wi" and c % 16) or (ONLY and kern not in ONLY):
+            continue
+        graph.SPMM_KERNEL = kern
         t = timeit(lambda: graph.lap_spmm(st, a, diag, P, shift=shift, out=V))
         td = timeit(lambda: graph.lap_spmm(st, a, diag, P, shift=shift, out=V, dot_with=P, dot_out=dot))
         res[f"spmm_{kern}_c{c}"] = {"us": round(t, 1), "us_with_dot": round(td, 1), "alg_GBs": round(alg / t / 1e3, 0)}
     graph.SPMM_KERNEL = "auto"
-    os.environ["MGP_SPMM_PIPE"] = "1"
 # CG vector kernels via a short solve timing split
 import warnings
 warnings.simplefilter("ignore")
+if os.environ.get("BENCH_NO_CG"):
+    print(json.dumps(res)); sys.exit(0)
 B = torch.randn(n, 16, device=dev)
 for _ in range(2):
     solvers.linear_cg(prec, B, tolerance=0.0, max_iter=50, max_tridiag_iter=20)

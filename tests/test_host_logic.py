@@ -1,0 +1,80 @@
+"""Host-side index plumbing that needs no GPU: the padded entry streams of the pipelined SpMM kernel."""
+import torch
+
+
+def test_padded_streams_layout():
+    from manifold_gp_b200.graph import padded_streams
+    g = torch.Generator().manual_seed(0)
+    for n, R, maxlen in ((300, 128, 9), (128, 128, 40), (1000, 128, 3), (5, 128, 7)):
+        rowlen = torch.randint(0, maxlen, (n,), generator=g)
+        rowptr = torch.zeros(n + 1, dtype=torch.int32)
+        rowptr[1:] = torch.cumsum(rowlen, 0)
+        nnz = int(rowptr[-1])
+        lcol = torch.randint(0, 400, (nnz,), generator=g).to(torch.int16)
+        t = padded_streams(rowptr, lcol, n, R)
+        pr, pl = t["prowptr"].long(), t["plcol"]
+        assert pl.numel() == t["nnzp"] + 8 and t["nnzp"] % 8 == 0 and t["pnzmax"] % 8 == 0
+        assert all(int(pr[i]) % 8 == 0 for i in range(0, n, R))             # tiles start at multiples of 8 entries
+        assert bool(((pr[1:] - pr[:-1]) % 4 == 0).all())                     # rows hold multiples of 4 entries
+        for r in range(n):
+            L, q0, q1 = int(rowlen[r]), int(pr[r]), int(pr[r + 1])
+            assert torch.equal(pl[q0:q0 + L], lcol[int(rowptr[r]):int(rowptr[r]) + L])
+            assert bool((pl[q0 + L:q1] == r % R).all())                      # padding points at the row itself
+
+
+def test_wi_streams_layout():
+    """Warp-interleaved streams: position wptr[b] + 32 t + lane <-> nonzero 4t + (lane & 3) of row 128 tile + 8 w + lane // 4."""
+    from manifold_gp_b200.graph import wi_streams
+    g = torch.Generator().manual_seed(1)
+    R = 128
+    for n, maxlen in ((300, 9), (128, 40), (1000, 3), (5, 7), (257, 50)):
+        rowlen = torch.randint(0, maxlen, (n,), generator=g)
+        rowptr = torch.zeros(n + 1, dtype=torch.int32)
+        rowptr[1:] = torch.cumsum(rowlen, 0)
+        nnz = int(rowptr[-1])
+        lcol = torch.randint(0, 400, (nnz,), generator=g).to(torch.int16)
+        t = wi_streams(rowptr, lcol, n, R)
+        wptr, wcol = t["wptr"].long(), t["wcol"]
+        ntiles = (n + R - 1) // R
+        assert wptr.numel() == 512 * ((ntiles + 31) // 32) + 4          # padded to whole 32-tile metadata chunks
+        assert bool((wptr[16 * ntiles:] == t["nnzw"]).all())
+        assert wcol.numel() == t["nnzw"] + 64 and t["wnzmax"] % 32 == 0
+        seen = 0
+        for blk in range(ntiles * 16):
+            o, size = int(wptr[blk]), int(wptr[blk + 1] - wptr[blk])
+            assert size % 32 == 0
+            steps = size // 32
+            for lane in range(32):
+                rl = (blk % 16) * 8 + lane // 4
+                row = (blk // 16) * R + rl
+                L = int(rowlen[row]) if row < n else 0
+                assert (L + 3) // 4 <= steps
+                for tt in range(steps):
+                    e, pos = 4 * tt + (lane & 3), o + 32 * tt + lane
+                    if e < L:
+                        assert int(wcol[pos]) == int(lcol[int(rowptr[row]) + e])
+                        seen += 1
+                    else:   # padding: neighbour row (opposite parity) when it exists, 0 for rows beyond n
+                        exp = 0 if row >= n else ((rl ^ 1) if (blk // 16) * R + (rl ^ 1) < n else rl)
+                        assert int(wcol[pos]) == exp
+        assert seen == nnz
+
+
+def test_wi_halo_lists_padding():
+    from manifold_gp_b200.graph import wi_halo_lists
+    g = torch.Generator().manual_seed(2)
+    for ntiles in (1, 3, 40):
+        hlen = torch.randint(0, 11, (ntiles,), generator=g)
+        hptr = torch.zeros(ntiles + 1, dtype=torch.int32)
+        hptr[1:] = torch.cumsum(hlen, 0)
+        hcol = torch.randint(0, 10000, (int(hptr[-1]) + 1,), generator=g).to(torch.int32)
+        t = wi_halo_lists(hptr, hcol, ntiles)
+        hp, hc = t["hptr"].long(), t["hcol"]
+        assert hp.numel() == 32 * ((ntiles + 31) // 32) + 4 and t["hmax"] % 4 == 0
+        assert bool((hp[:ntiles + 1] % 4 == 0).all()) and bool((hp[ntiles:] == hp[ntiles]).all())
+        for k in range(ntiles):
+            L, a, b = int(hlen[k]), int(hp[k]), int(hp[k + 1])
+            assert b - a == (L + 3) // 4 * 4 and b - a <= t["hmax"]
+            assert torch.equal(hc[a:a + L], hcol[int(hptr[k]):int(hptr[k]) + L])
+            if L:
+                assert bool((hc[a + L:b] == hcol[int(hptr[k]) + L - 1]).all())   # padding repeats the last (valid) id
