@@ -246,6 +246,19 @@ int mgp_cg_update_f32(float* x, float* r, const float* p, const float* v, int64_
                       float* state, float* hist, int32_t max_hist, void* ws, void* stream);
 int mgp_cg_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
                       double* state, double* hist, int32_t max_hist, void* ws, void* stream);
+
+/* Split form of the update (8 instead of 9 vector passes per iteration; same arithmetic and scalars):
+ *   mgp_cg_rupdate : r -= alpha v, rz' = |r|^2, then the scalar step (beta, norms, flags, history) -- or, with rbuf != NULL,
+ *                    the column sums are exported to rbuf for an all-reduce and mgp_cg_dist_scalars(what=2) finishes;
+ *   mgp_cg_pxupdate: x += alpha p, p = r + beta p (alpha, beta from state).  Runs once more after the iteration that set
+ *                    the done flag (the x update of that iteration) and is a no-op afterwards.
+ * Iteration: matvec (+ p^T A p) -> mgp_cg_alpha -> mgp_cg_rupdate -> mgp_cg_pxupdate. */
+int mgp_cg_rupdate_f32(float* r, const float* v, int64_t ld, int64_t n, int32_t ncols, float* state, float* hist,
+                       int32_t max_hist, float* rbuf, void* ws, void* stream);
+int mgp_cg_rupdate_f64(double* r, const double* v, int64_t ld, int64_t n, int32_t ncols, double* state, double* hist,
+                       int32_t max_hist, double* rbuf, void* ws, void* stream);
+int mgp_cg_pxupdate_f32(float* x, float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream);
+int mgp_cg_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream);
 /* Multi-GPU split of the two reductions (rows partitioned across ranks): the kernels export their LOCAL column sums to
  * rbuf[ncols]; the host all-reduces rbuf (NCCL) and mgp_cg_dist_scalars finishes the scalar bookkeeping on every rank
  * (what = 0: right-hand-side norms, 1: initial residual / state, 2: one iteration's beta, norms, flags, done).

@@ -66,6 +66,10 @@ _SIG = {
     "mgp_cg_alpha_f64": (c_int32, [P, P, c_int64, c_int64, c_int32, c_int32, P, P, P]),
     "mgp_cg_update_f32": (c_int32, [P, P, P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P]),
     "mgp_cg_update_f64": (c_int32, [P, P, P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P]),
+    "mgp_cg_rupdate_f32": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P, P]),
+    "mgp_cg_rupdate_f64": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P, P]),
+    "mgp_cg_pxupdate_f32": (c_int32, [P, P, P, c_int64, c_int64, c_int32, P, P]),
+    "mgp_cg_pxupdate_f64": (c_int32, [P, P, P, c_int64, c_int64, c_int32, P, P]),
     "mgp_cg_dist_norm2_f32": (c_int32, [P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_cg_dist_norm2_f64": (c_int32, [P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_cg_dist_init_f32": (c_int32, [P, c_int64, P, P, P, c_int64, c_int64, c_int32, P, P, P, P]),

@@ -15,7 +15,7 @@
 namespace mgp {
 
 enum : int { S_RHSNORM = 0, S_RZ, S_PAP, S_ALPHA, S_BETA, S_RESID, S_RHSZERO, S_CONV, S_NARR };
-enum : int { K_MEAN = 0, K_DONE, K_ITER, K_TOL, K_EPS, K_STOP, K_MINITER, K_NTRIMIN, K_MAXITER, K_NSCAL = 16 };
+enum : int { K_MEAN = 0, K_DONE, K_ITER, K_TOL, K_EPS, K_STOP, K_MINITER, K_NTRIMIN, K_MAXITER, K_XPEND, K_NSCAL = 16 };
 
 constexpr int kCgBlock = 256;
 constexpr int kCgMaxCols = 128;
@@ -182,6 +182,7 @@ __device__ __forceinline__ void cg_finish_update(T* state, const T* tot, int nco
     const T mean = s / T(ncols);
     k[K_MEAN] = mean;
     k[K_ITER] = T(it + 1);
+    k[K_XPEND] = T(1);      // x += alpha p of this iteration is still to be applied (split-update path: cg_pxupdate)
     // published stopping rule: k >= min(10, max_iter-1) and mean residual < tol and the tridiagonal has enough rows
     const bool tri_pending = (k[K_NTRIMIN] > T(0)) && (T(it) < k[K_NTRIMIN]);
     if (T(it) >= k[K_MINITER] && mean < k[K_TOL] && !tri_pending) k[K_DONE] = T(1);
@@ -552,6 +553,199 @@ static int cg_update(T* x, T* r, const T* p, const T* v, int64_t ld, int64_t n, 
   return MGP_OK;
 }
 
+
+// ---- split update (8 instead of 9 vector passes per iteration) ---------------------------------------------------------
+//   cg_rupdate : r -= alpha v ; rz' = |r|^2 ; scalars            (reads r, v; writes r)
+//   cg_pxupdate: x += alpha p ; p = r + beta p                   (reads x, p, r; writes x, p)
+// x only needs alpha_k and p_k, both still available when p is rewritten, so its update rides on the pass that reads p
+// anyway.  alpha_k is kept in state[S_ALPHA] by the scalar step; K_XPEND says "the x update of the last executed
+// iteration is pending", so the pass still runs once after the iteration that set the done flag and never again.
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_rupdate_vec_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_t n, int ncols, T* __restrict__ state,
+                      T* __restrict__ hist, int max_hist, void* ws, T* __restrict__ rbuf) {
+  using V = typename V16<T>::type;
+  constexpr int N = V16<T>::N;
+  T* k = state + S_NARR * ncols;
+  if (k[K_DONE] != T(0)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) k[K_XPEND] = T(0);
+    return;
+  }
+  CgWs<T> w = cg_ws<T>(ws);
+  __shared__ T al[kCgMaxCols];
+  __shared__ T sm[kCgBlock][N];
+  const int tid = threadIdx.x;
+  const T eps = k[K_EPS];
+  for (int c = tid; c < ld; c += kCgBlock) al[c] = c < ncols ? cg_alpha_of<T>(state, ncols, c, eps) : T(0);
+  __syncthreads();
+  const int c0 = (tid * N) % ld;          // this thread's columns: constant because (blockDim * N) % ld == 0
+  T a[N], acc[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) { a[u] = al[c0 + u]; acc[u] = T(0); }
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* r4 = reinterpret_cast<V*>(r);
+  const V* v4 = reinterpret_cast<const V*>(v);
+#pragma unroll 4
+  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + tid; e < total; e += stride) {
+    T vv[N], rv[N];
+    v16_unpack<T>(__ldcs(v4 + e), vv); v16_unpack<T>(r4[e], rv);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      rv[u] = fma(-a[u], vv[u], rv[u]);
+      acc[u] = fma(rv[u], rv[u], acc[u]);
+    }
+    r4[e] = v16_pack<T>(rv);
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) sm[tid][u] = acc[u];
+  __syncthreads();
+  if (tid < ncols) {
+    const int groups = ld / N;
+    T s = T(0);
+    for (int t = tid / N; t < kCgBlock; t += groups) s += sm[t][tid % N];
+    w.partials[(int64_t)blockIdx.x * ncols + tid] = s;
+  }
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    if (rbuf) cg_export_tot<T>(tot, rbuf, ncols);
+    else cg_finish_update<T>(state, tot, ncols, hist, max_hist);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_pxupdate_vec_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r, int ld, int64_t n, int ncols,
+                       const T* __restrict__ state) {
+  using V = typename V16<T>::type;
+  constexpr int N = V16<T>::N;
+  if (state[S_NARR * ncols + K_XPEND] == T(0)) return;
+  const int c0 = (threadIdx.x * N) % ld;
+  T a[N], b[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    a[u] = (c0 + u) < ncols ? state[S_ALPHA * ncols + c0 + u] : T(0);
+    b[u] = (c0 + u) < ncols ? state[S_BETA * ncols + c0 + u] : T(0);
+  }
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* x4 = reinterpret_cast<V*>(x);
+  V* p4 = reinterpret_cast<V*>(p);
+  const V* r4 = reinterpret_cast<const V*>(r);
+#pragma unroll 4
+  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + threadIdx.x; e < total; e += stride) {
+    T pv[N], rv[N], xv[N];
+    v16_unpack<T>(p4[e], pv); v16_unpack<T>(r4[e], rv); v16_unpack<T>(__ldcs(x4 + e), xv);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      xv[u] = fma(a[u], pv[u], xv[u]);
+      pv[u] = fma(b[u], pv[u], rv[u]);
+    }
+    __stcs(x4 + e, v16_pack<T>(xv));
+    p4[e] = v16_pack<T>(pv);
+  }
+}
+
+// generic layouts (any ld): scalar grid-stride versions of the same two passes
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_rupdate_kernel(T* __restrict__ r, const T* __restrict__ v, int64_t ld, int64_t n, int ncols, int CP, T* __restrict__ state,
+                  T* __restrict__ hist, int max_hist, void* ws, T* __restrict__ rbuf) {
+  T* k = state + S_NARR * ncols;
+  if (k[K_DONE] != T(0)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) k[K_XPEND] = T(0);
+    return;
+  }
+  CgWs<T> w = cg_ws<T>(ws);
+  const int tid = threadIdx.x;
+  const int cl = tid % CP, rl = tid / CP, rpb = kCgBlock / CP;
+  const int ncb = (ncols + CP - 1) / CP;
+  const T eps = k[K_EPS];
+  T acc[kCgMaxCB], alpha[kCgMaxCB];
+#pragma unroll
+  for (int cb = 0; cb < kCgMaxCB; ++cb) {
+    acc[cb] = T(0);
+    const int c = cb * CP + cl;
+    alpha[cb] = (cb < ncb && c < ncols) ? cg_alpha_of<T>(state, ncols, c, eps) : T(0);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * rpb + rl; row < n; row += (int64_t)gridDim.x * rpb) {
+#pragma unroll
+    for (int cb = 0; cb < kCgMaxCB; ++cb) {
+      const int c = cb * CP + cl;
+      if (cb < ncb && c < ncols) {
+        const int64_t o = row * ld + c;
+        const T rn = fma(-alpha[cb], v[o], r[o]);
+        r[o] = rn;
+        acc[cb] = fma(rn, rn, acc[cb]);
+      }
+    }
+  }
+  block_col_reduce<T>(acc, ncb, CP, ncols, w.partials);
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    if (rbuf) cg_export_tot<T>(tot, rbuf, ncols);
+    else cg_finish_update<T>(state, tot, ncols, hist, max_hist);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_pxupdate_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r, int64_t ld, int64_t n, int ncols,
+                   const T* __restrict__ state) {
+  if (state[S_NARR * ncols + K_XPEND] == T(0)) return;
+  const int64_t total = n * ld;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % ld);
+    if (c < ncols) {
+      const T pv = p[e];
+      x[e] = fma(state[S_ALPHA * ncols + c], pv, x[e]);
+      p[e] = fma(state[S_BETA * ncols + c], pv, r[e]);
+    }
+  }
+}
+
+template <typename T>
+static int cg_rupdate(T* r, const T* v, int64_t ld, int64_t n, int ncols, T* state, T* hist, int max_hist, void* ws,
+                      cudaStream_t st, T* rbuf = nullptr) {
+  int rc = cg_check<T>(n, ncols, ld);
+  if (rc) return rc;
+  MGP_CHECK_ARG(r && v && state && ws, "cg_rupdate: null pointer");
+  if (cg_vec_ok<T>(ld, r, v, nullptr, nullptr)) {
+    int64_t g = ceil_div(n * ld / V16<T>::N, (int64_t)kCgBlock * 4);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    cg_rupdate_vec_kernel<T><<<(unsigned)g, kCgBlock, 0, st>>>(r, v, (int)ld, n, ncols, state, hist, max_hist, ws, rbuf);
+    MGP_LAUNCH_CHECK();
+    return MGP_OK;
+  }
+  const int CP = col_lanes(ncols);
+  cg_rupdate_kernel<T><<<cg_grid(n, kCgBlock / CP), kCgBlock, 0, st>>>(r, v, ld, n, ncols, CP, state, hist, max_hist, ws, rbuf);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
+template <typename T>
+static int cg_pxupdate(T* x, T* p, const T* r, int64_t ld, int64_t n, int ncols, const T* state, cudaStream_t st) {
+  MGP_CHECK_ARG(x && p && r && state && n > 0 && ncols > 0 && ld >= ncols, "cg_pxupdate: bad arguments");
+  const int64_t total = n * ld;
+  if (cg_vec_ok<T>(ld, x, p, r, nullptr)) {
+    int64_t gv = ceil_div(total / V16<T>::N, (int64_t)kCgBlock * 4);
+    if (gv > kNumSMs * 8) gv = kNumSMs * 8;
+    if (gv < 1) gv = 1;
+    cg_pxupdate_vec_kernel<T><<<(unsigned)gv, kCgBlock, 0, st>>>(x, p, r, (int)ld, n, ncols, state);
+    MGP_LAUNCH_CHECK();
+    return MGP_OK;
+  }
+  int64_t g = ceil_div(total, (int64_t)kCgBlock);
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  cg_pxupdate_kernel<T><<<(unsigned)g, kCgBlock, 0, st>>>(x, p, r, ld, n, ncols, state);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
 }  // namespace mgp
 
 using namespace mgp;
@@ -590,6 +784,20 @@ int mgp_cg_update_f32(float* x, float* r, const float* p, const float* v, int64_
 int mgp_cg_update_f64(double* x, double* r, const double* p, const double* v, int64_t ld, int64_t n, int32_t ncols,
                       double* state, double* hist, int32_t max_hist, void* ws, void* stream) {
   return cg_update<double>(x, r, p, v, ld, n, ncols, state, hist, max_hist, ws, (cudaStream_t)stream);
+}
+int mgp_cg_rupdate_f32(float* r, const float* v, int64_t ld, int64_t n, int32_t ncols, float* state, float* hist,
+                       int32_t max_hist, float* rbuf, void* ws, void* stream) {
+  return cg_rupdate<float>(r, v, ld, n, ncols, state, hist, max_hist, ws, (cudaStream_t)stream, rbuf);
+}
+int mgp_cg_rupdate_f64(double* r, const double* v, int64_t ld, int64_t n, int32_t ncols, double* state, double* hist,
+                       int32_t max_hist, double* rbuf, void* ws, void* stream) {
+  return cg_rupdate<double>(r, v, ld, n, ncols, state, hist, max_hist, ws, (cudaStream_t)stream, rbuf);
+}
+int mgp_cg_pxupdate_f32(float* x, float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream) {
+  return cg_pxupdate<float>(x, p, r, ld, n, ncols, state, (cudaStream_t)stream);
+}
+int mgp_cg_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream) {
+  return cg_pxupdate<double>(x, p, r, ld, n, ncols, state, (cudaStream_t)stream);
 }
 // ---- multi-GPU split entry points (column sums exported to rbuf, finished by mgp_cg_dist_scalars after the all-reduce) ----
 int mgp_cg_dist_norm2_f32(const float* b, int64_t ldb, int64_t n, int32_t ncols, float* state, float* rbuf, void* ws, void* stream) {

@@ -26,6 +26,17 @@ class PrecisionMaternOperator(LinearOperator):
         # 1/c with c = kappa^2/(2 nu)  (:27); stays on the device
         return (2.0 * self.nu) / self.lengthscale.square().reshape(-1)[:1]
 
+    def _shift_const(self, dtype):
+        """Detached ``_shift()`` for the solver loops, computed once per lengthscale value (not once per matvec)."""
+        ls = self.lengthscale
+        key = (ls.data_ptr(), ls._version, dtype)
+        hit = getattr(self, "_mgp_shift", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, self._shift().detach().to(dtype).contiguous())
+            self._mgp_shift = hit
+        return hit[1]
+
     def _native(self) -> bool:
         return isinstance(self.laplacian, GraphLaplacianOperator)
 
@@ -71,7 +82,7 @@ class PrecisionMaternOperator(LinearOperator):
             x, out, tmp = x[:, :ncols], out[:, :ncols], (tmp[:, :ncols] if tmp is not None else None)
         with torch.no_grad():
             _, _, diag, a = lap._values()
-            shift = self._shift().to(a.dtype)
+            shift = self._shift_const(a.dtype)
             rw = lap.normalization == "randomwalk"
             sq = lap._sqrt_degree if rw else None
             src = x

@@ -105,3 +105,25 @@ class cg_check_interval:
     @classmethod
     def value(cls):
         return cls._global_value
+
+
+class cg_cuda_graph:
+    """Replay the CG iterations of long solves from a captured CUDA graph (one graph = ``cg_check_interval`` iterations).
+    The first chunk always runs eagerly, so short solves never pay for a capture."""
+    _global_value = True
+
+    @classmethod
+    def on(cls):
+        return cls._global_value
+
+    def __init__(self, state: bool = True):
+        self.state = bool(state)
+
+    def __enter__(self):
+        self.prev = cg_cuda_graph._global_value
+        cg_cuda_graph._global_value = self.state
+        return self
+
+    def __exit__(self, *exc):
+        cg_cuda_graph._global_value = self.prev
+        return False

@@ -59,29 +59,52 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
               c_int32(n_tridiag_iter if n_tridiag else 0), ptr(state), ptr(ws), stream())
     pap = state[S_PAP * c:(S_PAP + 1) * c]
     check = max(1, int(settings.cg_check_interval.value()))
+    hist_p, hist_n = ptr(hist), c_int32(max_hist if n_tridiag else 0)
+
+    def iteration():
+        # matvec (p^T A p out of the last SpMM launch) -> r -= alpha v, scalars -> x += alpha p, p = r + beta p
+        if fused:
+            op._mgp_matvec(p, v, tmp, dot_with=p, dot_out=pap, ncols=c)
+            have_pap = 1
+        else:
+            with torch.no_grad():
+                out = op._matmul(p)
+            v.copy_(out)
+            have_pap = 0
+        _lib.call("mgp_cg_alpha_" + sfx, ptr(p), ptr(v), c_int64(ld), c_int64(n), c_int32(c), c_int32(have_pap),
+                  ptr(state), ptr(ws), stream())
+        _lib.call("mgp_cg_rupdate_" + sfx, ptr(r), ptr(v), c_int64(ld), c_int64(n), c_int32(c), ptr(state), hist_p, hist_n,
+                  None, ptr(ws), stream())
+        _lib.call("mgp_cg_pxupdate_" + sfx, ptr(x), ptr(p), ptr(r), c_int64(ld), c_int64(n), c_int32(c), ptr(state), stream())
+
+    # long solves replay whole chunks from a CUDA graph: an iteration is 4 launches of 30-150 us each and the launch gaps
+    # + ctypes calls cost ~5 % of it.  Every kernel is a no-op once the done flag is set, so replaying a full chunk past
+    # convergence is harmless.  The first chunk runs eagerly (attributes set, value layouts cached, short solves unaffected).
+    use_graph = fused and settings.cg_cuda_graph.on() and max_iter >= 4 * check
+    cuda_graph, launches_per_replay = None, 0
     k = 0
     done = 0.0
     scal = S_NARR * c
     while k < max_iter:
         steps = min(check, max_iter - k)
-        for _ in range(steps):
-            if fused:
-                op._mgp_matvec(p, v, tmp, dot_with=p, dot_out=pap, ncols=c)   # pAp comes out of the last SpMM launch
-                have_pap = 1
-            else:
-                with torch.no_grad():
-                    out = op._matmul(p)
-                v.copy_(out)
-                have_pap = 0
-            _lib.call("mgp_cg_alpha_" + sfx, ptr(p), ptr(v), c_int64(ld), c_int64(n), c_int32(c), c_int32(have_pap),
-                      ptr(state), ptr(ws), stream())
-            _lib.call("mgp_cg_update_" + sfx, ptr(x), ptr(r), ptr(p), ptr(v), c_int64(ld), c_int64(n), c_int32(c),
-                      ptr(state), ptr(hist), c_int32(max_hist if n_tridiag else 0), ptr(ws), stream())
-            _lib.call("mgp_cg_pupdate_" + sfx, ptr(p), ptr(r), c_int64(ld), c_int64(n), c_int32(c), ptr(state), stream())
+        if cuda_graph is not None and steps == check:
+            cuda_graph.replay()
+            _lib._dll.mgp_add_launch_count(launches_per_replay)
+        else:
+            for _ in range(steps):
+                iteration()
         k += steps
         done = float(state[scal + K_DONE].item())   # the only device->host read of the loop
         if done != 0.0:
             break
+        if use_graph and cuda_graph is None and max_iter - k >= check:
+            cuda_graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(cuda_graph):
+                for _ in range(check):
+                    iteration()
+            launches_per_replay = _lib.launch_count() - before        # kernels of ours inside one replay
+            _lib._dll.mgp_add_launch_count(-launches_per_replay)      # the capture pass itself executed nothing
     out = torch.empty((n, c), dtype=dt, device=dev)
     _lib.call("mgp_cg_finalize_" + sfx, ptr(x), c_int64(ld), ptr(out), c_int64(c), c_int64(n), c_int32(c), ptr(state), stream())
     if st is not None:

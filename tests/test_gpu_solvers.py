@@ -203,3 +203,39 @@ def test_schur_inner_cg_consumer(golden_k10):
         out = sch.matmul(V[mask])
     tag = gtag(0.5, 1.3, 2, "symmetric", True)
     assert rel_err(out, g[f"{tag}_PschurV"]) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_cg_cuda_graph_replay_is_bitwise_eager(dtype):
+    """Long solves replay chunks of iterations from a CUDA graph; the arithmetic must be exactly the eager loop's
+    (same kernels, same order), including the pending x update after the iteration that sets the done flag and the no-op
+    replays past convergence.  Also: the split update (rupdate / pxupdate) against the oracle's mBCG."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import settings, solvers
+    n, k = 30000, 12
+    x = oracle.datasets.torus(n, seed=5)
+    idx, val = mgp.NearestNeighbors(x.to(DEV)).graph(k)
+    lap = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, torch.tensor([[0.08]], dtype=dtype, device=DEV), "symmetric")
+    prec = mgp.PrecisionMaternOperator(lap, 2, torch.tensor([[1.0]], dtype=dtype, device=DEV))
+    g = torch.Generator().manual_seed(3)
+    B = torch.randn(n, 16, generator=g).to(dtype).to(DEV)
+    tol = 1e-5
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with settings.cg_cuda_graph(False):
+            xe, ie = solvers.linear_cg(prec, B, tolerance=tol, max_iter=3000, return_info=True)
+        with settings.cg_cuda_graph(True):
+            xg, ig = solvers.linear_cg(prec, B, tolerance=tol, max_iter=3000, return_info=True)
+            xg2, ig2 = solvers.linear_cg(prec, B, tolerance=tol, max_iter=3000, return_info=True)
+    assert ie["iterations"] > 4 * settings.cg_check_interval.value(), "problem too easy to exercise the graph path"
+    assert ie["iterations"] == ig["iterations"] == ig2["iterations"] and ie["converged"] and ig["converged"]
+    assert torch.equal(xe, xg) and torch.equal(xg, xg2)
+    res = (prec.matmul(xg) - B).double().norm(dim=0) / B.double().norm(dim=0)
+    assert float(res.max()) < 5e-3
+    # oracle mBCG on the same operator (fp64 only: iteration counts are then identical)
+    if dtype == torch.float64:
+        olap = oracle.LaplacianOracle(val.cpu().double(), idx.cpu(), n, torch.tensor(0.08, dtype=torch.float64), "symmetric", True)
+        ox, oi = oracle.linear_cg(lambda t: oracle.precision_matmul(olap, 2, 1.0, t), B.cpu(), tolerance=tol, max_iter=3000,
+                                  return_info=True)
+        assert oi["iterations"] == ig["iterations"]
+        assert rel_err(xg, ox) < 1e-6
