@@ -183,6 +183,9 @@ int mgp_lap_spmm_pipe_f64(const int32_t* prowptr, const uint16_t* plcol, const d
  * padded list; lmax >= 128 + hmax.  The kernel bulk-copies its metadata in chunks of 32 tiles, so wptr must be readable
  * up to index 512 ceil(ntiles/32) + 4 and hptr up to 32 ceil(ntiles/32) + 4, and wptr / hptr / hcol / wcol / aw must be
  * 16-byte aligned.  mgp_lap_wi_values copies a CSR-ordered value array into the stream layout.
+ * Multi-GPU (row-partitioned): peer_x = DEVICE array of npeers pointers to the ranks' X blocks (peer-mapped, same ldx);
+ * halo ids are then (rank << 26) | row-in-that-rank's-X and the halo rows are fetched straight from the owners over
+ * NVLink (no pack kernel, no all-to-all); the caller separates producer and consumer launches with mgp_peer_barrier.
  * Replaces graph_laplacian_operator.py:117-119 / precision_matern_operator.py:28-32 like the kernels above.
  * Returns MGP_EUNSUPPORTED (nothing launched) when the call does not qualify. */
 int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const float* a, int64_t n, float* aw, void* stream);
@@ -191,12 +194,12 @@ int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* 
                         const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
                         const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
                         int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
-                        void* stream);
+                        const void* peer_x, int32_t npeers, void* stream);
 int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag,
                         const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax,
                         const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
                         int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
-                        void* dot_ws, void* stream);
+                        void* dot_ws, const void* peer_x, int32_t npeers, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
  * Backward of the SpMM w.r.t. the matrix entries (what autograd through torch_sparse.spmm computes for `value`,
@@ -281,6 +284,21 @@ int mgp_cg_dist_scalars_f64(double* state, const double* rbuf, int32_t ncols, in
                             double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, double* hist, int32_t max_hist,
                             void* stream);
 /* p = r + beta p */
+/* Peer-memory (NVLink P2P) variants for the multi-GPU path.  red_ptrs / flag_ptrs: DEVICE arrays of `world` pointers to
+ * every rank's reduction buffer T[2][world][128] and flag array uint32[world] (peer-mapped symmetric allocations, zeroed
+ * once); epoch_ctr: this rank's private uint32 counter in device memory (zeroed once; advanced by the kernels, so a
+ * captured CUDA graph can be replayed).  All ranks must enqueue the same sequence of these calls per (flag, counter) set.
+ *   mgp_cg_peer_scalars: all-reduce of rbuf[ncols] over the ranks (stores into the peers' buffers, epoch flags, sum in rank
+ *                        order => bit-identical totals everywhere) fused with the scalar step `what` (0/1/2 as
+ *                        mgp_cg_dist_scalars, 3 = store the totals as p^T A p).  Replaces an NCCL all-reduce + a kernel.
+ *   mgp_peer_barrier:    cross-GPU barrier on the stream (prior writes of every rank visible to every rank). */
+int mgp_cg_peer_scalars_f32(float* state, const float* rbuf, int32_t ncols, int32_t what, float tolerance, float eps,
+                            float stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, float* hist, int32_t max_hist,
+                            void* red_ptrs, void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream);
+int mgp_cg_peer_scalars_f64(double* state, const double* rbuf, int32_t ncols, int32_t what, double tolerance, double eps,
+                            double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, double* hist, int32_t max_hist,
+                            void* red_ptrs, void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream);
+int mgp_peer_barrier(void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream);
 int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream);
 int mgp_cg_pupdate_f64(double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream);
 /* out[i,c] = x[i,c] * rhs_norm[c]  (un-normalise; out ld ldo) */

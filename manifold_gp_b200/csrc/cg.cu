@@ -746,6 +746,86 @@ static int cg_pxupdate(T* x, T* p, const T* r, int64_t ld, int64_t n, int ncols,
   return MGP_OK;
 }
 
+
+// ---- multi-GPU, peer-memory path: all-reduce of the column sums + scalar step in ONE one-block kernel ---------------------
+// NCCL's all-reduce of 16 floats costs ~37 us per call on the 8 x B200 box (measured, profiles/), more than a rank's whole
+// SpMM at N = 1M / 8.  Here every rank stores its C partial sums straight into slot [my_rank] of every peer's `red` buffer
+// (NVLink P2P stores), publishes an epoch number in every peer's flag array with a system-scope release store, spins until
+// all peers' flags carry the epoch, and adds the world partials in rank order -- so every rank computes bit-identical
+// totals -- before running the same scalar step as the single-GPU kernels.  Two alternating `red` buffers are enough: a
+// peer can only write epoch e+2 after it has seen my flag of epoch e+1, which I set after reading epoch e.
+//   red_ptrs[r]  -> rank r's buffer  T[2][world][kCgMaxCols]           (peer-mapped addresses, device array)
+//   flag_ptrs[r] -> rank r's flags   unsigned[world]                    (one flag per source rank)
+//   epoch        -> this rank's private counter (device memory), advanced by the kernel: CUDA-graph replay safe
+// what: 0 norm, 1 init, 2 update (as cg_scalars_kernel), 3 = store the totals as p^T A p.
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all peers' flags[src] >= epoch (wrap-safe); bounded so a lost peer traps instead of hanging the GPU
+__device__ __forceinline__ void wait_flags(const unsigned int* my_flags, int world, unsigned int epoch) {
+  if ((int)threadIdx.x < world) {
+    unsigned long long spins = 0;
+    while ((int)(ld_acquire_sys(my_flags + threadIdx.x) - epoch) < 0) {
+      if (++spins > (1ull << 25)) __trap();     // ~10 s: a peer died or the call sequences diverged
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_peer_scalars_kernel(T* __restrict__ state, const T* __restrict__ rbuf, int ncols, int what, T tol, T eps, T stop,
+                       int max_iter, int n_tridiag_iter, T* __restrict__ hist, int max_hist, T* const* __restrict__ red_ptrs,
+                       unsigned int* const* __restrict__ flag_ptrs, unsigned int* __restrict__ epoch_ctr, int rank, int world) {
+  __shared__ T tot[kCgMaxCols];
+  const int tid = threadIdx.x;
+  const unsigned int epoch = *epoch_ctr + 1u;
+  const int buf = (int)(epoch & 1u);
+  // 1. my partials -> every rank's red[buf][rank][:]
+  for (int i = tid; i < world * ncols; i += kCgBlock) {
+    const int r = i / ncols, c = i - r * ncols;
+    red_ptrs[r][((size_t)buf * world + rank) * kCgMaxCols + c] = rbuf[c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish, 3. wait for everyone
+  if (tid < world) st_release_sys(flag_ptrs[tid] + rank, epoch);
+  wait_flags(flag_ptrs[rank], world, epoch);
+  // 4. totals in rank order
+  const T* mine = red_ptrs[rank] + (size_t)buf * world * kCgMaxCols;
+  for (int c = tid; c < ncols; c += kCgBlock) {
+    T s = T(0);
+    for (int r = 0; r < world; ++r) s += __ldcv(mine + (size_t)r * kCgMaxCols + c);
+    tot[c] = s;
+  }
+  __syncthreads();
+  if (tid == 0) *epoch_ctr = epoch;
+  if (what == 3) {
+    for (int c = tid; c < ncols; c += kCgBlock) state[S_PAP * ncols + c] = tot[c];
+  } else if (what == 2) {
+    if (state[S_NARR * ncols + K_DONE] == T(0)) cg_finish_update<T>(state, tot, ncols, hist, max_hist);
+  } else if (what == 0) {
+    cg_finish_norm<T>(state, tot, ncols, eps);
+  } else {
+    cg_finish_init<T>(state, tot, ncols, tol, eps, stop, max_iter, n_tridiag_iter);
+  }
+}
+
+// cross-GPU barrier (one block): "everything this rank enqueued before is visible to its peers, and theirs to me"
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(unsigned int* const* __restrict__ flag_ptrs, unsigned int* __restrict__ epoch_ctr, int rank, int world) {
+  const unsigned int epoch = *epoch_ctr + 1u;
+  __threadfence_system();
+  if ((int)threadIdx.x < world) st_release_sys(flag_ptrs[threadIdx.x] + rank, epoch);
+  wait_flags(flag_ptrs[rank], world, epoch);
+  if (threadIdx.x == 0) *epoch_ctr = epoch;
+}
+
 }  // namespace mgp
 
 using namespace mgp;
@@ -841,6 +921,32 @@ int mgp_cg_dist_scalars_f64(double* state, const double* rbuf, int32_t ncols, in
                             void* stream) {
   MGP_CHECK_ARG(state && rbuf && ncols > 0 && ncols <= kCgMaxCols && what >= 0 && what <= 2, "cg_dist_scalars: bad arguments");
   cg_scalars_kernel<double><<<1, kCgBlock, 0, (cudaStream_t)stream>>>(state, rbuf, ncols, what, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter, hist, max_hist);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_scalars_f32(float* state, const float* rbuf, int32_t ncols, int32_t what, float tolerance, float eps,
+                            float stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, float* hist, int32_t max_hist,
+                            void* red_ptrs, void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(state && rbuf && red_ptrs && flag_ptrs && epoch_ctr && ncols > 0 && ncols <= kCgMaxCols && what >= 0 && what <= 3 &&
+                    world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_scalars: bad arguments");
+  cg_peer_scalars_kernel<float><<<1, kCgBlock, 0, (cudaStream_t)stream>>>(state, rbuf, ncols, what, tolerance, eps, stop_updating_after,
+      max_iter, n_tridiag_iter, hist, max_hist, (float* const*)red_ptrs, (unsigned int* const*)flag_ptrs, (unsigned int*)epoch_ctr, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_scalars_f64(double* state, const double* rbuf, int32_t ncols, int32_t what, double tolerance, double eps,
+                            double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, double* hist, int32_t max_hist,
+                            void* red_ptrs, void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(state && rbuf && red_ptrs && flag_ptrs && epoch_ctr && ncols > 0 && ncols <= kCgMaxCols && what >= 0 && what <= 3 &&
+                    world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_scalars: bad arguments");
+  cg_peer_scalars_kernel<double><<<1, kCgBlock, 0, (cudaStream_t)stream>>>(state, rbuf, ncols, what, tolerance, eps, stop_updating_after,
+      max_iter, n_tridiag_iter, hist, max_hist, (double* const*)red_ptrs, (unsigned int* const*)flag_ptrs, (unsigned int*)epoch_ctr, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_peer_barrier(void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(flag_ptrs && epoch_ctr && world >= 1 && world <= 32 && rank >= 0 && rank < world, "peer_barrier: bad arguments");
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned int* const*)flag_ptrs, (unsigned int*)epoch_ctr, rank, world);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

@@ -52,6 +52,9 @@ struct WiArgs {
   const int* xmap;
   const int* ymap;
   const T* x;
+  const unsigned char* const* peer_x;   // multi-GPU: device array of the ranks' X base pointers (peer-mapped); halo ids are then
+                                        // (rank << 26) | row-in-that-rank's-X and the halo rows are fetched over NVLink.  NULL: ids index x.
+  int npeers;
   int64_t ldx;
   T* y;
   int64_t ldy;
@@ -107,12 +110,14 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
   __shared__ __align__(8) uint64_t empty_bar[kWiMaxStages];
   __shared__ __align__(8) uint64_t meta_bar[2];
   __shared__ __align__(8) uint64_t ids_bar[kWiIdSlots];
+  __shared__ const unsigned char* peer_tab[32];
   const int nstages = g.stages;
   const size_t stage_bytes = wi_stage_bytes<T>(g.lmax, g.nzcap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* const ring = smem_raw + (size_t)nstages * stage_bytes;
   int* const ids_ring = reinterpret_cast<int*>(ring + 2 * kWiMetaBytes);
 
+  if (g.peer_x && tid < g.npeers) peer_tab[tid] = g.peer_x[tid];
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full_bar[s], 2 * kWiProducerThreads);   // per producer thread: one plain arrive (thread 0: expect_tx) + one cp.async arrive
@@ -140,6 +145,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
     const bool own_contig = (g.xmap == nullptr) && (g.ldx == CW);
     const unsigned char* const xbase = reinterpret_cast<const unsigned char*>(g.x + g.c0) + ch * 16;
     const int64_t ldxb = g.ldx * (int64_t)sizeof(T);
+    const int64_t xoff = (int64_t)g.c0 * (int64_t)sizeof(T) + ch * 16;   // same column window / chunk in a peer's X
     auto meta_w = [&](int c) { return reinterpret_cast<const int*>(ring + (size_t)((c - ch0) & 1) * kWiMetaBytes); };
     auto meta_h = [&](int c) { return meta_w(c) + kWiMetaW; };
     auto request_meta = [&](int c) {                               // one thread
@@ -203,7 +209,12 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         int sr = rr < nown ? (int)(row0 + rr) : ids[rr - nown];
         if (g.xmap) sr = __ldg(g.xmap + sr);
         const int dstrow = rr < nown ? rr : R + (rr - nown);
-        cp_async16(xs + (size_t)dstrow * ROW_BYTES + ch * 16, xbase + (int64_t)sr * ldxb);
+        const unsigned char* xb = xbase;
+        if (g.peer_x && rr >= nown) {                            // halo row of another rank: its X over NVLink
+          xb = peer_tab[sr >> 26] + xoff;
+          sr &= (1 << 26) - 1;
+        }
+        cp_async16(xs + (size_t)dstrow * ROW_BYTES + ch * 16, xb + (int64_t)sr * ldxb);
       }
       cp_async_arrive_noinc(&full_bar[s]);
       if (tid <= 16) rp[tid] = wp[tid] - base;
@@ -359,7 +370,7 @@ template <typename T>
 static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw, const T* diag, const int* hptr,
                        const int* hcol, int tile_rows, int lmax, int wnzmax, int hmax, const T* shift, const T* post, const int* xmap,
                        const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int ncols, const T* dot_with,
-                       T* dot_out, void* dot_ws, cudaStream_t st) {
+                       T* dot_out, void* dot_ws, const void* peer_x, int npeers, cudaStream_t st) {
   constexpr int R = kWiRows;
   constexpr int VEC = 16 / sizeof(T);
   constexpr int CW = 4 * VEC;
@@ -380,6 +391,8 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   WiArgs<T> g;
   g.wptr = wptr; g.wcol = wcol; g.aw = aw; g.diag = diag; g.hptr = hptr; g.hcol = hcol; g.shift = shift;
   g.post = post; g.xmap = xmap; g.ymap = ymap; g.x = x; g.ldx = ldx; g.y = y; g.ldy = ldy; g.n = n;
+  g.peer_x = reinterpret_cast<const unsigned char* const*>(peer_x); g.npeers = npeers;
+  MGP_CHECK_ARG(peer_x == nullptr || (npeers >= 1 && npeers <= 32 && xmap == nullptr), "lap_spmm_wi: peer X needs 1..32 ranks and no xmap");
   g.ntiles = (int)ceil_div(n, (int64_t)R);
   g.lmax = (lmax + 3) & ~3;
   g.nzcap = wnzmax + 32;                       // the consumers' look-ahead loads read one step past a warp block
@@ -426,17 +439,17 @@ int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* 
                         const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
                         const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
                         int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
-                        void* stream) {
+                        const void* peer_x, int32_t npeers, void* stream) {
   return mgp::lap_spmm_wi<float>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
-                                 ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
+                                 ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, (cudaStream_t)stream);
 }
 int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag,
                         const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax,
                         const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
                         int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
-                        void* dot_ws, void* stream) {
+                        void* dot_ws, const void* peer_x, int32_t npeers, void* stream) {
   return mgp::lap_spmm_wi<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
-                                  ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
+                                  ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -67,6 +67,7 @@ class HaloPlan:
         self.send_counts = send_counts_t.tolist()
         req = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
         dist.all_to_all_single(req, self.halo_ids, self.send_counts, self.recv_counts, group=group)
+        self.part = part
         self.send_idx = (req - lo).contiguous()          # local row index of every row I must send
         assert self.send_idx.numel() == 0 or (int(self.send_idx.min()) >= 0 and int(self.send_idx.max()) < self.n_loc)
         self.group = group
@@ -120,6 +121,13 @@ class LocalStructure:
                 hloc[:nt + 1] = t["hptr"][t0:t1 + 1]
                 self.tiles.update(wptr=wloc, wcol=t["wcol"], nnzw=t["nnzw"], wnzmax=t["wnzmax"], hptr=hloc,
                                   hcol=plan.to_local(t["hcol"]).to(torch.int32).contiguous(), hmax=t["hmax"])
+                # peer-memory variant: (owner rank << 26) | row inside the owner's block -- the kernel reads the owner's
+                # vector directly over NVLink (ids of rows this rank owns are never used by its own tiles' halo lists)
+                gid = t["hcol"].to(torch.int64)
+                own = plan.part.owner(gid).clamp_(max=plan.part.world - 1)
+                starts = torch.tensor(plan.part.bounds[:-1], dtype=torch.int64, device=self.device)
+                assert max(b1 - b0 for b0, b1 in zip(plan.part.bounds[:-1], plan.part.bounds[1:])) < (1 << 26)
+                self.tiles["hcol_peer"] = ((own << 26) | (gid - starts[own])).to(torch.int32).contiguous()
         self._gst = gst
         self.TILED_SMEM_LIMIT = gst.TILED_SMEM_LIMIT
 
@@ -198,6 +206,9 @@ class DistCG:
         self.graph = None
         self.use_graph = use_cuda_graph and dev.type == "cuda"
 
+    def _allreduce_rbuf(self):
+        dist.all_reduce(self.rbuf, group=self.group)
+
     def _scalars(self, what):
         from . import _lib
         from ._lib import c_double, c_float, c_int32, ptr, stream
@@ -228,11 +239,11 @@ class DistCG:
         self.state.zero_()
         _lib.call("mgp_cg_dist_norm2_" + sfx, ptr(self.b), c_int64(ld), c_int64(n_loc), c_int32(c), ptr(self.state), ptr(self.rbuf),
                   ptr(self.ws), stream())
-        dist.all_reduce(self.rbuf, group=self.group)
+        self._allreduce_rbuf()
         self._scalars(0)
         _lib.call("mgp_cg_dist_init_" + sfx, ptr(self.b), c_int64(ld), ptr(self.x), ptr(self.r), ptr(self.p), c_int64(ld),
                   c_int64(n_loc), c_int32(c), ptr(self.state), ptr(self.rbuf), ptr(self.ws), stream())
-        dist.all_reduce(self.rbuf, group=self.group)
+        self._allreduce_rbuf()
         self._scalars(1)
         scal = solvers.S_NARR * c
         k, done = 0, 0.0
@@ -263,6 +274,107 @@ class DistCG:
         tail = self.state[scal:scal + 3].tolist()
         info = dict(iterations=int(tail[solvers.K_ITER]), mean_residual=float(tail[solvers.K_MEAN]), converged=(done == 1.0))
         return out, info
+
+
+class PeerMemory:
+    """Peer-mapped ("symmetric") device allocations of one process group: every rank allocates the same shape and gets the
+    device pointers of all ranks' copies (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once at
+    rendezvous, NVLink P2P loads / stores afterwards).  Plumbing only -- the data path is the kernels that use the pointers."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._sm = symm_mem
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.handles = []
+
+    def alloc(self, shape, dtype):
+        """(local tensor, int64 device tensor with the world's base pointers)."""
+        t = self._sm.empty(*shape, dtype=dtype, device=self.device)
+        hdl = self._sm.rendezvous(t, self.group)
+        t.zero_()
+        ptrs = torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=self.device)
+        self.handles.append(hdl)
+        return t, ptrs
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+
+class PeerCG(DistCG):
+    """DistCG whose every exchange is a hand-written peer-memory kernel instead of an NCCL call (8 x B200 behind NVSwitch):
+
+    * halo rows are not exchanged at all: ``p`` and the intermediate vectors live in peer-mapped memory and the SpMM's
+      producer warps cp.async the halo rows straight from the owning rank's vector (``peer_x`` of mgp_lap_spmm_wi);
+      producer and consumer launches are separated by ``mgp_peer_barrier`` (one tiny kernel, epoch flags over NVLink);
+    * the two inner products of an iteration are all-reduced inside the scalar kernels (``mgp_cg_peer_scalars``).
+
+    An iteration is 8 kernel launches and no library call; NCCL's launch + protocol latency (~37 us per 16-float
+    all-reduce, ~2 x that per halo all-to-all on this box) was ~2/3 of the 8-GPU iteration time."""
+
+    def __init__(self, op: DistPrecision, ncols: int, dtype=torch.float32, tolerance=1e-6, eps=1e-10,
+                 stop_updating_after=1e-10, max_iter=1000, check_interval=16, group=None, use_cuda_graph=True):
+        super().__init__(op, ncols, dtype, tolerance, eps, stop_updating_after, max_iter, check_interval, group, use_cuda_graph)
+        from . import solvers
+        dev = self.dev
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        part = op.plan.part
+        n_sym = max(b1 - b0 for b0, b1 in zip(part.bounds[:-1], part.bounds[1:]))       # same allocation size on every rank
+        self.mem = PeerMemory(dev, group)
+        self.p, self.p_ptrs = self.mem.alloc((n_sym, self.ld), dtype)
+        self.tmps = [self.mem.alloc((n_sym, self.ld), dtype) for _ in range(max(op.nu - 1, 0))]
+        self.red, self.red_ptrs = self.mem.alloc((2 * self.world * 128,), dtype)
+        self.flags, self.flag_ptrs = self.mem.alloc((64,), torch.int32)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.rbuf_pap = torch.zeros(ncols, dtype=dtype, device=dev)
+        self.tmp = None
+        self.mem.sync()
+
+    # -- building blocks -----------------------------------------------------------------------------------------------
+    def _barrier(self):
+        from . import _lib
+        from ._lib import c_int32, ptr, stream
+        _lib.call("mgp_peer_barrier", ptr(self.flag_ptrs), ptr(self.epoch), c_int32(self.rank), c_int32(self.world), stream())
+
+    def _scalars(self, what, rbuf=None):
+        from . import _lib
+        from ._lib import c_double, c_float, c_int32, ptr, stream
+        fl = c_float if self.dt == torch.float32 else c_double
+        rbuf = self.rbuf if rbuf is None else rbuf
+        _lib.call("mgp_cg_peer_scalars_" + _lib.suffix(self.dt), ptr(self.state), ptr(rbuf), c_int32(self.c), c_int32(what),
+                  fl(self.tol), fl(self.eps), fl(self.stop), c_int32(self.max_iter), c_int32(0), None, c_int32(0),
+                  ptr(self.red_ptrs), ptr(self.flag_ptrs), ptr(self.epoch), c_int32(self.rank), c_int32(self.world), stream())
+
+    def _matvec(self):
+        """v <- P p with p^T v partial sums in rbuf_pap; halo rows come from the peers' copies of the source vector."""
+        from . import graph
+        op, c, n_loc = self.op, self.c, self.op.n_loc
+        src, src_ptrs = self.p, self.p_ptrs
+        for s in range(op.nu):
+            last = s == op.nu - 1
+            dst, dst_ptrs = (self.v, None) if last else self.tmps[s]
+            self._barrier()                                      # the source vector is complete on every rank
+            graph.lap_spmm(op.st, op.a, op.diag, src[:n_loc, :c], shift=op.shift, out=dst[:n_loc, :c],
+                           dot_with=self.p[:n_loc, :c] if last else None, dot_out=self.rbuf_pap if last else None,
+                           peer_x=src_ptrs)
+            src, src_ptrs = dst, dst_ptrs
+
+    def _iteration(self):
+        from . import _lib
+        from ._lib import c_int32, c_int64, ptr, stream
+        sfx = _lib.suffix(self.dt)
+        n_loc, c, ld = self.op.n_loc, self.c, self.ld
+        self._matvec()
+        self._scalars(3, self.rbuf_pap)                          # all-reduce(p^T A p) -> state
+        _lib.call("mgp_cg_rupdate_" + sfx, ptr(self.r), ptr(self.v), c_int64(ld), c_int64(n_loc), c_int32(c), ptr(self.state),
+                  None, c_int32(0), ptr(self.rbuf), ptr(self.ws), stream())
+        self._scalars(2)                                         # all-reduce(|r|^2) -> alpha, beta, flags
+        _lib.call("mgp_cg_pxupdate_" + sfx, ptr(self.x), ptr(self.p), ptr(self.r), c_int64(ld), c_int64(n_loc), c_int32(c),
+                  ptr(self.state), stream())
+
+    def _allreduce_rbuf(self):
+        pass                                                     # fused into _scalars
 
 
 def dist_cg(op: DistPrecision, b_loc: torch.Tensor, tolerance=1e-6, eps=1e-10, stop_updating_after=1e-10, max_iter=1000,
@@ -332,7 +444,11 @@ def bench_main(args, CFG):
     B = torch.randn(n, c, device=dev, generator=g)           # identical on every rank (same seed)
     b_loc = gst.to_internal(B)[lo:hi].contiguous()
 
-    cg = DistCG(op, c, torch.float32, tolerance=CFG["tol"], max_iter=CFG["max_iter"])
+    transport = os.environ.get("MGP_DIST_TRANSPORT", "peer")
+    if transport == "peer":
+        cg = PeerCG(op, c, torch.float32, tolerance=CFG["tol"], max_iter=CFG["max_iter"])
+    else:
+        cg = DistCG(op, c, torch.float32, tolerance=CFG["tol"], max_iter=CFG["max_iter"])
 
     def solve():
         return cg.solve(b_loc)
@@ -378,7 +494,10 @@ def bench_main(args, CFG):
                "e2e": {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": int(Bh.numel() * 4 * world),
                        "d2h_bytes_per_step": int(Xh.numel() * 4 * world)},
                "gpu_launches": int(launches),
-               "collectives_per_iteration": {"halo_all_to_all": CFG["nu"], "all_reduce": 2}}
+               "transport": transport,
+               "collectives_per_iteration": ({"peer_barrier": CFG["nu"], "peer_allreduce_fused_with_scalars": 2,
+                                              "halo": "read from the owners' vectors over NVLink inside the SpMM"}
+                                             if transport == "peer" else {"halo_all_to_all": CFG["nu"], "all_reduce": 2})}
         print(json.dumps(out))
     dist.barrier()
     return None

@@ -375,7 +375,7 @@ SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi"  (tests force 
 
 
 def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
-             x_external=False, y_external=False):
+             x_external=False, y_external=False, peer_x=None):
     """Y = post .* ((diag + shift) .* (pre .* X) - A (pre .* X)).  ``x``: [n, C] CUDA tensor with unit column stride.
 
     ``a, diag, pre, post`` are in the structure's row order.  ``x_external`` / ``y_external``: X (and ``dot_with``) / Y are
@@ -403,17 +403,21 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
         t = st.tiles
         if out is None:
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
-        if pre is None and "wptr" in t and SPMM_KERNEL in ("auto", "wi"):
+        if peer_x is not None and not (pre is None and "wptr" in t):
+            raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
+        if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi") or peer_x is not None):
             aw = st.wi_values(a)
+            hcol = t["hcol_peer"] if peer_x is not None else t["hcol"]
             rc = _lib.call_rc("mgp_lap_spmm_wi_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag),
-                              ptr(t["hptr"]), ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
+                              ptr(t["hptr"]), ptr(hcol), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
                               c_int32(t["wnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
                               ptr(st.perm32 if x_external else None),
                               ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
-                              c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())
+                              c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws),
+                              ptr(peer_x), c_int32(0 if peer_x is None else int(peer_x.numel())), stream())
             if rc == 0:
                 return out
-            if rc != _lib.MGP_EUNSUPPORTED:
+            if rc != _lib.MGP_EUNSUPPORTED or peer_x is not None:
                 raise RuntimeError(f"mgp_lap_spmm_wi_{sfx} failed ({rc}): {_lib.last_error()}")
         if SPMM_KERNEL == "wi":
             raise RuntimeError("lap_spmm: warp-interleaved kernel requested but this call does not qualify (pre scaling, "
@@ -442,6 +446,8 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
         if rc != _lib.MGP_EUNSUPPORTED or SPMM_KERNEL == "tiled":
             raise RuntimeError(f"mgp_lap_spmm_tiled_{sfx} failed ({rc}): {_lib.last_error()}")
         # a pass wider than estimated (unaligned leading dimension): the CSR kernel handles it
+    if peer_x is not None:
+        raise RuntimeError("lap_spmm: peer-memory halo reads requested but the tile structure does not fit this call")
     # v1 CSR kernel works in the structure's order only
     if x_external:
         x = x.index_select(0, st.perm)
