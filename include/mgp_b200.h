@@ -185,7 +185,10 @@ int mgp_lap_spmm_pipe_f64(const int32_t* prowptr, const uint16_t* plcol, const d
  * 16-byte aligned.  mgp_lap_wi_values copies a CSR-ordered value array into the stream layout.
  * Multi-GPU (row-partitioned): peer_x = DEVICE array of npeers pointers to the ranks' X blocks (peer-mapped, same ldx);
  * halo ids are then (rank << 26) | row-in-that-rank's-X and the halo rows are fetched straight from the owners over
- * NVLink (no pack kernel, no all-to-all); the caller separates producer and consumer launches with mgp_peer_barrier.
+ * NVLink (no pack kernel, no all-to-all).  Producer and consumer launches must be separated by a cross-GPU sync: either
+ * mgp_peer_barrier before the call, or the fused form -- sync_flags = DEVICE array of the ranks' flag arrays uint32[npeers]
+ * (zeroed + barrier once per solve), sync_epoch -> a device scalar e: block 0 publishes e + 1 to every peer at kernel start
+ * and the producer warps wait for all ranks' flags before fetching the first remote row (local copies start at once).
  * Replaces graph_laplacian_operator.py:117-119 / precision_matern_operator.py:28-32 like the kernels above.
  * Returns MGP_EUNSUPPORTED (nothing launched) when the call does not qualify. */
 int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const float* a, int64_t n, float* aw, void* stream);
@@ -194,12 +197,14 @@ int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* 
                         const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
                         const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
                         int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
-                        const void* peer_x, int32_t npeers, void* stream);
+                        const void* peer_x, int32_t npeers, int32_t rank, const void* sync_flags, const float* sync_epoch,
+                        void* stream);
 int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag,
                         const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax,
                         const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
                         int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
-                        void* dot_ws, const void* peer_x, int32_t npeers, void* stream);
+                        void* dot_ws, const void* peer_x, int32_t npeers, int32_t rank, const void* sync_flags,
+                        const double* sync_epoch, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
  * Backward of the SpMM w.r.t. the matrix entries (what autograd through torch_sparse.spmm computes for `value`,
@@ -298,6 +303,19 @@ int mgp_cg_peer_scalars_f32(float* state, const float* rbuf, int32_t ncols, int3
 int mgp_cg_peer_scalars_f64(double* state, const double* rbuf, int32_t ncols, int32_t what, double tolerance, double eps,
                             double stop_updating_after, int32_t max_iter, int32_t n_tridiag_iter, double* hist, int32_t max_hist,
                             void* red_ptrs, void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream);
+/* Fully fused iteration tail of the peer-memory path (replaces mgp_cg_peer_scalars(3) + mgp_cg_rupdate + mgp_cg_peer_scalars(2)
+ * + mgp_cg_pxupdate): sync points are keyed by the iteration number in `state` (epoch = iterations done + 1), so the flag
+ * arrays flag2 / flag3 (uint32[world] per rank, peer-mapped) must be ZEROED on every rank, followed by a barrier, before each
+ * solve.  red_ptrs[r] -> T[2][2][world][128].  pap_local: this rank's p^T A p partial sums (dot epilogue of the last SpMM).
+ * ld must be a power of two <= 128 and the vectors 16-byte aligned, else MGP_EUNSUPPORTED (use the unfused calls). */
+int mgp_cg_peer_rupdate_f32(float* r, const float* v, int64_t ld, int64_t n, int32_t ncols, float* state, const float* pap_local,
+                            void* ws, void* red_ptrs, void* flag2_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream);
+int mgp_cg_peer_rupdate_f64(double* r, const double* v, int64_t ld, int64_t n, int32_t ncols, double* state, const double* pap_local,
+                            void* ws, void* red_ptrs, void* flag2_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream);
+int mgp_cg_peer_pxupdate_f32(float* x, float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, float* state, float* hist,
+                             int32_t max_hist, void* ws, void* red_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream);
+int mgp_cg_peer_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, double* state, double* hist,
+                             int32_t max_hist, void* ws, void* red_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream);
 int mgp_peer_barrier(void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream);
 int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream);
 int mgp_cg_pupdate_f64(double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream);

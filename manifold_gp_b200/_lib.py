@@ -54,8 +54,8 @@ _SIG = {
     "mgp_lap_spmm_pipe_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_wi_values_f32": (c_int32, [P, P, P, c_int64, P, P]),
     "mgp_lap_wi_values_f64": (c_int32, [P, P, P, c_int64, P, P]),
-    "mgp_lap_spmm_wi_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P, c_int32, P]),
-    "mgp_lap_spmm_wi_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P, c_int32, P]),
+    "mgp_lap_spmm_wi_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P, c_int32, c_int32, P, P, P]),
+    "mgp_lap_spmm_wi_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P, c_int32, c_int32, P, P, P]),
     "mgp_lap_sddmm_f32": (c_int32, [P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P]),
     "mgp_lap_sddmm_f64": (c_int32, [P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P]),
     "mgp_cg_state_elems": (c_size_t, [c_int32]),
@@ -80,6 +80,10 @@ _SIG = {
     "mgp_cg_dist_scalars_f64": (c_int32, [P, P, c_int32, c_int32, c_double, c_double, c_double, c_int32, c_int32, P, c_int32, P]),
     "mgp_cg_peer_scalars_f32": (c_int32, [P, P, c_int32, c_int32, c_float, c_float, c_float, c_int32, c_int32, P, c_int32, P, P, P, c_int32, c_int32, P]),
     "mgp_cg_peer_scalars_f64": (c_int32, [P, P, c_int32, c_int32, c_double, c_double, c_double, c_int32, c_int32, P, c_int32, P, P, P, c_int32, c_int32, P]),
+    "mgp_cg_peer_rupdate_f32": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P, P, P, P, P, c_int32, c_int32, P]),
+    "mgp_cg_peer_rupdate_f64": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P, P, P, P, P, c_int32, c_int32, P]),
+    "mgp_cg_peer_pxupdate_f32": (c_int32, [P, P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P, P, c_int32, c_int32, P]),
+    "mgp_cg_peer_pxupdate_f64": (c_int32, [P, P, P, c_int64, c_int64, c_int32, P, P, c_int32, P, P, P, c_int32, c_int32, P]),
     "mgp_peer_barrier": (c_int32, [P, P, c_int32, c_int32, P]),
     "mgp_cg_pupdate_f32": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P]),
     "mgp_cg_pupdate_f64": (c_int32, [P, P, c_int64, c_int64, c_int32, P, P]),

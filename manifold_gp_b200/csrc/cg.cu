@@ -758,14 +758,6 @@ static int cg_pxupdate(T* x, T* p, const T* r, int64_t ld, int64_t n, int ncols,
 //   flag_ptrs[r] -> rank r's flags   unsigned[world]                    (one flag per source rank)
 //   epoch        -> this rank's private counter (device memory), advanced by the kernel: CUDA-graph replay safe
 // what: 0 norm, 1 init, 2 update (as cg_scalars_kernel), 3 = store the totals as p^T A p.
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // all peers' flags[src] >= epoch (wrap-safe); bounded so a lost peer traps instead of hanging the GPU
 __device__ __forceinline__ void wait_flags(const unsigned int* my_flags, int world, unsigned int epoch) {
   if ((int)threadIdx.x < world) {
@@ -824,6 +816,162 @@ peer_barrier_kernel(unsigned int* const* __restrict__ flag_ptrs, unsigned int* _
   if ((int)threadIdx.x < world) st_release_sys(flag_ptrs[threadIdx.x] + rank, epoch);
   wait_flags(flag_ptrs[rank], world, epoch);
   if (threadIdx.x == 0) *epoch_ctr = epoch;
+}
+
+
+// ---- multi-GPU, fully fused iteration tail: [rupdate + both all-reduces + scalar step + pxupdate] in TWO kernels ----------
+// Sync points are identified by the CG iteration number itself (epoch = K_ITER + 1, identical on every rank), so a captured
+// CUDA graph can be replayed and nothing has to be counted on the side; the flags are zeroed once per solve.
+//   flag2 / flag3 : uint32[world] per rank (peer-mapped) -- "p^T A p partials of rank r have landed" / "|r|^2 partials ..."
+//   red_ptrs[r]   : T[2 kinds][2 buffers][world][kCgMaxCols] of rank r
+// cg_peer_rupdate : block 0 ships this rank's p^T A p partials (dot epilogue of the last SpMM launch) to every peer; every
+//                   block waits for all ranks' partials, adds them in rank order, forms alpha with the published safe
+//                   division, updates r and accumulates |r|^2; the last block to finish ships the |r|^2 partials.
+// cg_peer_pxupdate: every block waits for all ranks' |r|^2 partials, forms beta, applies x += alpha p, p = r + beta p; the
+//                   last block to finish runs the scalar step (norms, flags, history, iteration counter).
+template <typename T>
+__device__ __forceinline__ T* peer_red_slot(T* base, int kind, int buf, int world, int src) {
+  return base + (((size_t)kind * 2 + buf) * world + src) * kCgMaxCols;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_peer_rupdate_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_t n, int ncols, T* __restrict__ state,
+                       const T* __restrict__ pap_local, void* ws, T* const* __restrict__ red_ptrs,
+                       unsigned int* const* __restrict__ flag2_ptrs, unsigned int* const* __restrict__ flag3_ptrs, int rank,
+                       int world) {
+  using V = typename V16<T>::type;
+  constexpr int N = V16<T>::N;
+  T* k = state + S_NARR * ncols;
+  if (k[K_DONE] != T(0)) return;
+  CgWs<T> w = cg_ws<T>(ws);
+  __shared__ T al[kCgMaxCols];
+  __shared__ T sm[kCgBlock][N];
+  const int tid = threadIdx.x;
+  const unsigned int epoch = (unsigned int)k[K_ITER] + 1u;
+  const int buf = (int)(epoch & 1u);
+  if (blockIdx.x == 0) {                                   // ship my p^T A p partials
+    for (int i = tid; i < world * ncols; i += kCgBlock) {
+      const int dst = i / ncols, c = i - dst * ncols;
+      peer_red_slot<T>(red_ptrs[dst], 0, buf, world, rank)[c] = pap_local[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(flag2_ptrs[tid] + rank, epoch);
+  }
+  wait_flags(flag2_ptrs[rank], world, epoch);
+  const T eps = k[K_EPS];
+  for (int c = tid; c < ld; c += kCgBlock) {
+    T a = T(0);
+    if (c < ncols) {
+      T pap = T(0);
+      for (int src = 0; src < world; ++src) pap += __ldcv(peer_red_slot<T>(red_ptrs[rank], 0, buf, world, src) + c);
+      const T rz = state[S_RZ * ncols + c];
+      a = (pap < eps) ? T(0) : rz / pap;
+      if (state[S_CONV * ncols + c] != T(0)) a = T(0);
+      if (blockIdx.x == 0) { state[S_PAP * ncols + c] = pap; state[S_ALPHA * ncols + c] = a; }   // read by nobody in this kernel
+    }
+    al[c] = a;
+  }
+  __syncthreads();
+  const int c0 = (tid * N) % ld;
+  T a[N], acc[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) { a[u] = al[c0 + u]; acc[u] = T(0); }
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* r4 = reinterpret_cast<V*>(r);
+  const V* v4 = reinterpret_cast<const V*>(v);
+#pragma unroll 4
+  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + tid; e < total; e += stride) {
+    T vv[N], rv[N];
+    v16_unpack<T>(v4[e], vv); v16_unpack<T>(r4[e], rv);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      rv[u] = fma(-a[u], vv[u], rv[u]);
+      acc[u] = fma(rv[u], rv[u], acc[u]);
+    }
+    r4[e] = v16_pack<T>(rv);
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) sm[tid][u] = acc[u];
+  __syncthreads();
+  if (tid < ncols) {
+    const int groups = ld / N;
+    T s = T(0);
+    for (int t = tid / N; t < kCgBlock; t += groups) s += sm[t][tid % N];
+    w.partials[(int64_t)blockIdx.x * ncols + tid] = s;
+  }
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot);
+    for (int i = tid; i < world * ncols; i += kCgBlock) {   // ship my |r|^2 partials
+      const int dst = i / ncols, c = i - dst * ncols;
+      peer_red_slot<T>(red_ptrs[dst], 1, buf, world, rank)[c] = tot[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(flag3_ptrs[tid] + rank, epoch);
+    if (tid == 0) k[K_XPEND] = T(1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_peer_pxupdate_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r, int ld, int64_t n, int ncols,
+                        T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws, T* const* __restrict__ red_ptrs,
+                        unsigned int* const* __restrict__ flag3_ptrs, int rank, int world) {
+  using V = typename V16<T>::type;
+  constexpr int N = V16<T>::N;
+  T* k = state + S_NARR * ncols;
+  if (k[K_XPEND] == T(0)) return;
+  __shared__ T al[kCgMaxCols], be[kCgMaxCols], tot[kCgMaxCols];
+  const int tid = threadIdx.x;
+  const unsigned int epoch = (unsigned int)k[K_ITER] + 1u;
+  const int buf = (int)(epoch & 1u);
+  wait_flags(flag3_ptrs[rank], world, epoch);
+  const T eps = k[K_EPS];
+  for (int c = tid; c < ld; c += kCgBlock) {
+    T a = T(0), b = T(0);
+    if (c < ncols) {
+      T rz_new = T(0);
+      for (int src = 0; src < world; ++src) rz_new += __ldcv(peer_red_slot<T>(red_ptrs[rank], 1, buf, world, src) + c);
+      const T rz_old = state[S_RZ * ncols + c];
+      b = (rz_old < eps) ? T(0) : rz_new / rz_old;
+      a = state[S_ALPHA * ncols + c];
+      tot[c] = rz_new;
+    }
+    al[c] = a; be[c] = b;
+  }
+  __syncthreads();
+  const int c0 = (tid * N) % ld;
+  T a[N], b[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) { a[u] = al[c0 + u]; b[u] = be[c0 + u]; }
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* x4 = reinterpret_cast<V*>(x);
+  V* p4 = reinterpret_cast<V*>(p);
+  const V* r4 = reinterpret_cast<const V*>(r);
+#pragma unroll 4
+  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + tid; e < total; e += stride) {
+    T pv[N], rv[N], xv[N];
+    v16_unpack<T>(p4[e], pv); v16_unpack<T>(r4[e], rv); v16_unpack<T>(x4[e], xv);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      xv[u] = fma(a[u], pv[u], xv[u]);
+      pv[u] = fma(b[u], pv[u], rv[u]);
+    }
+    x4[e] = v16_pack<T>(xv);
+    p4[e] = v16_pack<T>(pv);
+  }
+  // every block has read the old scalars: the last one to finish advances them (alpha via cg_alpha_of == S_ALPHA)
+  CgWs<T> w = cg_ws<T>(ws);
+  if (last_block_ticket(w.counter + 4)) {
+    cg_finish_update<T>(state, tot, ncols, hist, max_hist);
+    __syncthreads();
+    if (tid == 0) k[K_XPEND] = T(0);
+  }
 }
 
 }  // namespace mgp
@@ -941,6 +1089,50 @@ int mgp_cg_peer_scalars_f64(double* state, const double* rbuf, int32_t ncols, in
                     world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_scalars: bad arguments");
   cg_peer_scalars_kernel<double><<<1, kCgBlock, 0, (cudaStream_t)stream>>>(state, rbuf, ncols, what, tolerance, eps, stop_updating_after,
       max_iter, n_tridiag_iter, hist, max_hist, (double* const*)red_ptrs, (unsigned int* const*)flag_ptrs, (unsigned int*)epoch_ctr, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_rupdate_f32(float* r, const float* v, int64_t ld, int64_t n, int32_t ncols, float* state, const float* pap_local,
+                            void* ws, void* red_ptrs, void* flag2_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(r && v && state && pap_local && ws && red_ptrs && flag2_ptrs && flag3_ptrs && n > 0 && ncols > 0 && world >= 1 &&
+                    world <= 32 && rank >= 0 && rank < world, "cg_peer_rupdate: bad arguments");
+  if (!cg_vec_ok<float>(ld, r, v, nullptr, nullptr)) return MGP_EUNSUPPORTED;
+  int64_t g = ceil_div(n * ld / V16<float>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
+  cg_peer_rupdate_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(r, v, (int)ld, n, ncols, state, pap_local, ws,
+      (float* const*)red_ptrs, (unsigned int* const*)flag2_ptrs, (unsigned int* const*)flag3_ptrs, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_rupdate_f64(double* r, const double* v, int64_t ld, int64_t n, int32_t ncols, double* state, const double* pap_local,
+                            void* ws, void* red_ptrs, void* flag2_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(r && v && state && pap_local && ws && red_ptrs && flag2_ptrs && flag3_ptrs && n > 0 && ncols > 0 && world >= 1 &&
+                    world <= 32 && rank >= 0 && rank < world, "cg_peer_rupdate: bad arguments");
+  if (!cg_vec_ok<double>(ld, r, v, nullptr, nullptr)) return MGP_EUNSUPPORTED;
+  int64_t g = ceil_div(n * ld / V16<double>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
+  cg_peer_rupdate_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(r, v, (int)ld, n, ncols, state, pap_local, ws,
+      (double* const*)red_ptrs, (unsigned int* const*)flag2_ptrs, (unsigned int* const*)flag3_ptrs, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_pxupdate_f32(float* x, float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, float* state, float* hist,
+                             int32_t max_hist, void* ws, void* red_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(x && p && r && state && ws && red_ptrs && flag3_ptrs && n > 0 && ncols > 0 && world >= 1 && world <= 32 && rank >= 0 &&
+                    rank < world, "cg_peer_pxupdate: bad arguments");
+  if (!cg_vec_ok<float>(ld, x, p, r, nullptr)) return MGP_EUNSUPPORTED;
+  int64_t g = ceil_div(n * ld / V16<float>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
+  cg_peer_pxupdate_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, p, r, (int)ld, n, ncols, state, hist, max_hist, ws,
+      (float* const*)red_ptrs, (unsigned int* const*)flag3_ptrs, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, double* state, double* hist,
+                             int32_t max_hist, void* ws, void* red_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(x && p && r && state && ws && red_ptrs && flag3_ptrs && n > 0 && ncols > 0 && world >= 1 && world <= 32 && rank >= 0 &&
+                    rank < world, "cg_peer_pxupdate: bad arguments");
+  if (!cg_vec_ok<double>(ld, x, p, r, nullptr)) return MGP_EUNSUPPORTED;
+  int64_t g = ceil_div(n * ld / V16<double>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
+  cg_peer_pxupdate_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, p, r, (int)ld, n, ncols, state, hist, max_hist, ws,
+      (double* const*)red_ptrs, (unsigned int* const*)flag3_ptrs, rank, world);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

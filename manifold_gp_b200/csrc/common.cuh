@@ -115,4 +115,14 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
   return is_last;
 }
 
+// system-scope release / acquire on flags in peer-mapped memory (multi-GPU sync points)
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 }  // namespace mgp

@@ -55,6 +55,10 @@ struct WiArgs {
   const unsigned char* const* peer_x;   // multi-GPU: device array of the ranks' X base pointers (peer-mapped); halo ids are then
                                         // (rank << 26) | row-in-that-rank's-X and the halo rows are fetched over NVLink.  NULL: ids index x.
   int npeers;
+  int rank;
+  unsigned int* const* sync_flags;     // optional fused cross-GPU barrier: device array of the ranks' flag arrays uint32[npeers]
+  const T* sync_epoch;                 // epoch = (unsigned)*sync_epoch + 1 (the CG iteration counter): block 0 publishes it to
+                                        // every peer at kernel start, producers wait for all peers' flags before the first remote row
   int64_t ldx;
   T* y;
   int64_t ldy;
@@ -130,6 +134,15 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
   }
   __syncthreads();
 
+  unsigned int sync_epoch = 0u;
+  if (g.sync_flags) {
+    sync_epoch = (unsigned int)(*g.sync_epoch) + 1u;
+    if (blockIdx.x == 0 && warp == 1 && lane < g.npeers) {      // "everything enqueued before this launch is done on my side"
+      __threadfence_system();
+      st_release_sys(g.sync_flags[lane] + g.rank, sync_epoch);
+    }
+  }
+
   // contiguous tile range of this block
   const int t0 = (int)(((int64_t)blockIdx.x * g.ntiles) / gridDim.x);
   const int t1 = (int)(((int64_t)(blockIdx.x + 1) * g.ntiles) / gridDim.x);
@@ -174,6 +187,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
     }
     int s = 0;
     uint32_t ph = 0;
+    bool peers_ready = false;
     for (int t = t0; t < t1; ++t) {
       const int i = t - t0;
       unsigned char* const sb = smem_raw + (size_t)s * stage_bytes;
@@ -203,6 +217,17 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
           bulk_g2s(vs, g.aw + base, (uint32_t)cnt * (uint32_t)sizeof(T), &full_bar[s]);
         }
         if (own_contig) bulk_g2s(xs, g.x + row0 * g.ldx + g.c0, (uint32_t)nrows * ROW_BYTES, &full_bar[s]);
+      }
+      if (g.sync_flags && !peers_ready && nscat > nown) {           // first remote rows of this launch: all peers have signalled?
+        if (lane < g.npeers) {
+          const unsigned int* f = g.sync_flags[g.rank] + lane;
+          unsigned int spins = 0;
+          while ((int)(ld_acquire_sys(f) - sync_epoch) < 0) {
+            if (++spins > (1u << 25)) __trap();
+          }
+        }
+        __syncwarp();
+        peers_ready = true;
       }
       // scattered X rows: 4 consecutive lanes copy the four 16-byte chunks of one row (8 whole rows per warp instruction)
       for (int rr = 8 * pw + sub; rr < nscat; rr += 32) {
@@ -370,7 +395,8 @@ template <typename T>
 static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw, const T* diag, const int* hptr,
                        const int* hcol, int tile_rows, int lmax, int wnzmax, int hmax, const T* shift, const T* post, const int* xmap,
                        const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int ncols, const T* dot_with,
-                       T* dot_out, void* dot_ws, const void* peer_x, int npeers, cudaStream_t st) {
+                       T* dot_out, void* dot_ws, const void* peer_x, int npeers, int rank, const void* sync_flags, const T* sync_epoch,
+                       cudaStream_t st) {
   constexpr int R = kWiRows;
   constexpr int VEC = 16 / sizeof(T);
   constexpr int CW = 4 * VEC;
@@ -391,7 +417,9 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   WiArgs<T> g;
   g.wptr = wptr; g.wcol = wcol; g.aw = aw; g.diag = diag; g.hptr = hptr; g.hcol = hcol; g.shift = shift;
   g.post = post; g.xmap = xmap; g.ymap = ymap; g.x = x; g.ldx = ldx; g.y = y; g.ldy = ldy; g.n = n;
-  g.peer_x = reinterpret_cast<const unsigned char* const*>(peer_x); g.npeers = npeers;
+  g.peer_x = reinterpret_cast<const unsigned char* const*>(peer_x); g.npeers = npeers; g.rank = rank;
+  g.sync_flags = reinterpret_cast<unsigned int* const*>(const_cast<void*>(sync_flags)); g.sync_epoch = sync_epoch;
+  MGP_CHECK_ARG(sync_flags == nullptr || (peer_x && sync_epoch && rank >= 0 && rank < npeers), "lap_spmm_wi: fused barrier needs peer X, an epoch pointer and a valid rank");
   MGP_CHECK_ARG(peer_x == nullptr || (npeers >= 1 && npeers <= 32 && xmap == nullptr), "lap_spmm_wi: peer X needs 1..32 ranks and no xmap");
   g.ntiles = (int)ceil_div(n, (int64_t)R);
   g.lmax = (lmax + 3) & ~3;
@@ -439,17 +467,19 @@ int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* 
                         const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
                         const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
                         int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
-                        const void* peer_x, int32_t npeers, void* stream) {
+                        const void* peer_x, int32_t npeers, int32_t rank, const void* sync_flags, const float* sync_epoch,
+                        void* stream) {
   return mgp::lap_spmm_wi<float>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
-                                 ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, (cudaStream_t)stream);
+                                 ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, rank, sync_flags, sync_epoch, (cudaStream_t)stream);
 }
 int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag,
                         const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax,
                         const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
                         int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
-                        void* dot_ws, const void* peer_x, int32_t npeers, void* stream) {
+                        void* dot_ws, const void* peer_x, int32_t npeers, int32_t rank, const void* sync_flags, const double* sync_epoch,
+                        void* stream) {
   return mgp::lap_spmm_wi<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
-                                  ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, (cudaStream_t)stream);
+                                  ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, rank, sync_flags, sync_epoch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -375,9 +375,11 @@ SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi"  (tests force 
 
 
 def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
-             x_external=False, y_external=False, peer_x=None):
+             x_external=False, y_external=False, peer_x=None, peer_sync=None):
     """Y = post .* ((diag + shift) .* (pre .* X) - A (pre .* X)).  ``x``: [n, C] CUDA tensor with unit column stride.
 
+    ``peer_x``: int64 device tensor of every rank's X base pointer (row-partitioned multi-GPU, see distributed.PeerCG);
+    ``peer_sync`` = (rank, flag pointer table, epoch scalar) fuses the cross-GPU barrier into the launch.
     ``a, diag, pre, post`` are in the structure's row order.  ``x_external`` / ``y_external``: X (and ``dot_with``) / Y are
     in the caller's row order (only matters when the structure is internally permuted)."""
     if x.dim() != 2 or x.shape[0] < st.n:   # a row-partitioned structure reads [own rows | halo rows]: more rows than it writes
@@ -414,7 +416,9 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
                               ptr(st.perm32 if x_external else None),
                               ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
                               c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws),
-                              ptr(peer_x), c_int32(0 if peer_x is None else int(peer_x.numel())), stream())
+                              ptr(peer_x), c_int32(0 if peer_x is None else int(peer_x.numel())),
+                              c_int32(0 if peer_sync is None else int(peer_sync[0])), ptr(None if peer_sync is None else peer_sync[1]),
+                              ptr(None if peer_sync is None else peer_sync[2]), stream())
             if rc == 0:
                 return out
             if rc != _lib.MGP_EUNSUPPORTED or peer_x is not None:
