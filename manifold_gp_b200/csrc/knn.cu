@@ -83,7 +83,14 @@ __device__ __forceinline__ void knn_drain(KnnSmem* s, float* listd, int* listi, 
 
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q, int64_t nq, int d, int k,
-           float* __restrict__ out_d, int64_t* __restrict__ out_i) {
+           float* __restrict__ out_d, int64_t* __restrict__ out_i, const int* __restrict__ qlist,
+           const unsigned int* __restrict__ qcount) {
+  // qlist != NULL: the block's 64 query rows are qlist[q0 .. q0+64) (the re-run of the queries the tensor-core search
+  // could not certify, knn_tc.cu); *qcount entries are valid and blocks beyond them exit at once.
+  if (qlist) {
+    nq = (int64_t)*qcount;
+    if ((int64_t)blockIdx.x * kKnnQ >= nq) return;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KnnSmem* s = reinterpret_cast<KnnSmem*>(smem_raw);
   float* listd = reinterpret_cast<float*>(smem_raw + sizeof(KnnSmem));
@@ -105,8 +112,9 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
   auto load_q_chunk = [&](int d0) {
     for (int e = tid; e < kKnnD * kKnnQ; e += kKnnThreads) {
       const int r = e % kKnnQ, dd = e / kKnnQ;
-      const int64_t qi = q0 + r;
-      s->qs[dd][r] = (qi < nq && d0 + dd < d) ? __ldg(q + qi * d + d0 + dd) : 0.f;
+      const int64_t qe = q0 + r;
+      const int64_t qi = qe < nq ? (qlist ? (int64_t)qlist[qe] : qe) : 0;
+      s->qs[dd][r] = (qe < nq && d0 + dd < d) ? __ldg(q + qi * d + d0 + dd) : 0.f;
     }
   };
   if (single_chunk) load_q_chunk(0);
@@ -192,8 +200,9 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
   __syncthreads();
   for (int e = tid; e < kKnnQ * k; e += kKnnThreads) {
     const int r = e / k, c = e % k;
-    const int64_t qi = q0 + r;
-    if (qi < nq) {
+    const int64_t qe = q0 + r;
+    if (qe < nq) {
+      const int64_t qi = qlist ? (int64_t)qlist[qe] : qe;
       const int id = listi[e];
       const bool filled = id != 0x7fffffff;
       out_d[qi * k + c] = filled ? listd[e] : __int_as_float(0x7f800000);
@@ -202,6 +211,19 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
   }
 }
 
+}  // namespace mgp
+
+namespace mgp {
+// Exact search restricted to the query rows qlist[0 .. *qcount) (device memory); `nq_max` bounds the launch.
+int knn_search_list(const float* db, int64_t n, const float* q, int64_t nq_max, int d, int k, float* dist2, int64_t* idx,
+                    const int* qlist, const unsigned int* qcount, cudaStream_t st) {
+  const size_t smem = sizeof(KnnSmem) + (size_t)kKnnQ * k * 8;
+  MGP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = ceil_div(nq_max, kKnnQ);
+  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, st>>>(db, n, q, nq_max, d, k, dist2, idx, qlist, qcount);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
 }  // namespace mgp
 
 using namespace mgp;
@@ -224,7 +246,7 @@ int mgp_knn_search_f32(const float* db, int64_t n, const float* q, int64_t nq, i
   MGP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = ceil_div(nq, kKnnQ);
   MGP_CHECK_ARG(grid < ((int64_t)1 << 31), "knn_search: too many queries for one launch");
-  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, (cudaStream_t)stream>>>(db, n, q, nq, d, k, dist2, idx);
+  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, (cudaStream_t)stream>>>(db, n, q, nq, d, k, dist2, idx, nullptr, nullptr);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

@@ -1,0 +1,631 @@
+// Exact brute-force kNN for large d on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
+//
+// Reference: NearestNeighbors.search, manifold_gp/utils/nearest_neighbors.py:35-37 -> faiss Index{Flat,IVFFlat(nlist=1)}
+// .search, whose large-batch path is the BLAS form |q|^2 + |x|^2 - 2 q.x.  Here the q.x tiles are
+// TF32 tcgen05.mma contractions and the result is made EXACT (identical to mgp_knn_search_f32 / the oracle's fp32
+// "direct" form) by a certified re-rank:
+//
+//   1. knn_tc_colsum / knn_tc_prep   centre the points on the database mean, split every coordinate into two TF32-exact
+//                                    terms hi + lo (hi = top 19 bits, lo = x - hi), |x|^2 accumulated in fp64.
+//   2. knn_tc_sweep_kernel           persistent, warp-specialised: one TMA producer thread, one tcgen05.mma issuer thread,
+//                                    four epilogue warps.  Per (128 queries x 128 points) tile and 32-wide k-block it issues
+//                                    hi.hi + hi.lo + lo.hi (3xTF32: the dropped lo.lo term is 2^-22 relative) into a
+//                                    double-buffered TMEM accumulator; the epilogue warps read the accumulator with
+//                                    tcgen05.ld (one query row per thread), form d~ = |q|^2 + |x|^2 - 2 q.x and run the
+//                                    fused selection: an in-register threshold test per candidate, survivors appended to the
+//                                    row's candidate list, warp-cooperative rank-and-compact when a list fills.  Output: the
+//                                    K' = k + margin best candidates per (query, database split) and the threshold tau that
+//                                    every discarded point exceeded.
+//   3. knn_tc_rerank_kernel          exact fp32 distances of the candidates (sum_d (q_d - x_d)^2, ascending d, mul-then-add:
+//                                    bit-identical to knn.cu), top-k by (distance, index), and the certificate
+//                                    tau_min - E > d_k, E = 8 x (largest |d~ - d| seen on this query's candidates) + floor.
+//                                    A query that fails it is appended to a list ...
+//   4. knn_kernel (knn.cu)           ... and re-searched exhaustively on the CUDA cores (device-side count, no host sync).
+#include <cuda.h>
+#include <float.h>
+
+#include "pipe_common.cuh"
+
+namespace mgp {
+
+int knn_search_list(const float* db, int64_t n, const float* q, int64_t nq_max, int d, int k, float* dist2, int64_t* idx,
+                    const int* qlist, const unsigned int* qcount, cudaStream_t st);
+
+constexpr int kTcBM = 128;       // query rows per tile  (UMMA M)
+constexpr int kTcBN = 128;       // database points per tile (UMMA N)
+constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B atom row
+constexpr int kTcStages = 3;
+constexpr int kTcTileBytes = kTcBM * kTcBK * 4;      // 16 KB
+constexpr int kTcStageBytes = 4 * kTcTileBytes;      // Qhi, Qlo, Xhi, Xlo
+constexpr int kTcThreads = 192;                      // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 epilogue
+constexpr int kTcTmemCols = 2 * kTcBN;               // double-buffered fp32 accumulator
+constexpr int kTcMaxKp = 64;                         // K' (candidates kept per row)
+constexpr int kTcMaxSplit = 8;
+constexpr int kTcMaxCand = 256;                      // nsplit * K' handled by the re-rank
+constexpr size_t kTcSmemBytes = (size_t)kTcStages * kTcStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate, 128 x 128 x 8 per instruction
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile written by TMA with SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// (bit layout: cute::UMMA::SmemDescriptor -- start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in
+//  [46,48), layout type SWIZZLE_128B = 2 in [61,64))
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;                    // leading byte offset: unused for swizzled K-major operands
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 = 1 @4, a/b_format TF32 = 2 @7/@10, K-major A and B, N >> 3 @17, M >> 4 @24
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+
+// order-preserving float <-> uint32 (so that (key >> 32) sorts like the float and the low word breaks ties by index)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// ---- 1. preparation --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_tc_colsum_kernel(const float* __restrict__ x, int64_t n, int d, double* __restrict__ sums) {
+  const int64_t r0 = (int64_t)blockIdx.x * 256;
+  const int64_t r1 = min(n, r0 + 256);
+  for (int c = threadIdx.x; c < d; c += 256) {
+    double s = 0.0;
+    for (int64_t r = r0; r < r1; ++r) s += (double)x[r * d + c];
+    atomicAdd(sums + c, s);
+  }
+}
+
+// one warp per row: centred point -> hi / lo TF32 terms (row stride dp, zero padded) and its squared norm
+__global__ void __launch_bounds__(256)
+knn_tc_prep_kernel(const float* __restrict__ x, int64_t n, int64_t npad, int d, int dp, const double* __restrict__ sums,
+                   double inv_count, float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norm) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= npad) return;
+  if (row >= n) {
+    if (lane == 0) norm[row] = __int_as_float(0x7f800000);   // padding columns of the last tile can never be selected
+    return;
+  }
+  double acc = 0.0;
+  for (int c = lane; c < dp; c += 32) {
+    float h = 0.f, l = 0.f;
+    if (c < d) {
+      const float mu = (float)(sums[c] * inv_count);
+      const float v = __fsub_rn(x[row * d + c], mu);
+      h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      l = __fsub_rn(v, h);
+      acc += (double)v * (double)v;
+    }
+    hi[row * dp + c] = h;
+    lo[row * dp + c] = l;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) norm[row] = (float)acc;
+}
+
+// ---- 2. tensor-core sweep --------------------------------------------------------------------------------------------------
+struct TcArgs {
+  const float* qn;          // [nq]
+  const float* xn;          // [ntiles * 128], +inf beyond n
+  int64_t nq, n;
+  int nkb;                  // k-blocks of 32 dims
+  int ntiles, nqtiles, nsplit, tiles_per_split;
+  int kp, cap;              // K', candidate-list capacity per row (kp + 32)
+  unsigned long long* lists;  // [gridDim.x][128][cap]
+  int* cand_idx;            // [nq][nsplit][kp]   (-1 = empty)
+  float* cand_dt;           // [nq][nsplit][kp]   approximate distances
+  float* tau;               // [nq][nsplit]       every discarded point of the split had d~ >= tau (FLT_MAX: nothing discarded)
+};
+
+// Keep the kp smallest of the n keys of one row (sorted ascending, in place).  Returns the kp-th key's distance, or
+// FLT_MAX when n < kp.  n <= 96.
+__device__ __forceinline__ float tc_compact_row(unsigned long long* rb, int n, int kp, int lane) {
+  const unsigned long long kInv = ~0ull;
+  const unsigned long long k0 = lane < n ? __ldcg(rb + lane) : kInv;
+  const unsigned long long k1 = lane + 32 < n ? __ldcg(rb + lane + 32) : kInv;
+  const unsigned long long k2 = lane + 64 < n ? __ldcg(rb + lane + 64) : kInv;
+  int r0 = 0, r1 = 0, r2 = 0;
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const unsigned long long kj = __shfl_sync(0xffffffffu, k0, j);
+    r0 += kj < k0; r1 += kj < k1; r2 += kj < k2;
+  }
+  if (n > 32) {
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const unsigned long long kj = __shfl_sync(0xffffffffu, k1, j);
+      r0 += kj < k0; r1 += kj < k1; r2 += kj < k2;
+    }
+  }
+  if (n > 64) {
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const unsigned long long kj = __shfl_sync(0xffffffffu, k2, j);
+      r0 += kj < k0; r1 += kj < k1; r2 += kj < k2;
+    }
+  }
+  __syncwarp();
+  unsigned long long kt = kInv;
+  if (k0 != kInv) { if (r0 < kp) __stcg(rb + r0, k0); if (r0 == kp - 1) kt = k0; }
+  if (k1 != kInv) { if (r1 < kp) __stcg(rb + r1, k1); if (r1 == kp - 1) kt = k1; }
+  if (k2 != kInv) { if (r2 < kp) __stcg(rb + r2, k2); if (r2 == kp - 1) kt = k2; }
+  const unsigned m = __ballot_sync(0xffffffffu, kt != kInv);
+  float tau = FLT_MAX;
+  if (m) {
+    kt = __shfl_sync(0xffffffffu, kt, __ffs(m) - 1);
+    tau = ord2f((uint32_t)(kt >> 32));
+  }
+  __syncwarp();
+  return tau;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+                    const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, const TcArgs g) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kTcStages * kTcStageBytes);
+  uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kTcStages;          // [stages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * kTcStages;      // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kTcStages + 2; // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nitems = g.nqtiles * g.nsplit;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int qt = item / g.nsplit, sp = item - qt * g.nsplit;
+        const int t0 = sp * g.tiles_per_split, t1 = min(g.ntiles, t0 + g.tiles_per_split);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < g.nkb; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            unsigned char* sb = smem + (size_t)s * kTcStageBytes;
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kTcStageBytes);
+            tma_load_2d(sb, &tm_qhi, kb * kTcBK, qt * kTcBM, &full_bar[s]);
+            tma_load_2d(sb + kTcTileBytes, &tm_qlo, kb * kTcBK, qt * kTcBM, &full_bar[s]);
+            tma_load_2d(sb + 2 * kTcTileBytes, &tm_xhi, kb * kTcBK, t * kTcBN, &full_bar[s]);
+            tma_load_2d(sb + 3 * kTcTileBytes, &tm_xlo, kb * kTcBK, t * kTcBN, &full_bar[s]);
+            if (++s == kTcStages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== tcgen05.mma issuer (one thread) =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t jt = 0;   // tiles issued by this CTA: accumulator buffer = jt & 1, its use count = jt >> 1
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int qt = item / g.nsplit, sp = item - qt * g.nsplit;
+        const int t0 = sp * g.tiles_per_split, t1 = min(g.ntiles, t0 + g.tiles_per_split);
+        for (int t = t0; t < t1; ++t, ++jt) {
+          const uint32_t buf = jt & 1u;
+          mbar_wait(&tempty_bar[buf], ((jt >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + buf * kTcBN;
+          for (int kb = 0; kb < g.nkb; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem + (size_t)s * kTcStageBytes);
+            const uint64_t dqh = umma_desc_sw128(sb), dql = umma_desc_sw128(sb + kTcTileBytes);
+            const uint64_t dxh = umma_desc_sw128(sb + 2 * kTcTileBytes), dxl = umma_desc_sw128(sb + 3 * kTcTileBytes);
+#pragma unroll
+            for (int ks = 0; ks < kTcBK / 8; ++ks)     // +32 bytes per K = 8 step inside the swizzle atom
+              tc_mma_tf32(tacc, dqh + 2 * ks, dxh + 2 * ks, kTcIdesc, (kb | ks) != 0);
+#pragma unroll
+            for (int ks = 0; ks < kTcBK / 8; ++ks) tc_mma_tf32(tacc, dqh + 2 * ks, dxl + 2 * ks, kTcIdesc, 1u);
+#pragma unroll
+            for (int ks = 0; ks < kTcBK / 8; ++ks) tc_mma_tf32(tacc, dql + 2 * ks, dxh + 2 * ks, kTcIdesc, 1u);
+            tc_commit(&empty_bar[s]);      // the stage is free once these MMAs have read it
+            if (++s == kTcStages) { s = 0; ph ^= 1u; }
+          }
+          tc_commit(&tfull_bar[buf]);      // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: one query row per thread, fused selection =====
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    unsigned long long* const wlists = g.lists + ((size_t)blockIdx.x * kTcBM + quad * 32) * g.cap;
+    unsigned long long* const mylist = wlists + (size_t)lane * g.cap;
+    uint32_t jt = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int qt = item / g.nsplit, sp = item - qt * g.nsplit;
+      const int t0 = sp * g.tiles_per_split, t1 = min(g.ntiles, t0 + g.tiles_per_split);
+      const int64_t qrow = (int64_t)qt * kTcBM + row;
+      const float qn = qrow < g.nq ? __ldg(g.qn + qrow) : 0.f;
+      float tau = qrow < g.nq ? FLT_MAX : -FLT_MAX;   // rows beyond the last query never collect candidates
+      int cnt = 0;
+      for (int t = t0; t < t1; ++t, ++jt) {
+        const uint32_t buf = jt & 1u;
+        mbar_wait(&tfull_bar[buf], (jt >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kTcBN;
+#pragma unroll 1
+        for (int ch = 0; ch < kTcBN / 32; ++ch) {
+          uint32_t acc[32];
+          tc_ld32(tacc + ch * 32, acc);
+          if (ch == kTcBN / 32 - 1) {                // accumulator fully read: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          }
+          const int col0 = t * kTcBN + ch * 32;
+          const float xv = __ldg(g.xn + col0 + lane);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float xc = __shfl_sync(0xffffffffu, xv, c);
+            const float dt = fmaf(-2.f, __uint_as_float(acc[c]), qn + xc);
+            if (dt <= tau) {
+              __stcg(mylist + cnt, ((unsigned long long)f2ord(dt) << 32) | (unsigned)(col0 + c));
+              ++cnt;
+            }
+            unsigned need = __ballot_sync(0xffffffffu, cnt == g.cap);
+            while (need) {                           // warp-uniform: compact the full lists, one row at a time
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              __syncwarp();
+              const float tnew = tc_compact_row(wlists + (size_t)src * g.cap, g.cap, g.kp, lane);
+              if (lane == src) { tau = tnew; cnt = g.kp; }
+            }
+          }
+        }
+      }
+      // ---- item done: final compaction and write-out ----
+      unsigned need = __ballot_sync(0xffffffffu, cnt > g.kp);
+      __syncwarp();
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int nsrc = __shfl_sync(0xffffffffu, cnt, src);
+        const float tnew = tc_compact_row(wlists + (size_t)src * g.cap, nsrc, g.kp, lane);
+        if (lane == src) { tau = tnew; cnt = g.kp; }
+      }
+      __syncwarp();
+      for (int rr = 0; rr < 32; ++rr) {
+        const int64_t qr = (int64_t)qt * kTcBM + quad * 32 + rr;
+        if (qr >= g.nq) break;
+        const int nr = __shfl_sync(0xffffffffu, cnt, rr);
+        const unsigned long long* rb = wlists + (size_t)rr * g.cap;
+        const size_t ob = ((size_t)qr * g.nsplit + sp) * g.kp;
+        for (int j = lane; j < g.kp; j += 32) {
+          const bool v = j < nr;
+          const unsigned long long key = v ? __ldcg(rb + j) : 0ull;
+          g.cand_idx[ob + j] = v ? (int)(uint32_t)key : -1;
+          g.cand_dt[ob + j] = v ? ord2f((uint32_t)(key >> 32)) : 0.f;
+        }
+      }
+      if (qrow < g.nq) g.tau[(size_t)qrow * g.nsplit + sp] = tau;
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
+  }
+}
+
+// ---- 3. exact re-rank + certificate ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tc_lex_less(float d0, int i0, float d1, int i1) { return d0 < d1 || (d0 == d1 && i0 < i1); }
+
+// stats: [0] queries that failed the certificate, [1] bits of the largest |d~ - d| seen, [2] queries processed
+template <int T>
+__global__ void __launch_bounds__(128)
+knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, int64_t nq, int d, int k, int nsplit, int kp,
+                     const int* __restrict__ cand_idx, const float* __restrict__ cand_dt, const float* __restrict__ tau_s,
+                     const float* __restrict__ qn, float* __restrict__ out_d, int64_t* __restrict__ out_i,
+                     int* __restrict__ flag_list, unsigned int* __restrict__ stats) {
+  const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  const int total = nsplit * kp;
+  const float* qrow = q + qi * d;
+  const float kInf = __int_as_float(0x7f800000);
+  float ed[T];
+  int ei[T];
+  float err = 0.f;
+  int nvalid = 0;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int e = lane + 32 * t;
+    const int id = e < total ? cand_idx[(size_t)qi * total + e] : -1;
+    float acc = kInf;
+    if (id >= 0) {
+      const float* xr = db + (int64_t)id * d;
+      acc = 0.f;
+      if ((d & 3) == 0) {
+        for (int c = 0; c < d; c += 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(qrow + c));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(xr + c));
+          float df = __fsub_rn(a.x, b.x); acc = __fadd_rn(acc, __fmul_rn(df, df));
+          df = __fsub_rn(a.y, b.y); acc = __fadd_rn(acc, __fmul_rn(df, df));
+          df = __fsub_rn(a.z, b.z); acc = __fadd_rn(acc, __fmul_rn(df, df));
+          df = __fsub_rn(a.w, b.w); acc = __fadd_rn(acc, __fmul_rn(df, df));
+        }
+      } else {
+        for (int c = 0; c < d; ++c) {
+          const float df = __fsub_rn(__ldg(qrow + c), __ldg(xr + c));
+          acc = __fadd_rn(acc, __fmul_rn(df, df));
+        }
+      }
+      err = fmaxf(err, fabsf(acc - cand_dt[(size_t)qi * total + e]));
+      ++nvalid;
+    }
+    ed[t] = acc;
+    ei[t] = id >= 0 ? id : 0x7fffffff;
+  }
+  nvalid = warp_sum(nvalid);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+
+  int rank[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) rank[t] = 0;
+#pragma unroll
+  for (int t2 = 0; t2 < T; ++t2) {
+    if (32 * t2 < total) {
+      for (int j = 0; j < 32; ++j) {
+        const float dj = __shfl_sync(0xffffffffu, ed[t2], j);
+        const int ij = __shfl_sync(0xffffffffu, ei[t2], j);
+#pragma unroll
+        for (int t = 0; t < T; ++t) rank[t] += tc_lex_less(dj, ij, ed[t], ei[t]) ? 1 : 0;
+      }
+    }
+  }
+  float dk = kInf;   // exact k-th distance among the candidates
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    if (ei[t] != 0x7fffffff && rank[t] < k) {
+      out_d[qi * k + rank[t]] = ed[t];
+      out_i[qi * k + rank[t]] = (int64_t)ei[t];
+      if (rank[t] == k - 1) dk = ed[t];
+    }
+  }
+  for (int c = nvalid + lane; c < k; c += 32) { out_d[qi * k + c] = kInf; out_i[qi * k + c] = -1; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dk = fminf(dk, __shfl_xor_sync(0xffffffffu, dk, o));
+
+  if (lane == 0) {
+    float tmin = FLT_MAX;
+    for (int s = 0; s < nsplit; ++s) tmin = fminf(tmin, tau_s[(size_t)qi * nsplit + s]);
+    bool ok = true;
+    if (tmin < FLT_MAX) {          // something was discarded: it must be provably farther than the k-th neighbour
+      const float e = 8.f * err + 9.5367431640625e-07f * (4.f * qn[qi] + 2.f * fabsf(tmin));
+      ok = (nvalid >= k) && (tmin - e > dk);
+    }
+    if (!ok) {
+      const unsigned pos = atomicAdd(&stats[0], 1u);
+      flag_list[pos] = (int)qi;
+    }
+    atomicMax(&stats[1], __float_as_uint(err));
+    atomicAdd(&stats[2], 1u);
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows, dp] fp32 row-major, box = 128 rows x 32 elements, 128-byte swizzle, out-of-range elements read as zero
+static int make_tile_map(CUtensorMap* tm, const float* base, int64_t rows, int dp) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("knn_tc: cuTensorMapEncodeTiled is not available from the driver"); return MGP_ECUDA; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)dp * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("knn_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MGP_ECUDA; }
+  return MGP_OK;
+}
+
+struct TcPlan {
+  int dp, nkb, ntiles, nqtiles, nsplit, tiles_per_split, kp, cap, grid;
+  int64_t npad, nqpad;
+  bool same;
+  // workspace offsets (bytes)
+  size_t o_sums, o_xhi, o_xlo, o_xn, o_qhi, o_qlo, o_qn, o_lists, o_cidx, o_cdt, o_tau, o_flag, total;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
+  if (d < 16 || k < 1 || k > 48 || n < 256 || n >= ((int64_t)1 << 31) - 256 || nq < 1 || nq >= ((int64_t)1 << 31) - 256) return false;
+  p->same = same;
+  p->dp = (d + 3) & ~3;
+  p->nkb = (int)ceil_div(d, kTcBK);
+  p->ntiles = (int)ceil_div(n, kTcBN);
+  p->nqtiles = (int)ceil_div(nq, kTcBM);
+  p->kp = ((k + 16 + 31) / 32) * 32;            // 32 or 64
+  p->cap = p->kp + 32;
+  int smax = kTcMaxCand / p->kp;
+  if (smax > kTcMaxSplit) smax = kTcMaxSplit;
+  int s = (int)ceil_div((int64_t)kNumSMs * 6, p->nqtiles);   // aim for >= 6 waves of work items
+  if (s > smax) s = smax;
+  if (s > p->ntiles / 4) s = p->ntiles / 4;                   // at least 4 database tiles per split
+  if (s < 1) s = 1;
+  p->tiles_per_split = (int)ceil_div(p->ntiles, s);
+  p->nsplit = (int)ceil_div(p->ntiles, p->tiles_per_split);
+  const int64_t items = (int64_t)p->nqtiles * p->nsplit;
+  p->grid = (int)(items < kNumSMs ? items : kNumSMs);
+  p->npad = (int64_t)p->ntiles * kTcBN;
+  p->nqpad = (int64_t)p->nqtiles * kTcBM;
+  size_t o = 0;
+  p->o_sums = o; o = align256(o + (size_t)d * 8);
+  p->o_xhi = o; o = align256(o + (size_t)n * p->dp * 4);
+  p->o_xlo = o; o = align256(o + (size_t)n * p->dp * 4);
+  p->o_xn = o; o = align256(o + (size_t)p->npad * 4);
+  if (!same) {
+    p->o_qhi = o; o = align256(o + (size_t)nq * p->dp * 4);
+    p->o_qlo = o; o = align256(o + (size_t)nq * p->dp * 4);
+    p->o_qn = o; o = align256(o + (size_t)p->nqpad * 4);
+  } else {
+    p->o_qhi = p->o_xhi; p->o_qlo = p->o_xlo; p->o_qn = p->o_xn;
+  }
+  p->o_lists = o; o = align256(o + (size_t)p->grid * kTcBM * p->cap * 8);
+  p->o_cidx = o; o = align256(o + (size_t)nq * p->nsplit * p->kp * 4);
+  p->o_cdt = o; o = align256(o + (size_t)nq * p->nsplit * p->kp * 4);
+  p->o_tau = o; o = align256(o + (size_t)nq * p->nsplit * 4);
+  p->o_flag = o; o = align256(o + (size_t)nq * 4);
+  p->total = o;
+  return true;
+}
+
+template <int T>
+static void launch_rerank(const TcPlan& p, const float* db, const float* q, int64_t nq, int d, int k, unsigned char* w, float* dist2,
+                          int64_t* idx, unsigned int* stats, cudaStream_t st) {
+  knn_tc_rerank_kernel<T><<<(unsigned)ceil_div(nq, 4), 128, 0, st>>>(
+      db, q, nq, d, k, p.nsplit, p.kp, reinterpret_cast<const int*>(w + p.o_cidx), reinterpret_cast<const float*>(w + p.o_cdt),
+      reinterpret_cast<const float*>(w + p.o_tau), reinterpret_cast<const float*>(w + p.o_qn), dist2, idx,
+      reinterpret_cast<int*>(w + p.o_flag), stats);
+}
+
+}  // namespace mgp
+
+using namespace mgp;
+
+extern "C" {
+
+size_t mgp_knn_search_tc_ws_bytes(int64_t n, int64_t nq, int32_t d, int32_t k, int32_t same) {
+  TcPlan p;
+  if (!tc_plan(n, nq, d, k, same != 0, &p)) return 0;
+  return p.total;
+}
+
+int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq, int32_t d, int32_t k, float* dist2,
+                          int64_t* idx, void* ws, size_t ws_bytes, uint32_t* stats, void* stream) {
+  MGP_CHECK_ARG(db && q && dist2 && idx && stats, "knn_search_tc: null pointer");
+  const bool same = (db == q) && (n == nq);
+  TcPlan p;
+  if (!tc_plan(n, nq, d, k, same, &p)) return MGP_EUNSUPPORTED;
+  if (!ws || ws_bytes < p.total) { set_error("knn_search_tc: workspace too small (%zu < %zu)", ws_bytes, p.total); return MGP_EWORKSPACE; }
+  MGP_CHECK_ARG(((uintptr_t)ws & 255) == 0, "knn_search_tc: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = reinterpret_cast<unsigned char*>(ws);
+  double* sums = reinterpret_cast<double*>(w + p.o_sums);
+  float* xhi = reinterpret_cast<float*>(w + p.o_xhi);
+  float* xlo = reinterpret_cast<float*>(w + p.o_xlo);
+  float* xn = reinterpret_cast<float*>(w + p.o_xn);
+  float* qhi = reinterpret_cast<float*>(w + p.o_qhi);
+  float* qlo = reinterpret_cast<float*>(w + p.o_qlo);
+  float* qn = reinterpret_cast<float*>(w + p.o_qn);
+
+  MGP_CUDA(cudaMemsetAsync(sums, 0, (size_t)d * 8, st));
+  MGP_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(uint32_t), st));
+  knn_tc_colsum_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(db, n, d, sums);
+  MGP_LAUNCH_CHECK();
+  knn_tc_prep_kernel<<<(unsigned)ceil_div(p.npad, 8), 256, 0, st>>>(db, n, p.npad, d, p.dp, sums, 1.0 / (double)n, xhi, xlo, xn);
+  MGP_LAUNCH_CHECK();
+  if (!same) {
+    knn_tc_prep_kernel<<<(unsigned)ceil_div(p.nqpad, 8), 256, 0, st>>>(q, nq, p.nqpad, d, p.dp, sums, 1.0 / (double)n, qhi, qlo, qn);
+    MGP_LAUNCH_CHECK();
+  }
+
+  CUtensorMap tm_qhi, tm_qlo, tm_xhi, tm_xlo;
+  int rc;
+  if ((rc = make_tile_map(&tm_qhi, qhi, nq, p.dp)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_qlo, qlo, nq, p.dp)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_xhi, xhi, n, p.dp)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_xlo, xlo, n, p.dp)) != MGP_OK) return rc;
+
+  TcArgs g;
+  g.qn = qn; g.xn = xn; g.nq = nq; g.n = n; g.nkb = p.nkb; g.ntiles = p.ntiles; g.nqtiles = p.nqtiles; g.nsplit = p.nsplit;
+  g.tiles_per_split = p.tiles_per_split; g.kp = p.kp; g.cap = p.cap;
+  g.lists = reinterpret_cast<unsigned long long*>(w + p.o_lists);
+  g.cand_idx = reinterpret_cast<int*>(w + p.o_cidx);
+  g.cand_dt = reinterpret_cast<float*>(w + p.o_cdt);
+  g.tau = reinterpret_cast<float*>(w + p.o_tau);
+  MGP_CUDA(cudaFuncSetAttribute(knn_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  knn_tc_sweep_kernel<<<(unsigned)p.grid, kTcThreads, kTcSmemBytes, st>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, g);
+  MGP_LAUNCH_CHECK();
+
+  const int total = p.nsplit * p.kp;
+  if (total <= 32) launch_rerank<1>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
+  else if (total <= 64) launch_rerank<2>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
+  else if (total <= 128) launch_rerank<4>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
+  else launch_rerank<8>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
+  MGP_LAUNCH_CHECK();
+
+  // queries whose certificate failed: exhaustive CUDA-core search (device-side count; blocks beyond it exit at once)
+  return knn_search_list(db, n, q, nq, d, k, dist2, idx, reinterpret_cast<const int*>(w + p.o_flag), stats, st);
+}
+
+}  // extern "C"

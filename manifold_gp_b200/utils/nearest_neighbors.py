@@ -15,6 +15,8 @@ from .._lib import c_int32, c_int64, c_size_t, ptr, stream
 class NearestNeighbors():
     def __init__(self, x=None, nlist=1) -> None:
         self.min_ivf = 5000
+        self.tensor_core = True     # use the tcgen05 search where it applies (results are identical either way)
+        self.last_search = None
         if x is not None:
             self.train(x, nlist)
 
@@ -38,6 +40,22 @@ class NearestNeighbors():
             raise ValueError(f"query dimension {q.shape[1]} != database dimension {d}")
         dist = torch.empty((nq, k), dtype=torch.float32, device=q.device)
         idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        same = q.data_ptr() == self._db.data_ptr() and nq == n
+        self.last_search = {"kernel": "cuda_core"}
+        if self.tensor_core:
+            # d >= 16, k <= 48: TF32 tcgen05 distance tiles + fused top-(k+margin) + exact certified re-rank (knn_tc.cu);
+            # bit-identical results to the CUDA-core kernel below.
+            nb = _lib.query("mgp_knn_search_tc_ws_bytes", c_int64(n), c_int64(nq), c_int32(d), c_int32(k), c_int32(int(same)))
+            if nb > 0:
+                ws = _lib.workspace(nb, q.device)
+                stats = torch.zeros(4, dtype=torch.int32, device=q.device)
+                rc = _lib.call_rc("mgp_knn_search_tc_f32", ptr(self._db), c_int64(n), ptr(self._db if same else q), c_int64(nq),
+                                  c_int32(d), c_int32(k), ptr(dist), ptr(idx), ptr(ws), c_size_t(ws.numel()), ptr(stats), stream())
+                if rc == 0:
+                    self.last_search = {"kernel": "tcgen05", "stats": stats}   # device tensor: reading it synchronises
+                    return dist.to(self.x.dtype), idx
+                if rc != _lib.MGP_EUNSUPPORTED:
+                    raise RuntimeError(f"mgp_knn_search_tc_f32 failed ({rc}): {_lib.last_error()}")
         nb = _lib.query("mgp_knn_search_ws_bytes", c_int64(n), c_int64(nq), c_int32(d), c_int32(k))
         ws = _lib.workspace(nb, q.device)
         _lib.call("mgp_knn_search_f32", ptr(self._db), c_int64(n), ptr(q), c_int64(nq), c_int32(d), c_int32(k),

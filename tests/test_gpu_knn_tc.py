@@ -1,0 +1,75 @@
+"""GPU parity of the tcgen05 kNN search (knn_tc.cu) through the C ABI: bit-identical to the CUDA-core kernel and to the
+oracle, with the certificate / re-search statistics checked so that a broken tensor-core stage cannot hide behind the
+exhaustive re-search."""
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _search_both(x, q, k):
+    import manifold_gp_b200 as mgp
+    xd = x.to(DEV)
+    qd = xd if q is x else q.to(DEV)
+    knn = mgp.NearestNeighbors(xd)
+    d_tc, i_tc = knn.search(qd, k)
+    info = knn.last_search
+    assert info["kernel"] == "tcgen05", "the tensor-core search did not run"
+    stats = info["stats"].cpu()
+    knn.tensor_core = False
+    d_cc, i_cc = knn.search(qd, k)
+    assert knn.last_search["kernel"] == "cuda_core"
+    return d_tc.cpu(), i_tc.cpu(), d_cc.cpu(), i_cc.cpu(), stats
+
+
+def _check(x, q, k, max_research=0.05):
+    d_tc, i_tc, d_cc, i_cc, stats = _search_both(x, q, k)
+    nq = (x if q is x else q).shape[0]
+    research = int(stats[0]) / nq
+    err = float(stats[1:2].view(torch.float32))
+    assert int(stats[2]) == nq
+    assert torch.equal(i_tc, i_cc), f"index lists differ in {(i_tc != i_cc).any(1).sum().item()} rows"
+    assert torch.equal(d_tc, d_cc)
+    scale = float((x * x).sum(1).max())
+    assert err < 1e-4 * scale, f"approximate distances off by {err} (|x|^2 max {scale}): tensor-core stage is wrong"
+    assert research <= max_research, f"{research:.3f} of the queries fell back to the exhaustive search"
+    return research, err
+
+
+def test_tc_matches_cuda_core_d784():
+    x = oracle.datasets.rmnist_shape(20000, 784, prototypes=20, seed=1)
+    _check(x, x, 10)
+
+
+def test_tc_matches_oracle_small():
+    x = oracle.datasets.rmnist_shape(3000, 784, prototypes=10, seed=2)
+    d_tc, i_tc, d_cc, i_cc, stats = _search_both(x, x, 10)
+    od, oi = oracle.knn_search(x, x, 10)
+    assert torch.equal(i_tc, oi) and torch.equal(d_tc, od)
+    assert torch.equal(i_tc[:, 0], torch.arange(x.shape[0]))
+
+
+@pytest.mark.parametrize("d,k", [(16, 5), (20, 9), (64, 32), (200, 12), (257, 48)])
+def test_tc_ragged_dims_and_k(d, k):
+    g = torch.Generator().manual_seed(d)
+    # clustered data: neighbours are well separated from the bulk, as on a manifold
+    centres = torch.randn(40, d, generator=g) * 3.0
+    x = (centres[torch.randint(0, 40, (9001,), generator=g)] + 0.3 * torch.randn(9001, d, generator=g)).contiguous()
+    _check(x, x, k, max_research=0.2)
+
+
+def test_tc_separate_queries_and_offset_data():
+    g = torch.Generator().manual_seed(5)
+    x = oracle.datasets.rmnist_shape(12000, 96, prototypes=12, seed=3) + 7.0     # large common offset: centring matters
+    q = x[torch.randperm(12000, generator=g)[:1501]] + 0.01 * torch.randn(1501, 96, generator=g)
+    _check(x, q.contiguous(), 16)
+
+
+def test_tc_iid_gaussian_falls_back_but_stays_exact():
+    # i.i.d. high-dimensional noise: distances concentrate, certificates fail often -- results must still be exact
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4000, 128, generator=g)
+    _check(x, x, 8, max_research=1.0)
