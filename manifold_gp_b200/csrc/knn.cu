@@ -23,6 +23,7 @@ constexpr int kKnnD = 16;        // dims per shared-memory chunk
 constexpr int kKnnThreads = 256;
 constexpr int kKnnQueue = 2048;  // survivor queue capacity per tile
 constexpr int kKnnMaxK = 128;
+constexpr int kKnnMaxParts = 32;  // database split of the list-mode re-search
 
 struct KnnSmem {
   float qs[kKnnD][kKnnQ];
@@ -84,12 +85,21 @@ __device__ __forceinline__ void knn_drain(KnnSmem* s, float* listd, int* listi, 
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q, int64_t nq, int d, int k,
            float* __restrict__ out_d, int64_t* __restrict__ out_i, const int* __restrict__ qlist,
-           const unsigned int* __restrict__ qcount) {
-  // qlist != NULL: the block's 64 query rows are qlist[q0 .. q0+64) (the re-run of the queries the tensor-core search
-  // could not certify, knn_tc.cu); *qcount entries are valid and blocks beyond them exit at once.
+           const unsigned int* __restrict__ qcount, float* __restrict__ part_d, int* __restrict__ part_i) {
+  // qlist != NULL: the queries are qlist[0 .. *qcount) (the re-run of the queries the tensor-core search could not
+  // certify, knn_tc.cu).  The launch has ceil(nq_max / 64) blocks; with nqb = ceil(count / 64) query blocks actually
+  // needed, the spare blocks split the database Y = min(32, gridDim.x / nqb) ways: block b scans database part b / nqb for
+  // query block b % nqb and writes its k best to part_d / part_i [Y][count][k]; knn_merge_parts_kernel merges them.
+  int64_t blk = blockIdx.x;
+  int ypart = 0, yparts = 1;
   if (qlist) {
     nq = (int64_t)*qcount;
-    if ((int64_t)blockIdx.x * kKnnQ >= nq) return;
+    if (nq == 0) return;
+    const int64_t nqb = (nq + kKnnQ - 1) / kKnnQ;
+    yparts = (int)min((int64_t)kKnnMaxParts, (int64_t)gridDim.x / nqb);
+    ypart = (int)(blk / nqb);
+    if (ypart >= yparts) return;
+    blk -= (int64_t)ypart * nqb;
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KnnSmem* s = reinterpret_cast<KnnSmem*>(smem_raw);
@@ -98,15 +108,17 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 thread grid, 4 x 4 micro-tile each
-  const int64_t q0 = (int64_t)blockIdx.x * kKnnQ;
+  const int64_t q0 = blk * kKnnQ;
 
   for (int e = tid; e < kKnnQ * k; e += kKnnThreads) { listd[e] = FLT_MAX * 2.f; listi[e] = 0x7fffffff; }  // +inf
   if (tid < kKnnQ) s->tau[tid] = FLT_MAX * 2.f;
   if (tid == 0) s->qcount = 0;
   __syncthreads();
 
-  const int64_t ntiles = (n + kKnnT - 1) / kKnnT;
-  const int64_t t_first = (q0 / kKnnT) % ntiles;  // start with the tile that holds the block's own rows (self-search)
+  const int64_t ntiles_all = (n + kKnnT - 1) / kKnnT;
+  const int64_t tile_lo = qlist ? ntiles_all * ypart / yparts : 0;
+  const int64_t ntiles = qlist ? ntiles_all * (ypart + 1) / yparts - tile_lo : ntiles_all;
+  const int64_t t_first = qlist ? 0 : (q0 / kKnnT) % ntiles;  // start with the tile that holds the block's own rows (self-search)
   const bool single_chunk = d <= kKnnD;
 
   auto load_q_chunk = [&](int d0) {
@@ -120,7 +132,7 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
   if (single_chunk) load_q_chunk(0);
 
   for (int64_t tt = 0; tt < ntiles; ++tt) {
-    const int64_t tile = (t_first + tt) % ntiles;
+    const int64_t tile = tile_lo + (t_first + tt) % ntiles;
     const int64_t c0 = tile * kKnnT;
     float acc[4][4];
 #pragma unroll
@@ -202,11 +214,54 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
     const int r = e / k, c = e % k;
     const int64_t qe = q0 + r;
     if (qe < nq) {
-      const int64_t qi = qlist ? (int64_t)qlist[qe] : qe;
       const int id = listi[e];
       const bool filled = id != 0x7fffffff;
-      out_d[qi * k + c] = filled ? listd[e] : __int_as_float(0x7f800000);
-      out_i[qi * k + c] = filled ? (int64_t)id : (int64_t)-1;
+      if (qlist) {
+        part_d[((int64_t)ypart * nq + qe) * k + c] = filled ? listd[e] : __int_as_float(0x7f800000);
+        part_i[((int64_t)ypart * nq + qe) * k + c] = id;   // 0x7fffffff = empty
+      } else {
+        out_d[qe * k + c] = filled ? listd[e] : __int_as_float(0x7f800000);
+        out_i[qe * k + c] = filled ? (int64_t)id : (int64_t)-1;
+      }
+    }
+  }
+}
+
+// One warp per re-searched query: merge its <= 32 sorted partial lists (one per lane) into the final k nearest.
+__global__ void __launch_bounds__(128)
+knn_merge_parts_kernel(const int* __restrict__ qlist, const unsigned int* __restrict__ qcount, int64_t nblocks_search, int k,
+                       const float* __restrict__ part_d, const int* __restrict__ part_i, float* __restrict__ out_d,
+                       int64_t* __restrict__ out_i) {
+  const int64_t nq = (int64_t)*qcount;
+  const int64_t e = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= nq) return;
+  const int64_t nqb = (nq + kKnnQ - 1) / kKnnQ;
+  const int yparts = (int)min((int64_t)kKnnMaxParts, nblocks_search / nqb);
+  const int64_t qi = qlist[e];
+  const float kInf = __int_as_float(0x7f800000);
+  const float* pd = part_d + ((int64_t)lane * nq + e) * k;
+  const int* pi = part_i + ((int64_t)lane * nq + e) * k;
+  int head = 0;
+  float hd = lane < yparts ? pd[0] : kInf;
+  int hi = lane < yparts ? pi[0] : 0x7fffffff;
+  for (int c = 0; c < k; ++c) {
+    float bd = hd;
+    int bi = hi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (lex_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+      out_d[qi * k + c] = bd;
+      out_i[qi * k + c] = bi == 0x7fffffff ? (int64_t)-1 : (int64_t)bi;
+    }
+    if (bi != 0x7fffffff && hi == bi && hd == bd) {       // the winning lane advances (indices are unique across parts)
+      ++head;
+      hd = head < k ? pd[head] : kInf;
+      hi = head < k ? pi[head] : 0x7fffffff;
     }
   }
 }
@@ -215,12 +270,17 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
 
 namespace mgp {
 // Exact search restricted to the query rows qlist[0 .. *qcount) (device memory); `nq_max` bounds the launch.
+// part_d / part_i: scratch of knn_search_list_part_elems(nq_max, k) floats / ints.
+int64_t knn_search_list_part_elems(int64_t nq_max, int k) { return ceil_div(nq_max, kKnnQ) * kKnnQ * k; }
+
 int knn_search_list(const float* db, int64_t n, const float* q, int64_t nq_max, int d, int k, float* dist2, int64_t* idx,
-                    const int* qlist, const unsigned int* qcount, cudaStream_t st) {
+                    const int* qlist, const unsigned int* qcount, float* part_d, int* part_i, cudaStream_t st) {
   const size_t smem = sizeof(KnnSmem) + (size_t)kKnnQ * k * 8;
   MGP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = ceil_div(nq_max, kKnnQ);
-  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, st>>>(db, n, q, nq_max, d, k, dist2, idx, qlist, qcount);
+  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, st>>>(db, n, q, nq_max, d, k, dist2, idx, qlist, qcount, part_d, part_i);
+  MGP_LAUNCH_CHECK();
+  knn_merge_parts_kernel<<<(unsigned)ceil_div(nq_max, 4), 128, 0, st>>>(qlist, qcount, grid, k, part_d, part_i, dist2, idx);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }
@@ -246,7 +306,7 @@ int mgp_knn_search_f32(const float* db, int64_t n, const float* q, int64_t nq, i
   MGP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = ceil_div(nq, kKnnQ);
   MGP_CHECK_ARG(grid < ((int64_t)1 << 31), "knn_search: too many queries for one launch");
-  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, (cudaStream_t)stream>>>(db, n, q, nq, d, k, dist2, idx, nullptr, nullptr);
+  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, (cudaStream_t)stream>>>(db, n, q, nq, d, k, dist2, idx, nullptr, nullptr, nullptr, nullptr);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

@@ -18,7 +18,8 @@
 //                                    every discarded point exceeded.
 //   3. knn_tc_rerank_kernel          exact fp32 distances of the candidates (sum_d (q_d - x_d)^2, ascending d, mul-then-add:
 //                                    bit-identical to knn.cu), top-k by (distance, index), and the certificate
-//                                    tau_min - E > d_k, E = 8 x (largest |d~ - d| seen on this query's candidates) + floor.
+//                                    tau_min - b - E > d_k with b = mean of d~ - d over the query's candidates (the tensor cores accumulate with
+//                                    truncation: a bias proportional to q.x) and E = |b|/4 + 8 x max |d~ - d - b| + floor.
 //                                    A query that fails it is appended to a list ...
 //   4. knn_kernel (knn.cu)           ... and re-searched exhaustively on the CUDA cores (device-side count, no host sync).
 #include <cuda.h>
@@ -28,21 +29,31 @@
 
 namespace mgp {
 
+int64_t knn_search_list_part_elems(int64_t nq_max, int k);
 int knn_search_list(const float* db, int64_t n, const float* q, int64_t nq_max, int d, int k, float* dist2, int64_t* idx,
-                    const int* qlist, const unsigned int* qcount, cudaStream_t st);
+                    const int* qlist, const unsigned int* qcount, float* part_d, int* part_i, cudaStream_t st);
 
 constexpr int kTcBM = 128;       // query rows per tile  (UMMA M)
-constexpr int kTcBN = 128;       // database points per tile (UMMA N)
-constexpr int kTcBK = 32;        // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B atom row
-constexpr int kTcStages = 3;
-constexpr int kTcTileBytes = kTcBM * kTcBK * 4;      // 16 KB
-constexpr int kTcStageBytes = 4 * kTcTileBytes;      // Qhi, Qlo, Xhi, Xlo
-constexpr int kTcThreads = 192;                      // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 epilogue
-constexpr int kTcTmemCols = 2 * kTcBN;               // double-buffered fp32 accumulator
-constexpr int kTcMaxKp = 64;                         // K' (candidates kept per row)
+constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 epilogue
 constexpr int kTcMaxSplit = 8;
-constexpr int kTcMaxCand = 256;                      // nsplit * K' handled by the re-rank
-constexpr size_t kTcSmemBytes = (size_t)kTcStages * kTcStageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int kTcMaxCand = 256;  // nsplit * K' handled by the re-rank
+
+// Tile configuration: BN database points per tile (UMMA N), BK fp32 elements per k-block (32 = 128-byte rows, SWIZZLE_128B;
+// 16 = 64-byte rows, SWIZZLE_64B), STAGES shared-memory stages of {Qhi, Qlo, Xhi, Xlo}.
+template <int BN_, int BK_, int STAGES_>
+struct TcCfg {
+  static constexpr int BN = BN_, BK = BK_, STAGES = STAGES_;
+  static constexpr int QTileBytes = kTcBM * BK * 4;
+  static constexpr int XTileBytes = BN * BK * 4;
+  static constexpr int StageBytes = 2 * QTileBytes + 2 * XTileBytes;
+  static constexpr int TmemCols = 2 * BN;            // double-buffered fp32 accumulator
+  static constexpr size_t SmemBytes = (size_t)STAGES * StageBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+  // cute::UMMA::InstrDescriptor: c_format F32 = 1 @4, a/b_format TF32 = 2 @7/@10, K-major A and B, N >> 3 @17, M >> 4 @24
+  static constexpr uint32_t Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+  static_assert(BK == 32 || BK == 16, "k-block must be one 128-byte or 64-byte swizzle row");
+  static_assert(TmemCols <= 512 && (TmemCols & (TmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+  static_assert(SmemBytes <= 227 * 1024, "stages do not fit in shared memory");
+};
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -76,20 +87,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major operand tile written by TMA with SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// K-major operand tile written by TMA with a 128-byte (BK = 32) or 64-byte (BK = 16) swizzle: rows of BK * 4 bytes,
+// 8-row groups 8 * BK * 4 bytes apart.
 // (bit layout: cute::UMMA::SmemDescriptor -- start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in
-//  [46,48), layout type SWIZZLE_128B = 2 in [61,64))
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+//  [46,48), layout type in [61,64): SWIZZLE_128B = 2, SWIZZLE_64B = 4)
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
-  d |= (uint64_t)1 << 16;                    // leading byte offset: unused for swizzled K-major operands
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)1 << 16;                          // leading byte offset: unused for swizzled K-major operands
+  d |= (uint64_t)((8 * BK * 4) >> 4) << 32;        // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)(BK == 32 ? 2 : 4) << 61;
   return d;
 }
-// cute::UMMA::InstrDescriptor: c_format F32 = 1 @4, a/b_format TF32 = 2 @7/@10, K-major A and B, N >> 3 @17, M >> 4 @24
-constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 
 // order-preserving float <-> uint32 (so that (key >> 32) sorts like the float and the low word breaks ties by index)
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -146,7 +157,8 @@ struct TcArgs {
   int64_t nq, n;
   int nkb;                  // k-blocks of 32 dims
   int ntiles, nqtiles, nsplit, tiles_per_split;
-  int kp, cap;              // K', candidate-list capacity per row (kp + 32)
+  int kp, cap;              // K', candidate-list capacity per row (kp + 64: compaction when a row holds more than kp + 32)
+  int debug;                // timing experiments only (MGP_KNN_TC_DEBUG): 1 = hi.hi products only, 2 = epilogue skips the selection
   unsigned long long* lists;  // [gridDim.x][128][cap]
   int* cand_idx;            // [nq][nsplit][kp]   (-1 = empty)
   float* cand_dt;           // [nq][nsplit][kp]   approximate distances
@@ -154,37 +166,33 @@ struct TcArgs {
 };
 
 // Keep the kp smallest of the n keys of one row (sorted ascending, in place).  Returns the kp-th key's distance, or
-// FLT_MAX when n < kp.  n <= 96.
+// FLT_MAX when n < kp.  n <= 128.
 __device__ __forceinline__ float tc_compact_row(unsigned long long* rb, int n, int kp, int lane) {
   const unsigned long long kInv = ~0ull;
-  const unsigned long long k0 = lane < n ? __ldcg(rb + lane) : kInv;
-  const unsigned long long k1 = lane + 32 < n ? __ldcg(rb + lane + 32) : kInv;
-  const unsigned long long k2 = lane + 64 < n ? __ldcg(rb + lane + 64) : kInv;
-  int r0 = 0, r1 = 0, r2 = 0;
-#pragma unroll 8
-  for (int j = 0; j < 32; ++j) {
-    const unsigned long long kj = __shfl_sync(0xffffffffu, k0, j);
-    r0 += kj < k0; r1 += kj < k1; r2 += kj < k2;
-  }
-  if (n > 32) {
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const unsigned long long kj = __shfl_sync(0xffffffffu, k1, j);
-      r0 += kj < k0; r1 += kj < k1; r2 += kj < k2;
-    }
-  }
-  if (n > 64) {
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const unsigned long long kj = __shfl_sync(0xffffffffu, k2, j);
-      r0 += kj < k0; r1 += kj < k1; r2 += kj < k2;
+  unsigned long long key[4];
+  int rank[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) key[t] = lane + 32 * t < n ? __ldcg(rb + lane + 32 * t) : kInv;
+#pragma unroll
+  for (int t2 = 0; t2 < 4; ++t2) {
+    if (32 * t2 < n) {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const unsigned long long kj = __shfl_sync(0xffffffffu, key[t2], j);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) rank[t] += kj < key[t];
+      }
     }
   }
   __syncwarp();
   unsigned long long kt = kInv;
-  if (k0 != kInv) { if (r0 < kp) __stcg(rb + r0, k0); if (r0 == kp - 1) kt = k0; }
-  if (k1 != kInv) { if (r1 < kp) __stcg(rb + r1, k1); if (r1 == kp - 1) kt = k1; }
-  if (k2 != kInv) { if (r2 < kp) __stcg(rb + r2, k2); if (r2 == kp - 1) kt = k2; }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (key[t] != kInv) {
+      if (rank[t] < kp) __stcg(rb + rank[t], key[t]);
+      if (rank[t] == kp - 1) kt = key[t];
+    }
+  }
   const unsigned m = __ballot_sync(0xffffffffu, kt != kInv);
   float tau = FLT_MAX;
   if (m) {
@@ -195,9 +203,28 @@ __device__ __forceinline__ float tc_compact_row(unsigned long long* rb, int n, i
   return tau;
 }
 
+// Compact the candidate lists of the rows flagged in `need` (one bit per lane = row of this warp).  Deliberately NOT
+// inlined: the selection loop around it must stay small enough for the instruction cache.  Returns the lane's own new
+// (tau, cnt) packed as {float bits, int}.
+__device__ __noinline__ uint2 tc_compact_rows(unsigned long long* wlists, unsigned need, int cap, int kp, int lane, float tau,
+                                              int cnt) {
+  __syncwarp();
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const int nsrc = __shfl_sync(0xffffffffu, cnt, src);
+    const float tnew = tc_compact_row(wlists + (size_t)src * cap, nsrc, kp, lane);
+    if (lane == src) { tau = tnew; cnt = min(nsrc, kp); }
+  }
+  return make_uint2(__float_as_uint(tau), (unsigned)cnt);
+}
+
+template <class Cfg>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                     const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, const TcArgs g) {
+  constexpr int kTcBN = Cfg::BN, kTcBK = Cfg::BK, kTcStages = Cfg::STAGES, kTcStageBytes = Cfg::StageBytes;
+  constexpr int kQTile = Cfg::QTileBytes, kXTile = Cfg::XTileBytes, kTcTmemCols = Cfg::TmemCols;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kTcStages * kTcStageBytes);
@@ -240,9 +267,9 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
             unsigned char* sb = smem + (size_t)s * kTcStageBytes;
             mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kTcStageBytes);
             tma_load_2d(sb, &tm_qhi, kb * kTcBK, qt * kTcBM, &full_bar[s]);
-            tma_load_2d(sb + kTcTileBytes, &tm_qlo, kb * kTcBK, qt * kTcBM, &full_bar[s]);
-            tma_load_2d(sb + 2 * kTcTileBytes, &tm_xhi, kb * kTcBK, t * kTcBN, &full_bar[s]);
-            tma_load_2d(sb + 3 * kTcTileBytes, &tm_xlo, kb * kTcBK, t * kTcBN, &full_bar[s]);
+            tma_load_2d(sb + kQTile, &tm_qlo, kb * kTcBK, qt * kTcBM, &full_bar[s]);
+            tma_load_2d(sb + 2 * kQTile, &tm_xhi, kb * kTcBK, t * kTcBN, &full_bar[s]);
+            tma_load_2d(sb + 2 * kQTile + kXTile, &tm_xlo, kb * kTcBK, t * kTcBN, &full_bar[s]);
             if (++s == kTcStages) { s = 0; ph ^= 1u; }
           }
         }
@@ -266,15 +293,17 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t sb = smem_u32(smem + (size_t)s * kTcStageBytes);
-            const uint64_t dqh = umma_desc_sw128(sb), dql = umma_desc_sw128(sb + kTcTileBytes);
-            const uint64_t dxh = umma_desc_sw128(sb + 2 * kTcTileBytes), dxl = umma_desc_sw128(sb + 3 * kTcTileBytes);
+            const uint64_t dqh = umma_desc_kmajor<kTcBK>(sb), dql = umma_desc_kmajor<kTcBK>(sb + kQTile);
+            const uint64_t dxh = umma_desc_kmajor<kTcBK>(sb + 2 * kQTile), dxl = umma_desc_kmajor<kTcBK>(sb + 2 * kQTile + kXTile);
 #pragma unroll
             for (int ks = 0; ks < kTcBK / 8; ++ks)     // +32 bytes per K = 8 step inside the swizzle atom
-              tc_mma_tf32(tacc, dqh + 2 * ks, dxh + 2 * ks, kTcIdesc, (kb | ks) != 0);
+              tc_mma_tf32(tacc, dqh + 2 * ks, dxh + 2 * ks, Cfg::Idesc, (kb | ks) != 0);
+            if (!(g.debug & 1)) {
 #pragma unroll
-            for (int ks = 0; ks < kTcBK / 8; ++ks) tc_mma_tf32(tacc, dqh + 2 * ks, dxl + 2 * ks, kTcIdesc, 1u);
+              for (int ks = 0; ks < kTcBK / 8; ++ks) tc_mma_tf32(tacc, dqh + 2 * ks, dxl + 2 * ks, Cfg::Idesc, 1u);
 #pragma unroll
-            for (int ks = 0; ks < kTcBK / 8; ++ks) tc_mma_tf32(tacc, dql + 2 * ks, dxh + 2 * ks, kTcIdesc, 1u);
+              for (int ks = 0; ks < kTcBK / 8; ++ks) tc_mma_tf32(tacc, dql + 2 * ks, dxh + 2 * ks, Cfg::Idesc, 1u);
+            }
             tc_commit(&empty_bar[s]);      // the stage is free once these MMAs have read it
             if (++s == kTcStages) { s = 0; ph ^= 1u; }
           }
@@ -310,8 +339,10 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
           }
+          if (g.debug & 2) continue;
           const int col0 = t * kTcBN + ch * 32;
           const float xv = __ldg(g.xn + col0 + lane);
+          // the list has room for a whole chunk here (cnt <= kp + 32 = cap - 32): no overflow check per candidate
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const float xc = __shfl_sync(0xffffffffu, xv, c);
@@ -320,26 +351,23 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
               __stcg(mylist + cnt, ((unsigned long long)f2ord(dt) << 32) | (unsigned)(col0 + c));
               ++cnt;
             }
-            unsigned need = __ballot_sync(0xffffffffu, cnt == g.cap);
-            while (need) {                           // warp-uniform: compact the full lists, one row at a time
-              const int src = __ffs(need) - 1;
-              need &= need - 1;
-              __syncwarp();
-              const float tnew = tc_compact_row(wlists + (size_t)src * g.cap, g.cap, g.kp, lane);
-              if (lane == src) { tau = tnew; cnt = g.kp; }
-            }
+          }
+          const unsigned need = __ballot_sync(0xffffffffu, cnt > g.kp + 32);
+          if (need) {
+            const uint2 r = tc_compact_rows(wlists, need, g.cap, g.kp, lane, tau, cnt);
+            tau = __uint_as_float(r.x);
+            cnt = (int)r.y;
           }
         }
       }
       // ---- item done: final compaction and write-out ----
-      unsigned need = __ballot_sync(0xffffffffu, cnt > g.kp);
-      __syncwarp();
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int nsrc = __shfl_sync(0xffffffffu, cnt, src);
-        const float tnew = tc_compact_row(wlists + (size_t)src * g.cap, nsrc, g.kp, lane);
-        if (lane == src) { tau = tnew; cnt = g.kp; }
+      {
+        const unsigned need = __ballot_sync(0xffffffffu, cnt > g.kp);
+        if (need) {
+          const uint2 r = tc_compact_rows(wlists, need, g.cap, g.kp, lane, tau, cnt);
+          tau = __uint_as_float(r.x);
+          cnt = (int)r.y;
+        }
       }
       __syncwarp();
       for (int rr = 0; rr < 32; ++rr) {
@@ -386,11 +414,13 @@ knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, 
   const float kInf = __int_as_float(0x7f800000);
   float ed[T];
   int ei[T];
-  float err = 0.f;
+  float err = 0.f, bsum = 0.f;
+  float diff[T];
   int nvalid = 0;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int e = lane + 32 * t;
+    diff[t] = 0.f;
     const int id = e < total ? cand_idx[(size_t)qi * total + e] : -1;
     float acc = kInf;
     if (id >= 0) {
@@ -411,15 +441,28 @@ knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, 
           acc = __fadd_rn(acc, __fmul_rn(df, df));
         }
       }
-      err = fmaxf(err, fabsf(acc - cand_dt[(size_t)qi * total + e]));
+      diff[t] = cand_dt[(size_t)qi * total + e] - acc;
+      err = fmaxf(err, fabsf(diff[t]));
+      bsum += diff[t];
       ++nvalid;
     }
     ed[t] = acc;
     ei[t] = id >= 0 ? id : 0x7fffffff;
   }
   nvalid = warp_sum(nvalid);
+  bsum = warp_sum(bsum);
+  // The tensor cores accumulate with truncation, so d~ - d is dominated by a bias proportional to q.x (measured: ~2e-5
+  // relative), nearly identical for all near candidates.  b = mean bias of this query's candidates, res = largest deviation.
+  const float bias = nvalid > 0 ? bsum / (float)nvalid : 0.f;
+  float res = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+  for (int t = 0; t < T; ++t)
+    if (ei[t] != 0x7fffffff) res = fmaxf(res, fabsf(diff[t] - bias));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+    res = fmaxf(res, __shfl_xor_sync(0xffffffffu, res, o));
+  }
 
   int rank[T];
 #pragma unroll
@@ -453,8 +496,8 @@ knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, 
     for (int s = 0; s < nsplit; ++s) tmin = fminf(tmin, tau_s[(size_t)qi * nsplit + s]);
     bool ok = true;
     if (tmin < FLT_MAX) {          // something was discarded: it must be provably farther than the k-th neighbour
-      const float e = 8.f * err + 9.5367431640625e-07f * (4.f * qn[qi] + 2.f * fabsf(tmin));
-      ok = (nvalid >= k) && (tmin - e > dk);
+      const float e = 0.25f * fabsf(bias) + 8.f * res + 9.5367431640625e-07f * (4.f * qn[qi] + 2.f * fabsf(tmin));
+      ok = (nvalid >= k) && (tmin - bias - e > dk);
     }
     if (!ok) {
       const unsigned pos = atomicAdd(&stats[0], 1u);
@@ -482,32 +525,51 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// [rows, dp] fp32 row-major, box = 128 rows x 32 elements, 128-byte swizzle, out-of-range elements read as zero
-static int make_tile_map(CUtensorMap* tm, const float* base, int64_t rows, int dp) {
+// [rows, dp] fp32 row-major, box = box_rows x bk elements, swizzle = row bytes, out-of-range elements read as zero
+static int make_tile_map(CUtensorMap* tm, const float* base, int64_t rows, int dp, int box_rows, int bk) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) { set_error("knn_tc: cuTensorMapEncodeTiled is not available from the driver"); return MGP_ECUDA; }
   const cuuint64_t gdim[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)dp * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBM};
+  const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("knn_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MGP_ECUDA; }
   return MGP_OK;
 }
 
 struct TcPlan {
+  int variant, bn, bk;
   int dp, nkb, ntiles, nqtiles, nsplit, tiles_per_split, kp, cap, grid;
   int64_t npad, nqpad;
   bool same;
   // workspace offsets (bytes)
-  size_t o_sums, o_xhi, o_xlo, o_xn, o_qhi, o_qlo, o_qn, o_lists, o_cidx, o_cdt, o_tau, o_flag, total;
+  size_t o_sums, o_xhi, o_xlo, o_xn, o_qhi, o_qlo, o_qn, o_lists, o_cidx, o_cdt, o_tau, o_flag, o_pd, o_pi, total;
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// tile configurations (TcCfg<BN, BK, STAGES>), selectable with MGP_KNN_TC_VARIANT for experiments
+using TcCfg0 = TcCfg<128, 32, 3>;
+using TcCfg1 = TcCfg<256, 32, 2>;
+using TcCfg2 = TcCfg<256, 16, 4>;
+using TcCfg3 = TcCfg<128, 16, 6>;
+constexpr int kTcDefaultVariant = 1;
+
+static int tc_variant() {
+  const char* e = getenv("MGP_KNN_TC_VARIANT");
+  const int v = e ? atoi(e) : kTcDefaultVariant;
+  return (v >= 0 && v <= 3) ? v : kTcDefaultVariant;
+}
+
 static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
+  p->variant = tc_variant();
+  p->bn = (p->variant == 1 || p->variant == 2) ? 256 : 128;
+  p->bk = (p->variant >= 2) ? 16 : 32;
+  const int kTcBN = p->bn, kTcBK = p->bk;
   if (d < 16 || k < 1 || k > 48 || n < 256 || n >= ((int64_t)1 << 31) - 256 || nq < 1 || nq >= ((int64_t)1 << 31) - 256) return false;
   p->same = same;
   p->dp = (d + 3) & ~3;
@@ -515,7 +577,7 @@ static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->ntiles = (int)ceil_div(n, kTcBN);
   p->nqtiles = (int)ceil_div(nq, kTcBM);
   p->kp = ((k + 16 + 31) / 32) * 32;            // 32 or 64
-  p->cap = p->kp + 32;
+  p->cap = p->kp + 64;
   int smax = kTcMaxCand / p->kp;
   if (smax > kTcMaxSplit) smax = kTcMaxSplit;
   int s = (int)ceil_div((int64_t)kNumSMs * 6, p->nqtiles);   // aim for >= 6 waves of work items
@@ -545,8 +607,19 @@ static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->o_cdt = o; o = align256(o + (size_t)nq * p->nsplit * p->kp * 4);
   p->o_tau = o; o = align256(o + (size_t)nq * p->nsplit * 4);
   p->o_flag = o; o = align256(o + (size_t)nq * 4);
+  p->o_pd = o; o = align256(o + (size_t)knn_search_list_part_elems(nq, k) * 4);
+  p->o_pi = o; o = align256(o + (size_t)knn_search_list_part_elems(nq, k) * 4);
   p->total = o;
   return true;
+}
+
+template <class Cfg>
+static int launch_sweep(int grid, const CUtensorMap& tm_qhi, const CUtensorMap& tm_qlo, const CUtensorMap& tm_xhi,
+                        const CUtensorMap& tm_xlo, const TcArgs& g, cudaStream_t st) {
+  MGP_CUDA(cudaFuncSetAttribute(knn_tc_sweep_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SmemBytes));
+  knn_tc_sweep_kernel<Cfg><<<(unsigned)grid, kTcThreads, Cfg::SmemBytes, st>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, g);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
 }
 
 template <int T>
@@ -601,21 +674,26 @@ int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq
 
   CUtensorMap tm_qhi, tm_qlo, tm_xhi, tm_xlo;
   int rc;
-  if ((rc = make_tile_map(&tm_qhi, qhi, nq, p.dp)) != MGP_OK) return rc;
-  if ((rc = make_tile_map(&tm_qlo, qlo, nq, p.dp)) != MGP_OK) return rc;
-  if ((rc = make_tile_map(&tm_xhi, xhi, n, p.dp)) != MGP_OK) return rc;
-  if ((rc = make_tile_map(&tm_xlo, xlo, n, p.dp)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_qhi, qhi, nq, p.dp, kTcBM, p.bk)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_qlo, qlo, nq, p.dp, kTcBM, p.bk)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_xhi, xhi, n, p.dp, p.bn, p.bk)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_xlo, xlo, n, p.dp, p.bn, p.bk)) != MGP_OK) return rc;
 
   TcArgs g;
   g.qn = qn; g.xn = xn; g.nq = nq; g.n = n; g.nkb = p.nkb; g.ntiles = p.ntiles; g.nqtiles = p.nqtiles; g.nsplit = p.nsplit;
   g.tiles_per_split = p.tiles_per_split; g.kp = p.kp; g.cap = p.cap;
+  { const char* e = getenv("MGP_KNN_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
   g.lists = reinterpret_cast<unsigned long long*>(w + p.o_lists);
   g.cand_idx = reinterpret_cast<int*>(w + p.o_cidx);
   g.cand_dt = reinterpret_cast<float*>(w + p.o_cdt);
   g.tau = reinterpret_cast<float*>(w + p.o_tau);
-  MGP_CUDA(cudaFuncSetAttribute(knn_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-  knn_tc_sweep_kernel<<<(unsigned)p.grid, kTcThreads, kTcSmemBytes, st>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, g);
-  MGP_LAUNCH_CHECK();
+  switch (p.variant) {
+    case 0: rc = launch_sweep<TcCfg0>(p.grid, tm_qhi, tm_qlo, tm_xhi, tm_xlo, g, st); break;
+    case 1: rc = launch_sweep<TcCfg1>(p.grid, tm_qhi, tm_qlo, tm_xhi, tm_xlo, g, st); break;
+    case 2: rc = launch_sweep<TcCfg2>(p.grid, tm_qhi, tm_qlo, tm_xhi, tm_xlo, g, st); break;
+    default: rc = launch_sweep<TcCfg3>(p.grid, tm_qhi, tm_qlo, tm_xhi, tm_xlo, g, st); break;
+  }
+  if (rc != MGP_OK) return rc;
 
   const int total = p.nsplit * p.kp;
   if (total <= 32) launch_rerank<1>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
@@ -625,7 +703,8 @@ int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq
   MGP_LAUNCH_CHECK();
 
   // queries whose certificate failed: exhaustive CUDA-core search (device-side count; blocks beyond it exit at once)
-  return knn_search_list(db, n, q, nq, d, k, dist2, idx, reinterpret_cast<const int*>(w + p.o_flag), stats, st);
+  return knn_search_list(db, n, q, nq, d, k, dist2, idx, reinterpret_cast<const int*>(w + p.o_flag), stats,
+                         reinterpret_cast<float*>(w + p.o_pd), reinterpret_cast<int*>(w + p.o_pi), st);
 }
 
 }  // extern "C"
