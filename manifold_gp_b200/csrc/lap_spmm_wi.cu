@@ -27,17 +27,14 @@
 namespace mgp {
 
 constexpr int kWiMaxStages = 3;
-constexpr int kWiProducerWarps = 4;
-constexpr int kWiProducerThreads = kWiProducerWarps * 32;
 constexpr int kWiConsumerWarps = 16;
-constexpr int kWiThreads = (kWiConsumerWarps + kWiProducerWarps) * 32;
 constexpr int kWiRows = 128;                       // rows per tile = 16 consumer warps x 8 row slots
 constexpr int kWiIdSlots = 4;                      // halo-id ring: ids are requested this many tiles ahead
 constexpr int kWiChunk = 32;                       // tiles per metadata chunk
 constexpr int kWiMetaW = 16 * kWiChunk + 4;        // ints of wptr per chunk (513 used)
 constexpr int kWiMetaH = kWiChunk + 4;             // ints of hptr per chunk (33 used)
 constexpr int kWiMetaBytes = (kWiMetaW + kWiMetaH) * 4;
-constexpr size_t kWiSmemLimit = 232448 - 8192;    // dynamic; static shared memory (dot epilogue, barriers) stays < 8 KB
+constexpr size_t kWiSmemLimit = 232448 - 10240;   // dynamic; static shared memory (dot epilogue, barriers) stays < 8 KB
 
 template <typename T>
 struct WiArgs {
@@ -85,7 +82,8 @@ __host__ __device__ inline size_t wi_stage_bytes(int lmax, int nzcap) {
 }
 __host__ __device__ inline size_t wi_ring_bytes(int hmax) { return 2 * (size_t)kWiMetaBytes + (size_t)kWiIdSlots * hmax * 4; }
 
-__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWiProducerThreads) : "memory"); }
+template <int PW>
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory"); }
 
 // Design notes (what three rounds of ncu / timing experiments on B200 established, profiles/):
 //  * consumers are bound by shared-memory wavefronts: 16 per 32 nonzeros for the 64-byte X rows; the warp-interleaved
@@ -102,9 +100,10 @@ __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;
 //      - the producers then only read shared memory (tens of cycles) and issue copies: thread 0 the three bulk copies of
 //        the stage, thread 32 the ring refills, all 128 the 16-byte cp.async of the halo rows (4 lanes per row);
 //      - the diagonal is read by the consumers themselves (issued before the row walk, used after it).
-template <typename T>
-__global__ void __launch_bounds__(kWiThreads, 1)
+template <typename T, int PW>
+__global__ void __launch_bounds__((kWiConsumerWarps + PW) * 32, 1)
 lap_spmm_wi_kernel(const WiArgs<T> g) {
+  constexpr int kWiProducerWarps = PW, kWiProducerThreads = PW * 32, kWiThreads = (kWiConsumerWarps + PW) * 32;
   constexpr int R = kWiRows;
   constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte chunk
   constexpr int CW = 4 * VEC;                  // columns per pass: 64-byte rows
@@ -230,7 +229,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         peers_ready = true;
       }
       // scattered X rows: 4 consecutive lanes copy the four 16-byte chunks of one row (8 whole rows per warp instruction)
-      for (int rr = 8 * pw + sub; rr < nscat; rr += 32) {
+      for (int rr = 8 * pw + sub; rr < nscat; rr += 8 * kWiProducerWarps) {
         int sr = rr < nown ? (int)(row0 + rr) : ids[rr - nown];
         if (g.xmap) sr = __ldg(g.xmap + sr);
         const int dstrow = rr < nown ? rr : R + (rr - nown);
@@ -244,7 +243,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
       cp_async_arrive_noinc(&full_bar[s]);
       if (tid <= 16) rp[tid] = wp[tid] - base;
       if (tid != 0) mbar_arrive(&full_bar[s]);
-      producers_sync();                                            // everyone is done with this tile's id slot and metadata
+      producers_sync<PW>();                                          // everyone is done with this tile's id slot and metadata
       if (tid == 32) {
         const int tn = t + kWiIdSlots;
         if (tn < t1) {
@@ -436,7 +435,16 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   g.partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
   g.dot_is_x = (dot_out && dot_with == x) ? 1 : 0;
   { const char* dbg = getenv("MGP_WI_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
-  auto kern = lap_spmm_wi_kernel<T>;
+  // producer warps: measured on B200 (cfg-C, C = 16, fp32): 4 -> 163.7 us, 8 -> 144.0, 12 -> 133.4, 16 -> 127.0 (the halo
+  // cp.async issue shares the LSU queue with the consumers' shared-memory loads; more producer warps = a larger share)
+  static const int pw = [] {
+    const char* e = getenv("MGP_WI_PW");
+    const int v = e ? atoi(e) : (sizeof(T) == 4 ? 16 : 8);
+    if (v == 16) return sizeof(T) == 4 ? 16 : 12;      // fp64 at 1024 threads would spill (64 registers)
+    return (v == 4 || v == 8 || v == 12) ? v : 8;
+  }();
+  auto kern = pw == 16 ? lap_spmm_wi_kernel<T, 16> : pw == 12 ? lap_spmm_wi_kernel<T, 12> : pw == 8 ? lap_spmm_wi_kernel<T, 8> : lap_spmm_wi_kernel<T, 4>;
+  const int kWiThreads = (kWiConsumerWarps + pw) * 32;
   static size_t configured = 0;   // per instantiation
   if (smem > configured) {
     MGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -329,6 +329,16 @@ class PeerCG(DistCG):
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.rbuf_pap = torch.zeros(ncols, dtype=dtype, device=dev)
         self.tmp = None
+        # fused iteration (default): the cross-GPU barriers ride inside the SpMM launches and the two all-reduces inside the
+        # r / (p, x) update kernels, all keyed by the iteration counter in ``state`` -> 2 nu + 2... = nu + 2 launches.
+        import os
+        self.fused = os.environ.get("MGP_PEER_FUSED", "1") != "0" and self.ld <= 128 and (self.ld & (self.ld - 1)) == 0
+        if self.fused:
+            self.red2, self.red2_ptrs = self.mem.alloc((2 * 2 * self.world * 128,), dtype)
+            nflag = op.nu + 2                                        # one flag array per SpMM stage + p^T A p + |r|^2
+            self.flags2, base = self.mem.alloc((nflag, 64), torch.int32)
+            self.flag_tabs = [(base + 64 * 4 * i).contiguous() for i in range(nflag)]
+            self.iter_scalar = self.state[solvers.S_NARR * ncols + solvers.K_ITER:]
         self.mem.sync()
 
     # -- building blocks -----------------------------------------------------------------------------------------------
@@ -354,10 +364,12 @@ class PeerCG(DistCG):
         for s in range(op.nu):
             last = s == op.nu - 1
             dst, dst_ptrs = (self.v, None) if last else self.tmps[s]
-            self._barrier()                                      # the source vector is complete on every rank
+            if not self.fused:
+                self._barrier()                                  # the source vector is complete on every rank
             graph.lap_spmm(op.st, op.a, op.diag, src[:n_loc, :c], shift=op.shift, out=dst[:n_loc, :c],
                            dot_with=self.p[:n_loc, :c] if last else None, dot_out=self.rbuf_pap if last else None,
-                           peer_x=src_ptrs)
+                           peer_x=src_ptrs,
+                           peer_sync=(self.rank, self.flag_tabs[s], self.iter_scalar) if self.fused else None)
             src, src_ptrs = dst, dst_ptrs
 
     def _iteration(self):
@@ -366,6 +378,15 @@ class PeerCG(DistCG):
         sfx = _lib.suffix(self.dt)
         n_loc, c, ld = self.op.n_loc, self.c, self.ld
         self._matvec()
+        if self.fused:
+            nu = self.op.nu
+            _lib.call("mgp_cg_peer_rupdate_" + sfx, ptr(self.r), ptr(self.v), c_int64(ld), c_int64(n_loc), c_int32(c),
+                      ptr(self.state), ptr(self.rbuf_pap), ptr(self.ws), ptr(self.red2_ptrs), ptr(self.flag_tabs[nu]),
+                      ptr(self.flag_tabs[nu + 1]), c_int32(self.rank), c_int32(self.world), stream())
+            _lib.call("mgp_cg_peer_pxupdate_" + sfx, ptr(self.x), ptr(self.p), ptr(self.r), c_int64(ld), c_int64(n_loc),
+                      c_int32(c), ptr(self.state), None, c_int32(0), ptr(self.ws), ptr(self.red2_ptrs),
+                      ptr(self.flag_tabs[nu + 1]), c_int32(self.rank), c_int32(self.world), stream())
+            return
         self._scalars(3, self.rbuf_pap)                          # all-reduce(p^T A p) -> state
         _lib.call("mgp_cg_rupdate_" + sfx, ptr(self.r), ptr(self.v), c_int64(ld), c_int64(n_loc), c_int32(c), ptr(self.state),
                   None, c_int32(0), ptr(self.rbuf), ptr(self.ws), stream())
@@ -375,6 +396,15 @@ class PeerCG(DistCG):
 
     def _allreduce_rbuf(self):
         pass                                                     # fused into _scalars
+
+    def solve(self, b_loc: torch.Tensor):
+        if self.fused:
+            # the iteration-keyed flags restart from zero every solve: nobody may still be publishing into them (barrier),
+            # and nobody may publish before everyone has zeroed (barrier)
+            self._barrier()
+            self.flags2.zero_()
+            self._barrier()
+        return super().solve(b_loc)
 
 
 def dist_cg(op: DistPrecision, b_loc: torch.Tensor, tolerance=1e-6, eps=1e-10, stop_updating_after=1e-10, max_iter=1000,

@@ -371,7 +371,13 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 
 
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
+LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call launched (bench.py reports it)
 SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi"  (tests force each; "auto": wi, else pipe, else tiled, else csr)
+
+
+def _note_kernel(name):
+    global LAST_SPMM_KERNEL
+    LAST_SPMM_KERNEL = name
 
 
 def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
@@ -420,6 +426,7 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
                               c_int32(0 if peer_sync is None else int(peer_sync[0])), ptr(None if peer_sync is None else peer_sync[1]),
                               ptr(None if peer_sync is None else peer_sync[2]), stream())
             if rc == 0:
+                _note_kernel("lap_spmm_wi_kernel")
                 return out
             if rc != _lib.MGP_EUNSUPPORTED or peer_x is not None:
                 raise RuntimeError(f"mgp_lap_spmm_wi_{sfx} failed ({rc}): {_lib.last_error()}")
@@ -434,6 +441,7 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
                               ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
                               c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())
             if rc == 0:
+                _note_kernel("lap_spmm_pipe_kernel")
                 return out
             if rc != _lib.MGP_EUNSUPPORTED:
                 raise RuntimeError(f"mgp_lap_spmm_pipe_{sfx} failed ({rc}): {_lib.last_error()}")
@@ -446,6 +454,7 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
                           ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
                           c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())
         if rc == 0:
+            _note_kernel("lap_spmm_tiled_kernel")
             return out
         if rc != _lib.MGP_EUNSUPPORTED or SPMM_KERNEL == "tiled":
             raise RuntimeError(f"mgp_lap_spmm_tiled_{sfx} failed ({rc}): {_lib.last_error()}")
@@ -458,6 +467,7 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
         if dot_with is not None:
             dot_with = dot_with.index_select(0, st.perm)
     y = torch.empty((st.n, c), dtype=dt, device=x.device) if (out is None or y_external) else out
+    _note_kernel("lap_spmm_csr_kernel")
     _lib.call("mgp_lap_spmm_" + sfx, ptr(st.rowptr), ptr(st.col), ptr(a), ptr(diag), ptr(shift_t),
               ptr(pre), ptr(post), ptr(x), c_int64(x.stride(0)), ptr(y), c_int64(y.stride(0)), c_int64(st.n),
               c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws), stream())

@@ -8,7 +8,8 @@ cached on ``edge_index``, only the O(nnz) value build is redone when the bandwid
 ``eval()`` (:117-130): the reference assembles the dense N x N Laplacian and calls ``torch.linalg.eigh`` -- O(N^3), which
 makes BASELINE cfg-B (70k points) impossible.  Here the dense branch is kept for ``N <= dense_eigh_limit`` (bit-for-bit the
 reference's post-processing) and larger graphs use the Lanczos path the reference left commented out at :120
-(``laplacian_operator.diagonalization(num_modes=...)`` -> CUDA Lanczos).
+(``laplacian_operator.diagonalization(num_modes=...)``), with the eigensolver swapped for one that converges at the
+bottom of the spectrum (``solvers.smallest_eigenpairs``, Chebyshev-filtered subspace iteration over the CUDA SpMM).
 """
 from __future__ import annotations
 
@@ -38,6 +39,7 @@ else:
 class RiemannKernel(_KernelBase):
     has_lengthscale = True
     dense_eigh_limit = 20000
+    large_graph_method = "chebyshev"      # "lanczos" reproduces linear_operator's diagonalization (see eval())
 
     def __init__(self,
                  x: torch.Tensor,
@@ -62,10 +64,7 @@ class RiemannKernel(_KernelBase):
         if graphbandwidth_constraint is None:
             graphbandwidth_constraint = Positive()
 
-        self.register_parameter(
-            name='raw_graphbandwidth',
-            parameter=torch.nn.Parameter(torch.zeros(*self.batch_shape, 1, 1)),
-        )
+        self.register_parameter('raw_graphbandwidth', torch.nn.Parameter(torch.zeros(*self.batch_shape, 1, 1)))
 
         if graphbandwidth_prior is not None:
             if not isinstance(graphbandwidth_prior, _Prior):
@@ -130,7 +129,11 @@ class RiemannKernel(_KernelBase):
                 eigval, eigvec = torch.linalg.eigh(dense)
                 eigval, eigvec = eigval[:self.num_modes].clone(), eigvec[:, :self.num_modes].clone()
             else:
-                eigval, eigvec = self.laplacian_operator._symmetric_twin().diagonalization(method="lanczos",
+                # the SMALLEST num_modes eigenpairs: Chebyshev-filtered subspace iteration over the CUDA SpMM
+                # (solvers.smallest_eigenpairs).  method="lanczos" -- linear_operator's 3 * num_modes-step Lanczos, the
+                # call the reference left commented out at :120 -- converges at the top of the spectrum first and does not
+                # deliver them at this size.
+                eigval, eigvec = self.laplacian_operator._symmetric_twin().diagonalization(method=self.large_graph_method,
                                                                                            num_modes=self.num_modes)
             eigval[0] = 0.0
             eigvec = eigvec * self.laplacian_operator.degree_mat.pow(-0.5).view(-1, 1)

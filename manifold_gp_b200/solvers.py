@@ -272,6 +272,70 @@ def lanczos_tridiag_to_diag(t_mat):
     return evals, evecs
 
 
+def smallest_eigenpairs(op, num_modes, rtol=1e-6, degree=24, max_outer=60, extra=None, generator=None, return_info=False):
+    """The ``num_modes`` smallest eigenpairs of a symmetric positive semi-definite operator by Chebyshev-filtered subspace
+    iteration (Zhou & Saad): a block of ``num_modes + extra`` vectors is repeatedly pushed through a degree-``degree``
+    Chebyshev polynomial of the operator that damps [largest Ritz value of the block, lambda_max] (``degree`` batched SpMMs,
+    every 16 columns one pass of the fused SpMM kernel), re-orthonormalised and Rayleigh-Ritz rotated, until
+    ``|A x - theta x| <= rtol * lambda_max`` for the wanted pairs.
+
+    Why it exists: ``RiemannKernel.eval`` needs the SMALLEST eigenpairs (riemann_kernel.py:117-130 gets them from a dense
+    ``eigh``, O(N^3)).  ``diagonalization(method="lanczos")`` reproduces linear_operator's 3 * num_modes-step Lanczos, whose
+    Ritz values converge at the TOP of the spectrum first: at N >> 3 * num_modes (BASELINE cfg-B: N = 70k, 500 modes) its
+    lowest ``num_modes`` Ritz pairs are not eigenpairs (measured residual |L phi - lambda phi| ~ 1).  The filter turns the
+    same matvec kernel into a solver that converges at the bottom.  Dense pieces (QR of [N, b], b x b ``eigh``) are plain
+    library calls on small matrices."""
+    n = op.shape[0]
+    dt, dev = op.dtype, op.device
+    if dev.type != "cuda":
+        raise RuntimeError("smallest_eigenpairs: operator must live on a CUDA device (no CPU fallback exists)")
+    m = int(min(num_modes, n))
+    if extra is None:
+        extra = max(32, m // 4)
+    b = min(n, ((m + extra + 15) // 16) * 16)
+    with torch.no_grad():
+        # upper bound of the spectrum: largest Ritz value of a short Lanczos run + its residual norm
+        _, t = lanczos_tridiag(op, min(40, n), generator=generator)
+        th = torch.linalg.eigvalsh(t.double())
+        lam_max = float(th[-1]) + (float(t[-1, -2].abs()) if t.shape[0] > 1 else 0.0)
+        lam_max *= 1.01
+        x = torch.randn(n, b, dtype=dt, device=dev, generator=generator)
+        x, _ = torch.linalg.qr(x)
+        info = {"outer": 0, "matvec_columns": 0, "lam_max": lam_max, "block": b}
+        theta = None
+        for outer in range(max_outer + 1):
+            ax = op._matmul(x)
+            info["matvec_columns"] += b
+            h = (x.transpose(0, 1) @ ax).double()
+            theta, v = torch.linalg.eigh(0.5 * (h + h.transpose(0, 1)))
+            v = v.to(dt)
+            x, ax = x @ v, ax @ v
+            res = (ax - x * theta.to(dt)).norm(dim=0)
+            worst = float(res[:m].max())
+            info.update(outer=outer, residual=worst)
+            if worst <= rtol * lam_max or outer == max_outer:
+                break
+            # damp [a, lam_max]; a = largest Ritz value of the block, a0 = smallest (the scaling point)
+            a, a0 = float(theta[-1]), float(theta[0])
+            a = max(a, a0 + 1e-6 * lam_max)
+            e, c = 0.5 * (lam_max - a), 0.5 * (lam_max + a)
+            sigma = e / (a0 - c)
+            sigma1 = sigma
+            y = (ax - c * x) * (sigma1 / e)
+            for _ in range(2, degree + 1):
+                sigma2 = 1.0 / (2.0 / sigma1 - sigma)
+                ay = op._matmul(y)
+                info["matvec_columns"] += b
+                ynew = (ay - c * y) * (2.0 * sigma2 / e) - (sigma * sigma2) * x
+                x, y, sigma = y, ynew, sigma2
+            x, _ = torch.linalg.qr(y)
+        evals = theta[:m].to(dt)
+        evecs = x[:, :m].contiguous()
+    if return_info:
+        return evals, evecs, info
+    return evals, evecs
+
+
 def diagonalization(op, method=None):
     """``LinearOperator.diagonalization``: 'symeig' (dense) when size <= max_cholesky_size, else 'lanczos' with
     ``settings.max_root_decomposition_size`` steps.  Returns (evals ascending, DenseEigenvectors)."""
@@ -287,6 +351,9 @@ def diagonalization(op, method=None):
             q, t = lanczos_tridiag(op, settings.max_root_decomposition_size.value())
             evals, v = lanczos_tridiag_to_diag(t)
             evecs = q.T @ v       # plain library GEMM [n, j] x [j, j]
+        return evals, DenseEigenvectors(evecs)
+    if method == "chebyshev":
+        evals, evecs = smallest_eigenpairs(op, min(n, max(1, settings.max_root_decomposition_size.value() // 3)))
         return evals, DenseEigenvectors(evecs)
     raise RuntimeError(f"Unknown diagonalization method '{method}'")
 
