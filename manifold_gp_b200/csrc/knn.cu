@@ -82,6 +82,7 @@ __device__ __forceinline__ void knn_drain(KnnSmem* s, float* listd, int* listi, 
   }
 }
 
+template <bool LIST>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q, int64_t nq, int d, int k,
            float* __restrict__ out_d, int64_t* __restrict__ out_i, const int* __restrict__ qlist,
@@ -92,7 +93,7 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
   // query block b % nqb and writes its k best to part_d / part_i [Y][count][k]; knn_merge_parts_kernel merges them.
   int64_t blk = blockIdx.x;
   int ypart = 0, yparts = 1;
-  if (qlist) {
+  if (LIST) {
     nq = (int64_t)*qcount;
     if (nq == 0) return;
     const int64_t nqb = (nq + kKnnQ - 1) / kKnnQ;
@@ -116,16 +117,16 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
   __syncthreads();
 
   const int64_t ntiles_all = (n + kKnnT - 1) / kKnnT;
-  const int64_t tile_lo = qlist ? ntiles_all * ypart / yparts : 0;
-  const int64_t ntiles = qlist ? ntiles_all * (ypart + 1) / yparts - tile_lo : ntiles_all;
-  const int64_t t_first = qlist ? 0 : (q0 / kKnnT) % ntiles;  // start with the tile that holds the block's own rows (self-search)
+  const int64_t tile_lo = LIST ? ntiles_all * ypart / yparts : 0;
+  const int64_t ntiles = LIST ? ntiles_all * (ypart + 1) / yparts - tile_lo : ntiles_all;
+  const int64_t t_first = LIST ? 0 : (q0 / kKnnT) % ntiles;  // start with the tile that holds the block's own rows (self-search)
   const bool single_chunk = d <= kKnnD;
 
   auto load_q_chunk = [&](int d0) {
     for (int e = tid; e < kKnnD * kKnnQ; e += kKnnThreads) {
       const int r = e % kKnnQ, dd = e / kKnnQ;
       const int64_t qe = q0 + r;
-      const int64_t qi = qe < nq ? (qlist ? (int64_t)qlist[qe] : qe) : 0;
+      const int64_t qi = qe < nq ? (LIST ? (int64_t)qlist[qe] : qe) : 0;
       s->qs[dd][r] = (qe < nq && d0 + dd < d) ? __ldg(q + qi * d + d0 + dd) : 0.f;
     }
   };
@@ -216,7 +217,7 @@ knn_kernel(const float* __restrict__ db, int64_t n, const float* __restrict__ q,
     if (qe < nq) {
       const int id = listi[e];
       const bool filled = id != 0x7fffffff;
-      if (qlist) {
+      if (LIST) {
         part_d[((int64_t)ypart * nq + qe) * k + c] = filled ? listd[e] : __int_as_float(0x7f800000);
         part_i[((int64_t)ypart * nq + qe) * k + c] = id;   // 0x7fffffff = empty
       } else {
@@ -276,9 +277,9 @@ int64_t knn_search_list_part_elems(int64_t nq_max, int k) { return ceil_div(nq_m
 int knn_search_list(const float* db, int64_t n, const float* q, int64_t nq_max, int d, int k, float* dist2, int64_t* idx,
                     const int* qlist, const unsigned int* qcount, float* part_d, int* part_i, cudaStream_t st) {
   const size_t smem = sizeof(KnnSmem) + (size_t)kKnnQ * k * 8;
-  MGP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGP_CUDA(cudaFuncSetAttribute(knn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = ceil_div(nq_max, kKnnQ);
-  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, st>>>(db, n, q, nq_max, d, k, dist2, idx, qlist, qcount, part_d, part_i);
+  knn_kernel<true><<<(unsigned)grid, kKnnThreads, smem, st>>>(db, n, q, nq_max, d, k, dist2, idx, qlist, qcount, part_d, part_i);
   MGP_LAUNCH_CHECK();
   knn_merge_parts_kernel<<<(unsigned)ceil_div(nq_max, 4), 128, 0, st>>>(qlist, qcount, grid, k, part_d, part_i, dist2, idx);
   MGP_LAUNCH_CHECK();
@@ -303,10 +304,10 @@ int mgp_knn_search_f32(const float* db, int64_t n, const float* q, int64_t nq, i
   MGP_CHECK_ARG(k > 0 && k <= kKnnMaxK, "knn_search: k must be in [1, %d] (got %d)", kKnnMaxK, k);
   MGP_CHECK_ARG(n < ((int64_t)1 << 31), "knn_search: n must be < 2^31");
   const size_t smem = sizeof(KnnSmem) + (size_t)kKnnQ * k * 8;
-  MGP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MGP_CUDA(cudaFuncSetAttribute(knn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = ceil_div(nq, kKnnQ);
   MGP_CHECK_ARG(grid < ((int64_t)1 << 31), "knn_search: too many queries for one launch");
-  knn_kernel<<<(unsigned)grid, kKnnThreads, smem, (cudaStream_t)stream>>>(db, n, q, nq, d, k, dist2, idx, nullptr, nullptr, nullptr, nullptr);
+  knn_kernel<false><<<(unsigned)grid, kKnnThreads, smem, (cudaStream_t)stream>>>(db, n, q, nq, d, k, dist2, idx, nullptr, nullptr, nullptr, nullptr);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

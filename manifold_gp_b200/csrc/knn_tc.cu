@@ -400,30 +400,85 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
 __device__ __forceinline__ bool tc_lex_less(float d0, int i0, float d1, int i1) { return d0 < d1 || (d0 == d1 && i0 < i1); }
 
 // stats: [0] queries that failed the certificate, [1] bits of the largest |d~ - d| seen, [2] queries processed
+//
+// Stage A: the nsplit * kp candidates of the query are ranked by their APPROXIMATE distance and only the kp best go on
+//          (the rest count as discarded, with the kp-th approximate distance as their threshold) -- so the exact stage
+//          costs kp distance evaluations per query however many database splits the sweep used.
+// Stage B: exact distances of those kp, top-k by (distance, index), certificate.
 template <int T>
 __global__ void __launch_bounds__(128)
 knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, int64_t nq, int d, int k, int nsplit, int kp,
                      const int* __restrict__ cand_idx, const float* __restrict__ cand_dt, const float* __restrict__ tau_s,
                      const float* __restrict__ qn, float* __restrict__ out_d, int64_t* __restrict__ out_i,
                      int* __restrict__ flag_list, unsigned int* __restrict__ stats) {
-  const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  __shared__ int s_idx[4][64];
+  __shared__ float s_dt[4][64];
+  const int wib = threadIdx.x >> 5;
+  const int64_t qi = (int64_t)blockIdx.x * 4 + wib;
   const int lane = threadIdx.x & 31;
   if (qi >= nq) return;
   const int total = nsplit * kp;
   const float* qrow = q + qi * d;
   const float kInf = __int_as_float(0x7f800000);
-  float ed[T];
-  int ei[T];
-  float err = 0.f, bsum = 0.f;
-  float diff[T];
-  int nvalid = 0;
+
+  // ---- stage A: approximate top-kp of the union -------------------------------------------------------------------------
+  float ad[T];
+  int ai[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int e = lane + 32 * t;
-    diff[t] = 0.f;
     const int id = e < total ? cand_idx[(size_t)qi * total + e] : -1;
+    ad[t] = id >= 0 ? cand_dt[(size_t)qi * total + e] : kInf;
+    ai[t] = id >= 0 ? id : 0x7fffffff;
+  }
+  for (int e = lane; e < 64; e += 32) { s_idx[wib][e] = 0x7fffffff; s_dt[wib][e] = kInf; }
+  __syncwarp();
+  float tau_u = FLT_MAX;     // approximate distance every candidate dropped here exceeds
+  if (T == 1 || total <= kp) {
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if (lane + 32 * t < 64) { s_idx[wib][lane + 32 * t] = ai[t]; s_dt[wib][lane + 32 * t] = ad[t]; }
+  } else {
+    int arank[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) arank[t] = 0;
+#pragma unroll
+    for (int t2 = 0; t2 < T; ++t2) {
+      if (32 * t2 < total) {
+        for (int j = 0; j < 32; ++j) {
+          const float dj = __shfl_sync(0xffffffffu, ad[t2], j);
+          const int ij = __shfl_sync(0xffffffffu, ai[t2], j);
+#pragma unroll
+          for (int t = 0; t < T; ++t) arank[t] += tc_lex_less(dj, ij, ad[t], ai[t]) ? 1 : 0;
+        }
+      }
+    }
+    float tu = FLT_MAX;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (ai[t] != 0x7fffffff) {
+        if (arank[t] < kp) { s_idx[wib][arank[t]] = ai[t]; s_dt[wib][arank[t]] = ad[t]; }
+        if (arank[t] == kp) tu = ad[t];          // the best dropped candidate
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tu = fminf(tu, __shfl_xor_sync(0xffffffffu, tu, o));
+    tau_u = tu;
+  }
+  __syncwarp();
+
+  // ---- stage B: exact distances of the kept candidates (two per lane) --------------------------------------------------
+  float ed[2], diff[2];
+  int ei[2];
+  float err = 0.f, bsum = 0.f;
+  int nvalid = 0;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int e = lane + 32 * t;
+    const int id = e < kp ? s_idx[wib][e] : 0x7fffffff;
     float acc = kInf;
-    if (id >= 0) {
+    diff[t] = 0.f;
+    if (id != 0x7fffffff) {
       const float* xr = db + (int64_t)id * d;
       acc = 0.f;
       if ((d & 3) == 0) {
@@ -441,13 +496,13 @@ knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, 
           acc = __fadd_rn(acc, __fmul_rn(df, df));
         }
       }
-      diff[t] = cand_dt[(size_t)qi * total + e] - acc;
+      diff[t] = s_dt[wib][e] - acc;
       err = fmaxf(err, fabsf(diff[t]));
       bsum += diff[t];
       ++nvalid;
     }
     ed[t] = acc;
-    ei[t] = id >= 0 ? id : 0x7fffffff;
+    ei[t] = id;
   }
   nvalid = warp_sum(nvalid);
   bsum = warp_sum(bsum);
@@ -456,7 +511,7 @@ knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, 
   const float bias = nvalid > 0 ? bsum / (float)nvalid : 0.f;
   float res = 0.f;
 #pragma unroll
-  for (int t = 0; t < T; ++t)
+  for (int t = 0; t < 2; ++t)
     if (ei[t] != 0x7fffffff) res = fmaxf(res, fabsf(diff[t] - bias));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -464,23 +519,21 @@ knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, 
     res = fmaxf(res, __shfl_xor_sync(0xffffffffu, res, o));
   }
 
-  int rank[T];
+  int rank[2] = {0, 0};
 #pragma unroll
-  for (int t = 0; t < T; ++t) rank[t] = 0;
-#pragma unroll
-  for (int t2 = 0; t2 < T; ++t2) {
-    if (32 * t2 < total) {
+  for (int t2 = 0; t2 < 2; ++t2) {
+    if (32 * t2 < kp) {
       for (int j = 0; j < 32; ++j) {
         const float dj = __shfl_sync(0xffffffffu, ed[t2], j);
         const int ij = __shfl_sync(0xffffffffu, ei[t2], j);
 #pragma unroll
-        for (int t = 0; t < T; ++t) rank[t] += tc_lex_less(dj, ij, ed[t], ei[t]) ? 1 : 0;
+        for (int t = 0; t < 2; ++t) rank[t] += tc_lex_less(dj, ij, ed[t], ei[t]) ? 1 : 0;
       }
     }
   }
   float dk = kInf;   // exact k-th distance among the candidates
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
+  for (int t = 0; t < 2; ++t) {
     if (ei[t] != 0x7fffffff && rank[t] < k) {
       out_d[qi * k + rank[t]] = ed[t];
       out_i[qi * k + rank[t]] = (int64_t)ei[t];
@@ -492,7 +545,7 @@ knn_tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, 
   for (int o = 16; o > 0; o >>= 1) dk = fminf(dk, __shfl_xor_sync(0xffffffffu, dk, o));
 
   if (lane == 0) {
-    float tmin = FLT_MAX;
+    float tmin = tau_u;
     for (int s = 0; s < nsplit; ++s) tmin = fminf(tmin, tau_s[(size_t)qi * nsplit + s]);
     bool ok = true;
     if (tmin < FLT_MAX) {          // something was discarded: it must be provably farther than the k-th neighbour
@@ -578,10 +631,17 @@ static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->nqtiles = (int)ceil_div(nq, kTcBM);
   p->kp = ((k + 16 + 31) / 32) * 32;            // 32 or 64
   p->cap = p->kp + 64;
+  // Database splits: enough (query tile, split) work items for >= 6 waves over the SMs, no more.  Measured on B200
+  // (70k x 784, k = 10): 2 splits 52.6 ms, 4 splits 58.5, 8 splits 66.2 -- every item restarts the selection warm-up, and
+  // the database tiles are fetched from DRAM per CTA whatever the schedule (ncu: ~240 GB per search = one 1.6 MB tile per
+  // (query tile, database tile) pair; the query slabs are the L2 hits).  Sharing a database tile between CTAs needs a
+  // cluster + TMA multicast (next round), not a different split count.  The re-rank prunes the nsplit * K' candidates by
+  // approximate distance before the exact stage, so its cost does not grow with the split count.
   int smax = kTcMaxCand / p->kp;
   if (smax > kTcMaxSplit) smax = kTcMaxSplit;
-  int s = (int)ceil_div((int64_t)kNumSMs * 6, p->nqtiles);   // aim for >= 6 waves of work items
+  int s = (int)ceil_div((int64_t)kNumSMs * 6, p->nqtiles);
   if (s > smax) s = smax;
+  { const char* e = getenv("MGP_KNN_TC_SPLITS"); if (e && atoi(e) > 0) s = atoi(e) < smax ? atoi(e) : smax; }
   if (s > p->ntiles / 4) s = p->ntiles / 4;                   // at least 4 database tiles per split
   if (s < 1) s = 1;
   p->tiles_per_split = (int)ceil_div(p->ntiles, s);
