@@ -122,38 +122,52 @@ __global__ void __launch_bounds__(256) knn_tc_colsum_kernel(const float* __restr
   }
 }
 
-// one warp per row: centred point -> hi / lo TF32 terms (row stride dp, zero padded) and its squared norm
+constexpr float kTcBig = 1e30f;     // "never selected": padding rows of the database / the initial threshold (1e29)
+
+// one warp per row: centred point -> hi / lo TF32 terms (row stride dp, zero padded).  Column d carries the norm term so that
+// the contraction itself yields q.x - |x|^2 / 2 and the epilogue needs ONE compare per candidate:
+//   database role (role 0): column d = -|x|^2 / 2 (split hi + lo like a coordinate); rows n .. npad-1 (tile padding) get -1e30
+//   query role    (role 1): column d = 1;  norm[row] = |q|^2 (fp64 accumulation)
 __global__ void __launch_bounds__(256)
 knn_tc_prep_kernel(const float* __restrict__ x, int64_t n, int64_t npad, int d, int dp, const double* __restrict__ sums,
-                   double inv_count, float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norm) {
+                   double inv_count, int role, float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norm) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= npad) return;
   if (row >= n) {
-    if (lane == 0) norm[row] = __int_as_float(0x7f800000);   // padding columns of the last tile can never be selected
+    for (int c = lane; c < dp; c += 32) {
+      hi[row * dp + c] = (c == d && role == 0) ? -kTcBig : 0.f;
+      lo[row * dp + c] = 0.f;
+    }
+    if (lane == 0 && norm) norm[row] = 0.f;
     return;
   }
   double acc = 0.0;
-  for (int c = lane; c < dp; c += 32) {
+  for (int c = lane; c < d; c += 32) {
+    const float mu = (float)(sums[c] * inv_count);
+    const float v = __fsub_rn(x[row * d + c], mu);
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[row * dp + c] = h;
+    lo[row * dp + c] = __fsub_rn(v, h);
+    acc += (double)v * (double)v;
+  }
+  acc = warp_sum(acc);
+  for (int c = d + lane; c < dp; c += 32) {
     float h = 0.f, l = 0.f;
-    if (c < d) {
-      const float mu = (float)(sums[c] * inv_count);
-      const float v = __fsub_rn(x[row * d + c], mu);
+    if (c == d) {
+      const float v = role == 0 ? (float)(-0.5 * acc) : 1.f;
       h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       l = __fsub_rn(v, h);
-      acc += (double)v * (double)v;
     }
     hi[row * dp + c] = h;
     lo[row * dp + c] = l;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) norm[row] = (float)acc;
+  if (lane == 0 && norm) norm[row] = (float)acc;
 }
 
 // ---- 2. tensor-core sweep --------------------------------------------------------------------------------------------------
 struct TcArgs {
   const float* qn;          // [nq]
-  const float* xn;          // [ntiles * 128], +inf beyond n
   int64_t nq, n;
   int nkb;                  // k-blocks of 32 dims
   int ntiles, nqtiles, nsplit, tiles_per_split;
@@ -203,18 +217,72 @@ __device__ __forceinline__ float tc_compact_row(unsigned long long* rb, int n, i
   return tau;
 }
 
-// Compact the candidate lists of the rows flagged in `need` (one bit per lane = row of this warp).  Deliberately NOT
-// inlined: the selection loop around it must stay small enough for the instruction cache.  Returns the lane's own new
-// (tau, cnt) packed as {float bits, int}.
+// Cheap in-sweep pruning of one row's list (n <= 128 keys): bisection on the ordered distance for a pivot that keeps
+// between kp and kp + 8 keys (a superset of the kp best -- all the selection needs while the sweep is running; every dropped
+// key is > pivot).  ~10 rounds of (4 compares + one warp reduction) instead of the ~2000 instructions of the exact ranking;
+// falls back to the exact ranking when ties make the window unreachable.  Returns the new threshold, *ncnt the new length.
+__device__ __forceinline__ float tc_prune_row(unsigned long long* rb, int n, int kp, int lane, int* ncnt) {
+  unsigned long long key[4];
+  uint32_t o[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const bool v = lane + 32 * t < n;
+    key[t] = v ? __ldcg(rb + lane + 32 * t) : ~0ull;
+    o[t] = v ? (uint32_t)(key[t] >> 32) : 0xffffffffu;
+  }
+  uint32_t mn = min(min(o[0], o[1]), min(o[2], o[3]));
+  uint32_t mx = 0u;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) if (o[t] != 0xffffffffu) mx = max(mx, o[t]);
+  uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+  int chi = n;
+  for (int it = 0; it < 34 && lo < hi; ++it) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) c += o[t] <= mid ? 1 : 0;
+    c = (int)__reduce_add_sync(0xffffffffu, (unsigned)c);
+    if (c >= kp) {
+      hi = mid; chi = c;
+      if (c <= kp + 8) break;
+    } else {
+      lo = mid + 1;
+    }
+  }
+  if (chi > kp + 8) {                     // ties at the pivot: exact ranking decides
+    __syncwarp();
+    *ncnt = min(n, kp);
+    return tc_compact_row(rb, n, kp, lane);
+  }
+  __syncwarp();
+  int base = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const bool keep = o[t] <= hi;         // invalid slots are 0xffffffff > hi
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) __stcg(rb + base + __popc(m & ((1u << lane) - 1u)), key[t]);
+    base += __popc(m);
+  }
+  __syncwarp();
+  *ncnt = base;
+  return ord2f(hi);
+}
+
+// Prune / compact the candidate lists of the rows flagged in `need` (one bit per lane = row of this warp).  Deliberately
+// NOT inlined: the selection loop around it must stay small enough for the instruction cache.  exact != 0: keep exactly
+// the kp best, sorted (end of a work item); else the cheap superset pruning.  Returns the lane's own new (tau, cnt).
 __device__ __noinline__ uint2 tc_compact_rows(unsigned long long* wlists, unsigned need, int cap, int kp, int lane, float tau,
-                                              int cnt) {
+                                              int cnt, int exact) {
   __syncwarp();
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1;
     const int nsrc = __shfl_sync(0xffffffffu, cnt, src);
-    const float tnew = tc_compact_row(wlists + (size_t)src * cap, nsrc, kp, lane);
-    if (lane == src) { tau = tnew; cnt = min(nsrc, kp); }
+    int nnew = min(nsrc, kp);
+    float tnew;
+    if (exact) tnew = tc_compact_row(wlists + (size_t)src * cap, nsrc, kp, lane);
+    else tnew = tc_prune_row(wlists + (size_t)src * cap, nsrc, kp, lane, &nnew);
+    if (lane == src) { tau = tnew; cnt = nnew; }
   }
   return make_uint2(__float_as_uint(tau), (unsigned)cnt);
 }
@@ -323,7 +391,7 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
       const int t0 = sp * g.tiles_per_split, t1 = min(g.ntiles, t0 + g.tiles_per_split);
       const int64_t qrow = (int64_t)qt * kTcBM + row;
       const float qn = qrow < g.nq ? __ldg(g.qn + qrow) : 0.f;
-      float tau = qrow < g.nq ? FLT_MAX : -FLT_MAX;   // rows beyond the last query never collect candidates
+      float tau = qrow < g.nq ? 0.1f * kTcBig : -kTcBig;   // rows beyond the last query never collect candidates
       int cnt = 0;
       for (int t = t0; t < t1; ++t, ++jt) {
         const uint32_t buf = jt & 1u;
@@ -341,21 +409,31 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
           }
           if (g.debug & 2) continue;
           const int col0 = t * kTcBN + ch * 32;
-          const float xv = __ldg(g.xn + col0 + lane);
-          // the list has room for a whole chunk here (cnt <= kp + 32 = cap - 32): no overflow check per candidate
+          // acc = q.x - |x|^2 / 2 (the norm rides in the contraction): d~ <= tau  <=>  acc >= (|q|^2 - tau) / 2.
+          // The list has room for a whole chunk here (cnt <= kp + 32 = cap - 32): no overflow check per candidate.
+          const float thr = 0.5f * (qn - tau);
+          // 8 columns at a time: one max chain + one warp vote; the per-candidate tests run only where some lane passes
+          // (steady state: ~6e-4 of the candidates pass, ~14 % of the 8 x 32 groups)
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float xc = __shfl_sync(0xffffffffu, xv, c);
-            const float dt = fmaf(-2.f, __uint_as_float(acc[c]), qn + xc);
-            if (dt <= tau) {
-              __stcg(mylist + cnt, ((unsigned long long)f2ord(dt) << 32) | (unsigned)(col0 + c));
-              ++cnt;
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float m8 = __uint_as_float(acc[8 * g8]);
+#pragma unroll
+            for (int c = 1; c < 8; ++c) m8 = fmaxf(m8, __uint_as_float(acc[8 * g8 + c]));
+            if (__any_sync(0xffffffffu, m8 >= thr)) {
+#pragma unroll
+              for (int c = 8 * g8; c < 8 * g8 + 8; ++c) {
+                const float av = __uint_as_float(acc[c]);
+                if (av >= thr) {
+                  __stcg(mylist + cnt, ((unsigned long long)f2ord(fmaf(-2.f, av, qn)) << 32) | (unsigned)(col0 + c));
+                  ++cnt;
+                }
+              }
             }
           }
           const unsigned need = __ballot_sync(0xffffffffu, cnt > g.kp + 32);
           if (need) {
-            const uint2 r = tc_compact_rows(wlists, need, g.cap, g.kp, lane, tau, cnt);
-            tau = __uint_as_float(r.x);
+            const uint2 r = tc_compact_rows(wlists, need, g.cap, g.kp, lane, tau, cnt, 0);
+            tau = fminf(__uint_as_float(r.x), 0.1f * kTcBig);
             cnt = (int)r.y;
           }
         }
@@ -364,7 +442,7 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
       {
         const unsigned need = __ballot_sync(0xffffffffu, cnt > g.kp);
         if (need) {
-          const uint2 r = tc_compact_rows(wlists, need, g.cap, g.kp, lane, tau, cnt);
+          const uint2 r = tc_compact_rows(wlists, need, g.cap, g.kp, lane, tau, cnt, 1);
           tau = __uint_as_float(r.x);
           cnt = (int)r.y;
         }
@@ -383,7 +461,7 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
           g.cand_dt[ob + j] = v ? ord2f((uint32_t)(key >> 32)) : 0.f;
         }
       }
-      if (qrow < g.nq) g.tau[(size_t)qrow * g.nsplit + sp] = tau;
+      if (qrow < g.nq) g.tau[(size_t)qrow * g.nsplit + sp] = tau >= 0.1f * kTcBig ? FLT_MAX : tau;   // FLT_MAX: nothing discarded
       __syncwarp();
     }
   }
@@ -600,7 +678,7 @@ struct TcPlan {
   int64_t npad, nqpad;
   bool same;
   // workspace offsets (bytes)
-  size_t o_sums, o_xhi, o_xlo, o_xn, o_qhi, o_qlo, o_qn, o_lists, o_cidx, o_cdt, o_tau, o_flag, o_pd, o_pi, total;
+  size_t o_sums, o_xhi, o_xlo, o_qhi, o_qlo, o_qn, o_lists, o_cidx, o_cdt, o_tau, o_flag, o_pd, o_pi, total;
 };
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -620,13 +698,14 @@ static int tc_variant() {
 
 static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->variant = tc_variant();
+  if (!getenv("MGP_KNN_TC_VARIANT") && d + 1 <= 16) p->variant = 2;      // small d: 16-wide k-blocks (64-byte rows)
   p->bn = (p->variant == 1 || p->variant == 2) ? 256 : 128;
   p->bk = (p->variant >= 2) ? 16 : 32;
   const int kTcBN = p->bn, kTcBK = p->bk;
-  if (d < 16 || k < 1 || k > 48 || n < 256 || n >= ((int64_t)1 << 31) - 256 || nq < 1 || nq >= ((int64_t)1 << 31) - 256) return false;
+  if (d < 1 || k < 1 || k > 48 || n < 256 || n >= ((int64_t)1 << 31) - 256 || nq < 1 || nq >= ((int64_t)1 << 31) - 256) return false;
   p->same = same;
-  p->dp = (d + 3) & ~3;
-  p->nkb = (int)ceil_div(d, kTcBK);
+  p->dp = (d + 1 + 3) & ~3;                     // + the norm column
+  p->nkb = (int)ceil_div(d + 1, kTcBK);
   p->ntiles = (int)ceil_div(n, kTcBN);
   p->nqtiles = (int)ceil_div(nq, kTcBM);
   p->kp = ((k + 16 + 31) / 32) * 32;            // 32 or 64
@@ -652,16 +731,12 @@ static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->nqpad = (int64_t)p->nqtiles * kTcBM;
   size_t o = 0;
   p->o_sums = o; o = align256(o + (size_t)d * 8);
-  p->o_xhi = o; o = align256(o + (size_t)n * p->dp * 4);
-  p->o_xlo = o; o = align256(o + (size_t)n * p->dp * 4);
-  p->o_xn = o; o = align256(o + (size_t)p->npad * 4);
-  if (!same) {
-    p->o_qhi = o; o = align256(o + (size_t)nq * p->dp * 4);
-    p->o_qlo = o; o = align256(o + (size_t)nq * p->dp * 4);
-    p->o_qn = o; o = align256(o + (size_t)p->nqpad * 4);
-  } else {
-    p->o_qhi = p->o_xhi; p->o_qlo = p->o_xlo; p->o_qn = p->o_xn;
-  }
+  p->o_xhi = o; o = align256(o + (size_t)p->npad * p->dp * 4);
+  p->o_xlo = o; o = align256(o + (size_t)p->npad * p->dp * 4);
+  // the query-role copy differs from the database-role copy in the norm column, so it is always materialised
+  p->o_qhi = o; o = align256(o + (size_t)p->nqpad * p->dp * 4);
+  p->o_qlo = o; o = align256(o + (size_t)p->nqpad * p->dp * 4);
+  p->o_qn = o; o = align256(o + (size_t)p->nqpad * 4);
   p->o_lists = o; o = align256(o + (size_t)p->grid * kTcBM * p->cap * 8);
   p->o_cidx = o; o = align256(o + (size_t)nq * p->nsplit * p->kp * 4);
   p->o_cdt = o; o = align256(o + (size_t)nq * p->nsplit * p->kp * 4);
@@ -716,7 +791,6 @@ int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq
   double* sums = reinterpret_cast<double*>(w + p.o_sums);
   float* xhi = reinterpret_cast<float*>(w + p.o_xhi);
   float* xlo = reinterpret_cast<float*>(w + p.o_xlo);
-  float* xn = reinterpret_cast<float*>(w + p.o_xn);
   float* qhi = reinterpret_cast<float*>(w + p.o_qhi);
   float* qlo = reinterpret_cast<float*>(w + p.o_qlo);
   float* qn = reinterpret_cast<float*>(w + p.o_qn);
@@ -725,22 +799,20 @@ int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq
   MGP_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(uint32_t), st));
   knn_tc_colsum_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(db, n, d, sums);
   MGP_LAUNCH_CHECK();
-  knn_tc_prep_kernel<<<(unsigned)ceil_div(p.npad, 8), 256, 0, st>>>(db, n, p.npad, d, p.dp, sums, 1.0 / (double)n, xhi, xlo, xn);
+  knn_tc_prep_kernel<<<(unsigned)ceil_div(p.npad, 8), 256, 0, st>>>(db, n, p.npad, d, p.dp, sums, 1.0 / (double)n, 0, xhi, xlo, nullptr);
   MGP_LAUNCH_CHECK();
-  if (!same) {
-    knn_tc_prep_kernel<<<(unsigned)ceil_div(p.nqpad, 8), 256, 0, st>>>(q, nq, p.nqpad, d, p.dp, sums, 1.0 / (double)n, qhi, qlo, qn);
-    MGP_LAUNCH_CHECK();
-  }
+  knn_tc_prep_kernel<<<(unsigned)ceil_div(p.nqpad, 8), 256, 0, st>>>(q, nq, p.nqpad, d, p.dp, sums, 1.0 / (double)n, 1, qhi, qlo, qn);
+  MGP_LAUNCH_CHECK();
 
   CUtensorMap tm_qhi, tm_qlo, tm_xhi, tm_xlo;
   int rc;
-  if ((rc = make_tile_map(&tm_qhi, qhi, nq, p.dp, kTcBM, p.bk)) != MGP_OK) return rc;
-  if ((rc = make_tile_map(&tm_qlo, qlo, nq, p.dp, kTcBM, p.bk)) != MGP_OK) return rc;
-  if ((rc = make_tile_map(&tm_xhi, xhi, n, p.dp, p.bn, p.bk)) != MGP_OK) return rc;
-  if ((rc = make_tile_map(&tm_xlo, xlo, n, p.dp, p.bn, p.bk)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_qhi, qhi, p.nqpad, p.dp, kTcBM, p.bk)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_qlo, qlo, p.nqpad, p.dp, kTcBM, p.bk)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_xhi, xhi, p.npad, p.dp, p.bn, p.bk)) != MGP_OK) return rc;
+  if ((rc = make_tile_map(&tm_xlo, xlo, p.npad, p.dp, p.bn, p.bk)) != MGP_OK) return rc;
 
   TcArgs g;
-  g.qn = qn; g.xn = xn; g.nq = nq; g.n = n; g.nkb = p.nkb; g.ntiles = p.ntiles; g.nqtiles = p.nqtiles; g.nsplit = p.nsplit;
+  g.qn = qn; g.nq = nq; g.n = n; g.nkb = p.nkb; g.ntiles = p.ntiles; g.nqtiles = p.nqtiles; g.nsplit = p.nsplit;
   g.tiles_per_split = p.tiles_per_split; g.kp = p.kp; g.cap = p.cap;
   { const char* e = getenv("MGP_KNN_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
   g.lists = reinterpret_cast<unsigned long long*>(w + p.o_lists);

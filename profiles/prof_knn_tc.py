@@ -16,10 +16,8 @@ n = int(args[0]) if len(args) > 0 else 70000
 d = int(args[1]) if len(args) > 1 else 784
 k = int(args[2]) if len(args) > 2 else 10
 dev = torch.device("cuda:0")
-x = synthetic.rmnist_shape(n, d, device=dev) if hasattr(synthetic, "rmnist_shape") else None
-if x is None:
-    import oracle
-    x = oracle.datasets.rmnist_shape(n, d).to(dev)
+x = synthetic.torus(n, device=dev) if "--torus" in sys.argv else synthetic.rmnist_shape(n, d, device=dev)
+d = x.shape[1]
 knn = mgp.NearestNeighbors(x)
 
 
