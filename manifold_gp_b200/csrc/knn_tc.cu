@@ -34,7 +34,8 @@ int knn_search_list(const float* db, int64_t n, const float* q, int64_t nq_max, 
                     const int* qlist, const unsigned int* qcount, float* part_d, int* part_i, cudaStream_t st);
 
 constexpr int kTcBM = 128;       // query rows per tile  (UMMA M)
-constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-5 epilogue
+constexpr int kTcEpiWarps = 8;    // two per TMEM lane quadrant: each takes every other 32-column chunk of a tile, with its own lists
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2-9 epilogue
 constexpr int kTcMaxSplit = 8;
 constexpr int kTcMaxCand = 256;  // nsplit * K' handled by the re-rank
 
@@ -173,10 +174,10 @@ struct TcArgs {
   int ntiles, nqtiles, nsplit, tiles_per_split;
   int kp, cap;              // K', candidate-list capacity per row (kp + 64: compaction when a row holds more than kp + 32)
   int debug;                // timing experiments only (MGP_KNN_TC_DEBUG): 1 = hi.hi products only, 2 = epilogue skips the selection
-  unsigned long long* lists;  // [gridDim.x][128][cap]
-  int* cand_idx;            // [nq][nsplit][kp]   (-1 = empty)
+  unsigned long long* lists;  // [gridDim.x][2 epilogue warps per quadrant][128][cap]
+  int* cand_idx;            // [nq][2 * nsplit][kp]   (-1 = empty)
   float* cand_dt;           // [nq][nsplit][kp]   approximate distances
-  float* tau;               // [nq][nsplit]       every discarded point of the split had d~ >= tau (FLT_MAX: nothing discarded)
+  float* tau;               // [nq][2 * nsplit]       every discarded point of the split had d~ >= tau (FLT_MAX: nothing discarded)
 };
 
 // Keep the kp smallest of the n keys of one row (sorted ascending, in place).  Returns the kp-th key's distance, or
@@ -306,7 +307,7 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -382,8 +383,9 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
   } else {
     // ===== epilogue: one query row per thread, fused selection =====
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                // which of the quadrant's two warps: chunks half, half + 2, ...
     const int row = quad * 32 + lane;
-    unsigned long long* const wlists = g.lists + ((size_t)blockIdx.x * kTcBM + quad * 32) * g.cap;
+    unsigned long long* const wlists = g.lists + (((size_t)blockIdx.x * 2 + half) * kTcBM + quad * 32) * g.cap;
     unsigned long long* const mylist = wlists + (size_t)lane * g.cap;
     uint32_t jt = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -399,10 +401,10 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
         tc_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kTcBN;
 #pragma unroll 1
-        for (int ch = 0; ch < kTcBN / 32; ++ch) {
+        for (int ch = half; ch < kTcBN / 32; ch += 2) {
           uint32_t acc[32];
           tc_ld32(tacc + ch * 32, acc);
-          if (ch == kTcBN / 32 - 1) {                // accumulator fully read: hand the buffer back to the MMA warp
+          if (ch >= kTcBN / 32 - 2) {                // accumulator fully read: hand the buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
@@ -453,7 +455,7 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
         if (qr >= g.nq) break;
         const int nr = __shfl_sync(0xffffffffu, cnt, rr);
         const unsigned long long* rb = wlists + (size_t)rr * g.cap;
-        const size_t ob = ((size_t)qr * g.nsplit + sp) * g.kp;
+        const size_t ob = ((size_t)qr * (2 * g.nsplit) + 2 * sp + half) * g.kp;
         for (int j = lane; j < g.kp; j += 32) {
           const bool v = j < nr;
           const unsigned long long key = v ? __ldcg(rb + j) : 0ull;
@@ -461,7 +463,7 @@ knn_tc_sweep_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
           g.cand_dt[ob + j] = v ? ord2f((uint32_t)(key >> 32)) : 0.f;
         }
       }
-      if (qrow < g.nq) g.tau[(size_t)qrow * g.nsplit + sp] = tau >= 0.1f * kTcBig ? FLT_MAX : tau;   // FLT_MAX: nothing discarded
+      if (qrow < g.nq) g.tau[(size_t)qrow * (2 * g.nsplit) + 2 * sp + half] = tau >= 0.1f * kTcBig ? FLT_MAX : tau;   // FLT_MAX: nothing discarded
       __syncwarp();
     }
   }
@@ -716,7 +718,7 @@ static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   // (query tile, database tile) pair; the query slabs are the L2 hits).  Sharing a database tile between CTAs needs a
   // cluster + TMA multicast (next round), not a different split count.  The re-rank prunes the nsplit * K' candidates by
   // approximate distance before the exact stage, so its cost does not grow with the split count.
-  int smax = kTcMaxCand / p->kp;
+  int smax = kTcMaxCand / (2 * p->kp);           // every split yields two candidate sets (one per epilogue warp of a quadrant)
   if (smax > kTcMaxSplit) smax = kTcMaxSplit;
   int s = (int)ceil_div((int64_t)kNumSMs * 6, p->nqtiles);
   if (s > smax) s = smax;
@@ -737,10 +739,10 @@ static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->o_qhi = o; o = align256(o + (size_t)p->nqpad * p->dp * 4);
   p->o_qlo = o; o = align256(o + (size_t)p->nqpad * p->dp * 4);
   p->o_qn = o; o = align256(o + (size_t)p->nqpad * 4);
-  p->o_lists = o; o = align256(o + (size_t)p->grid * kTcBM * p->cap * 8);
-  p->o_cidx = o; o = align256(o + (size_t)nq * p->nsplit * p->kp * 4);
-  p->o_cdt = o; o = align256(o + (size_t)nq * p->nsplit * p->kp * 4);
-  p->o_tau = o; o = align256(o + (size_t)nq * p->nsplit * 4);
+  p->o_lists = o; o = align256(o + (size_t)p->grid * 2 * kTcBM * p->cap * 8);
+  p->o_cidx = o; o = align256(o + (size_t)nq * 2 * p->nsplit * p->kp * 4);
+  p->o_cdt = o; o = align256(o + (size_t)nq * 2 * p->nsplit * p->kp * 4);
+  p->o_tau = o; o = align256(o + (size_t)nq * 2 * p->nsplit * 4);
   p->o_flag = o; o = align256(o + (size_t)nq * 4);
   p->o_pd = o; o = align256(o + (size_t)knn_search_list_part_elems(nq, k) * 4);
   p->o_pi = o; o = align256(o + (size_t)knn_search_list_part_elems(nq, k) * 4);
@@ -761,7 +763,7 @@ template <int T>
 static void launch_rerank(const TcPlan& p, const float* db, const float* q, int64_t nq, int d, int k, unsigned char* w, float* dist2,
                           int64_t* idx, unsigned int* stats, cudaStream_t st) {
   knn_tc_rerank_kernel<T><<<(unsigned)ceil_div(nq, 4), 128, 0, st>>>(
-      db, q, nq, d, k, p.nsplit, p.kp, reinterpret_cast<const int*>(w + p.o_cidx), reinterpret_cast<const float*>(w + p.o_cdt),
+      db, q, nq, d, k, 2 * p.nsplit, p.kp, reinterpret_cast<const int*>(w + p.o_cidx), reinterpret_cast<const float*>(w + p.o_cdt),
       reinterpret_cast<const float*>(w + p.o_tau), reinterpret_cast<const float*>(w + p.o_qn), dist2, idx,
       reinterpret_cast<int*>(w + p.o_flag), stats);
 }
@@ -827,7 +829,7 @@ int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq
   }
   if (rc != MGP_OK) return rc;
 
-  const int total = p.nsplit * p.kp;
+  const int total = 2 * p.nsplit * p.kp;
   if (total <= 32) launch_rerank<1>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
   else if (total <= 64) launch_rerank<2>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
   else if (total <= 128) launch_rerank<4>(p, db, q, nq, d, k, w, dist2, idx, stats, st);
