@@ -46,53 +46,82 @@ def spmm_algorithmic_bytes(n, nnz, c, w=4):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  Sampled in-process through NVML (pynvml)
+    every 100 ms: polling with an `nvidia-smi -lms` child process was measured to perturb the host-in-the-loop CG solve on
+    some boxes (same code 615 ms without it, 700-1150 ms with it); NVML queries from a thread do not.  Falls back to one
+    nvidia-smi snapshot at the end of the region if pynvml is unavailable."""
 
     def __init__(self, index=0):
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (sm_mhz, sm_max_mhz, set(reasons))
         self.index = index
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self.period = float(os.environ.get("MGP_BENCH_CLOCK_PERIOD", "0.1"))
 
-    def __enter__(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-        return self
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([s.strip() for s in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
+    def _loop(self):
+        nv, h = self._nvml, self._handle
+        names = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        while not self._stop.is_set():
             try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-
-    def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), {n for n, bit in names if mask & bit}))
             except Exception:
                 pass
-        if not sm:
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.period <= 0:
+            return self
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self._handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = nv
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._nvml = None
+        return self
+
+    def __exit__(self, *a):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        elif not self.rows:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                self.rows.append((float(out[0]), float(out[1]),
+                                  {n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")}))
+            except Exception:
+                pass
+
+    def summary(self):
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            reasons |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in self.rows), "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def dist_info():
@@ -170,11 +199,15 @@ def run_ours(args):
     _lib.reset_launch_count()
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         ev0.record()
-        for _ in range(args.steps):
+        marks[0].record()
+        for i in range(args.steps):
             sol, info = solve_dev()
+            marks[i + 1].record()
         ev1.record()
         torch.cuda.synchronize()
+    per_solve_ms = [round(marks[i].elapsed_time(marks[i + 1]), 1) for i in range(args.steps)]
     launches = _lib.launch_count()
     ms_step = ev0.elapsed_time(ev1) / args.steps
     iters = info["iterations"]
@@ -230,7 +263,7 @@ def run_ours(args):
 
     out = {
         "metric": "precision_cg_solve_time", "value": round(ms_step, 3), "unit": "ms", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": False, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "per_step_ms": per_solve_ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": CFG["workload"], "n": n, "k": k, "edges_M": m, "nnz": nnz, "nu": CFG["nu"], "kappa": CFG["kappa"],
                    "eps": round(eps, 6), "rhs": c, "tol": CFG["tol"], "normalization": CFG["normalization"],

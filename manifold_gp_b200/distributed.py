@@ -251,13 +251,14 @@ class DistCG:
             self._iteration()                       # eager once: kernel attributes set, NCCL warmed up
             k = 1
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
-            with torch.cuda.graph(self.graph):
-                for _ in range(self.check):
-                    self._iteration()
+            self.graph = solvers._capture(self._iteration, self.check)
             self.launches_per_replay = _lib.launch_count() - before      # kernels of ours inside one replay
             _lib._dll.mgp_add_launch_count(-self.launches_per_replay)    # the capture pass itself launched nothing
+        # the done flag of chunk j is read while chunk j + 1 is already enqueued (see solvers.linear_cg)
+        flags = torch.zeros(solvers._FLAG_DEPTH, dtype=self.dt).pin_memory()
+        events = [torch.cuda.Event() for _ in range(solvers._FLAG_DEPTH)]
+        pending, slot = [], 0
         while k < self.max_iter and done == 0.0:
             steps = min(self.check, self.max_iter - k)
             if self.graph is not None and steps == self.check:
@@ -267,7 +268,19 @@ class DistCG:
                 for _ in range(steps):
                     self._iteration()
             k += steps
-            done = float(self.state[scal + solvers.K_DONE].item())
+            flags[slot:slot + 1].copy_(self.state[scal + solvers.K_DONE:scal + solvers.K_DONE + 1], non_blocking=True)
+            events[slot].record()
+            pending.append(slot)
+            slot = (slot + 1) % solvers._FLAG_DEPTH
+            if len(pending) == solvers._FLAG_DEPTH or self.graph is None:
+                s0 = pending.pop(0)
+                events[s0].synchronize()
+                done = float(flags[s0])
+        for s0 in pending:
+            if done != 0.0:
+                break
+            events[s0].synchronize()
+            done = float(flags[s0])
         out = torch.empty((n_loc, c), dtype=self.dt, device=self.dev)
         _lib.call("mgp_cg_finalize_" + sfx, ptr(self.x), c_int64(ld), ptr(out), c_int64(c), c_int64(n_loc), c_int32(c),
                   ptr(self.state), stream())

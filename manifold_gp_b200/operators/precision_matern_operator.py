@@ -37,6 +37,19 @@ class PrecisionMaternOperator(LinearOperator):
             self._mgp_shift = hit
         return hit[1]
 
+    def _mgp_cache_key(self, dtype):
+        """Identity of everything ``_mgp_matvec`` reads (memory + version): the CG driver keeps its captured CUDA graph
+        while this is unchanged."""
+        lap = self.laplacian
+        _, _, diag, a = lap._values()
+        shift = self._shift_const(a.dtype)
+        key = [lap.structure is not None and id(lap.structure), a.data_ptr(), a._version, diag.data_ptr(), diag._version,
+               shift.data_ptr(), shift._version, self.nu, lap.normalization]
+        if lap.normalization == "randomwalk":
+            sq = lap._sqrt_degree
+            key += [sq.data_ptr(), sq._version]
+        return tuple(key)
+
     def _native(self) -> bool:
         return isinstance(self.laplacian, GraphLaplacianOperator)
 

@@ -11,6 +11,9 @@ from __future__ import annotations
 
 import warnings
 
+import os
+import time
+
 import torch
 
 from . import _lib, settings
@@ -18,6 +21,10 @@ from ._compat.linear_operator import DenseEigenvectors
 from ._lib import c_double, c_float, c_int32, c_int64, ptr, stream
 
 # state layout (must match csrc/cg.cu)
+# chunks of CG iterations kept enqueued ahead of the host's convergence check: the GPU rides out host hiccups of up to
+# (_FLAG_DEPTH - 1) x check_interval iterations (~12 ms at cfg-C); at most that many iterations run past convergence (the
+# vector kernels are no-ops then, the SpMMs are not: ~4 ms per chunk at cfg-C)
+_FLAG_DEPTH = 3
 S_RHSNORM, S_RZ, S_PAP, S_ALPHA, S_BETA, S_RESID, S_RHSZERO, S_CONV, S_NARR = range(9)
 K_MEAN, K_DONE, K_ITER = 0, 1, 2
 MAX_CG_COLS = 128
@@ -41,15 +48,40 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
     ld = _pad_ld(c, dt) if fused else c
     fl = c_float if dt == torch.float32 else c_double
 
-    x = torch.empty((n, ld), dtype=dt, device=dev)
-    r = torch.empty((n, ld), dtype=dt, device=dev)
-    p = torch.empty((n, ld), dtype=dt, device=dev)
-    v = torch.zeros((n, ld), dtype=dt, device=dev)
-    tmp = torch.zeros((n, ld), dtype=dt, device=dev) if fused else None
-    state = torch.zeros(_lib.query("mgp_cg_state_elems", c_int32(c)), dtype=dt, device=dev)
-    ws = torch.zeros(_lib.query("mgp_cg_ws_bytes", c_int64(n), c_int32(c)), dtype=torch.uint8, device=dev)
     max_hist = max(1, min(max_iter, n_tridiag_iter)) if n_tridiag else 1
-    hist = torch.zeros((max_hist, 2, c), dtype=dt, device=dev) if n_tridiag else None
+    check = max(1, int(settings.cg_check_interval.value()))
+    # Work buffers and the captured graph of `check` iterations are kept on the operator between solves, valid as long as
+    # every array the matvec reads is the same memory holding the same version (op._mgp_cache_key): a repeated solve with
+    # a new right-hand side (posterior evaluation, bench) replays the graph from the first chunk on.  Capturing costs
+    # 5 - 800 ms per solve on B200 boxes (measured), far more than it saves on a 0.6 s solve if it is redone every time.
+    ckey = op._mgp_cache_key(dt) if (fused and hasattr(op, "_mgp_cache_key")) else None
+    bkey = (n, c, dt, bool(n_tridiag), max_hist, check)
+    entry = None
+    if ckey is not None:
+        cache = getattr(op, "_mgp_cg_cache", None)
+        if cache is None or cache["key"] != ckey:
+            cache = {"key": ckey, "entries": {}}
+            op._mgp_cg_cache = cache
+        entry = cache["entries"].get(bkey)
+    if entry is not None:
+        x, r, p, v, tmp, state, ws, hist = entry["buffers"]
+        state.zero_()
+        if hist is not None:
+            hist.zero_()
+    else:
+        x = torch.empty((n, ld), dtype=dt, device=dev)
+        r = torch.empty((n, ld), dtype=dt, device=dev)
+        p = torch.empty((n, ld), dtype=dt, device=dev)
+        v = torch.zeros((n, ld), dtype=dt, device=dev)
+        tmp = torch.zeros((n, ld), dtype=dt, device=dev) if fused else None
+        state = torch.zeros(_lib.query("mgp_cg_state_elems", c_int32(c)), dtype=dt, device=dev)
+        ws = torch.zeros(_lib.query("mgp_cg_ws_bytes", c_int64(n), c_int32(c)), dtype=torch.uint8, device=dev)
+        hist = torch.zeros((max_hist, 2, c), dtype=dt, device=dev) if n_tridiag else None
+        if ckey is not None:
+            entry = {"buffers": (x, r, p, v, tmp, state, ws, hist), "graph": None, "launches": 0}
+            if len(cache["entries"]) >= 2:          # bound the memory kept alive per operator
+                cache["entries"].pop(next(iter(cache["entries"])))
+            cache["entries"][bkey] = entry
     st = op._mgp_structure() if fused else None     # fused path runs in the structure's (permuted) row order
     rhs_c = st.to_internal(rhs) if st is not None else rhs
     rhs_c = rhs_c if rhs_c.stride(1) == 1 else rhs_c.contiguous()
@@ -58,7 +90,6 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
               c_int32(c), fl(tolerance), fl(eps), fl(stop_updating_after), c_int32(max_iter),
               c_int32(n_tridiag_iter if n_tridiag else 0), ptr(state), ptr(ws), stream())
     pap = state[S_PAP * c:(S_PAP + 1) * c]
-    check = max(1, int(settings.cg_check_interval.value()))
     hist_p, hist_n = ptr(hist), c_int32(max_hist if n_tridiag else 0)
 
     def iteration():
@@ -82,9 +113,19 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
     # convergence is harmless.  The first chunk runs eagerly (attributes set, value layouts cached, short solves unaffected).
     use_graph = fused and settings.cg_cuda_graph.on() and max_iter >= 4 * check
     cuda_graph, launches_per_replay = None, 0
+    if entry is not None and entry["graph"] is not None and use_graph:
+        cuda_graph, launches_per_replay = entry["graph"], entry["launches"]
     k = 0
     done = 0.0
     scal = S_NARR * c
+    _dbg = os.environ.get("MGP_CG_TIMING") is not None
+    _t = {"start": time.perf_counter(), "capture": 0.0, "max_wait": 0.0, "waits": 0} if _dbg else None
+    # The done flag of chunk j is read while chunk j + 1 is already enqueued (pinned-memory copy + event): the GPU never
+    # waits for the host between chunks.  Running one chunk past convergence is harmless (every kernel is a no-op then).
+    flags = torch.zeros(_FLAG_DEPTH, dtype=dt).pin_memory()
+    events = [torch.cuda.Event() for _ in range(_FLAG_DEPTH)]
+    pending = []          # slots whose flag copy is in flight, oldest first
+    slot = 0
     while k < max_iter:
         steps = min(check, max_iter - k)
         if cuda_graph is not None and steps == check:
@@ -94,17 +135,49 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
             for _ in range(steps):
                 iteration()
         k += steps
-        done = float(state[scal + K_DONE].item())   # the only device->host read of the loop
-        if done != 0.0:
-            break
-        if use_graph and cuda_graph is None and max_iter - k >= check:
-            cuda_graph = torch.cuda.CUDAGraph()
-            before = _lib.launch_count()
-            with torch.cuda.graph(cuda_graph):
-                for _ in range(check):
-                    iteration()
-            launches_per_replay = _lib.launch_count() - before        # kernels of ours inside one replay
-            _lib._dll.mgp_add_launch_count(-launches_per_replay)      # the capture pass itself executed nothing
+        flags[slot:slot + 1].copy_(state[scal + K_DONE:scal + K_DONE + 1], non_blocking=True)
+        events[slot].record()
+        pending.append(slot)
+        slot = (slot + 1) % _FLAG_DEPTH
+        if cuda_graph is None:
+            # eager chunks (short solves, the first chunk): check at once, then capture the graph for the rest
+            s0 = pending.pop(0)
+            events[s0].synchronize()
+            done = float(flags[s0])
+            if done != 0.0:
+                break
+            if use_graph and max_iter - k >= check:
+                _tc = time.perf_counter()
+                before = _lib.launch_count()
+                cuda_graph = _capture(iteration, check)
+                launches_per_replay = _lib.launch_count() - before        # kernels of ours inside one replay
+                _lib._dll.mgp_add_launch_count(-launches_per_replay)      # the capture pass itself executed nothing
+                if entry is not None:
+                    entry["graph"], entry["launches"] = cuda_graph, launches_per_replay
+                if _dbg:
+                    _t["capture"] = time.perf_counter() - _tc
+        elif len(pending) == _FLAG_DEPTH:
+            s0 = pending.pop(0)
+            _tw = time.perf_counter()
+            events[s0].synchronize()
+            if _dbg:
+                _w = time.perf_counter() - _tw
+                _t["max_wait"] = max(_t["max_wait"], _w); _t["waits"] += 1
+            done = float(flags[s0])
+            if done != 0.0:
+                break
+    if done == 0.0:
+        for s0 in pending:
+            events[s0].synchronize()
+            done = float(flags[s0])
+            if done != 0.0:
+                break
+    if _dbg:
+        torch.cuda.synchronize()
+        _t["total"] = time.perf_counter() - _t["start"]
+        import sys as _sys
+        print("[cg timing] " + " ".join(f"{k_}={v_:.4f}" if isinstance(v_, float) else f"{k_}={v_}" for k_, v_ in _t.items() if k_ != "start"),
+              file=_sys.stderr)
     out = torch.empty((n, c), dtype=dt, device=dev)
     _lib.call("mgp_cg_finalize_" + sfx, ptr(x), c_int64(ld), ptr(out), c_int64(c), c_int64(n), c_int32(c), ptr(state), stream())
     if st is not None:
@@ -113,6 +186,31 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
     info = CGInfo(iterations=int(tail[K_ITER]), mean_residual=float(tail[K_MEAN]), converged=(done == 1.0),
                   residual_norm=state[S_RESID * c:(S_RESID + 1) * c].clone())
     return out, (hist.cpu() if n_tridiag else None), info
+
+
+_CAPTURE_STREAM = None
+
+
+def _capture(fn, reps):
+    """Capture ``reps`` calls of ``fn`` into a CUDA graph.  Deliberately NOT ``with torch.cuda.graph(...)``: that context
+    manager runs ``gc.collect()`` and ``torch.cuda.empty_cache()`` on entry, which was measured to take anywhere from 5 ms
+    to 800 ms per capture on B200 boxes (per-solve times of 0.64 s .. 1.45 s for the same 0.63 s of GPU work).  A side
+    stream and capture_begin / capture_end only."""
+    global _CAPTURE_STREAM
+    if _CAPTURE_STREAM is None:
+        _CAPTURE_STREAM = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    cur = torch.cuda.current_stream()
+    _CAPTURE_STREAM.wait_stream(cur)
+    with torch.cuda.stream(_CAPTURE_STREAM):
+        g.capture_begin()
+        try:
+            for _ in range(reps):
+                fn()
+        finally:
+            g.capture_end()
+    cur.wait_stream(_CAPTURE_STREAM)
+    return g
 
 
 def _tridiag_from_hist(hist, n_rows, n_tridiag, dtype):

@@ -6,6 +6,8 @@ nearest_neighbors.py:12,23,25 + riemann_kernel.py:40) and ``mgp_graph_symmetrize
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib
@@ -15,7 +17,8 @@ from .._lib import c_int32, c_int64, c_size_t, ptr, stream
 class NearestNeighbors():
     def __init__(self, x=None, nlist=1) -> None:
         self.min_ivf = 5000
-        self.tensor_core = True     # use the tcgen05 search where it applies (results are identical either way)
+        # use the tcgen05 search (results are identical either way; MGP_KNN_TC=0 selects the CUDA-core kernel for A/B runs)
+        self.tensor_core = os.environ.get("MGP_KNN_TC", "1") != "0"
         self.last_search = None
         if x is not None:
             self.train(x, nlist)
