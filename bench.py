@@ -35,9 +35,9 @@ CFG = dict(workload="torus_R3_N1M_k32_nu2_cg16rhs", n=1_000_000, k=32, nu=2, kap
 # CG iterations the GPU solve of exactly this configuration needs (deterministic; measured on B200, see profiles/).
 # Used only by the CPU arms to scale their bounded sample (a few iterations) to a full solve.
 CG_ITERS_FULL_SOLVE = 1696
-# dram__bytes_read.sum + dram__bytes_write.sum of one lap_spmm_pipe_kernel launch (C=16, cfg-C) from the ncu --set full
-# capture committed as profiles/r01_ncu_spmm_pipe_c16.txt (281.8 MB read + 51.5 MB written)
-NCU_DRAM_BYTES_PER_SPMM16 = 333_309_440
+# dram__bytes_read.sum + dram__bytes_write.sum of one lap_spmm_wi_kernel<float,16> launch (C=16, cfg-C) from the
+# ncu --set full capture committed as profiles/r01_ncu_spmm_wi_pw16_c16.txt (306.2 MB read + 53.6 MB written)
+NCU_DRAM_BYTES_PER_SPMM16 = 359_816_192
 
 
 def spmm_algorithmic_bytes(n, nnz, c, w=4):
@@ -249,6 +249,8 @@ def run_ours(args):
     ev1.record(); torch.cuda.synchronize()
     spmv1_us = ev0.elapsed_time(ev1) * 1e3 / (2 * (reps // 2))
 
+    knn_tensor = knn_tensor_bench(dev)
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -281,12 +283,56 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": b1},
         "knn_build_s": round(t_search, 4), "graph_symmetrize_s": round(max(t_graph - t_search, 0.0), 4),
         "structure_build_s": round(t_struct, 4), "laplacian_values_ms": round(t_values_ms, 3),
+        "knn_tensor": knn_tensor,
         "clocks": clk.summary(),
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(idx.cpu(), val.cpu(), n, eps, iters)
     print(json.dumps(out))
     return out
+
+
+def knn_tensor_bench(dev, n=70000, d=784, k=10):
+    """BASELINE cfg-B's kNN (RMNIST-shape cloud) through the tcgen05 search, against the tensor-pipe roofline: the
+    denominator is cuBLAS TF32 (torch.matmul, 8192^3) measured in this process, as SURVEY.md 8(d) prescribes when TF32 MMA
+    is the instruction used; `issued` counts the 3 TF32 products per element pair, `useful` the 2*Q*N*d of the problem."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200.utils import synthetic
+    try:
+        x = synthetic.rmnist_shape(n, d, device=dev)
+        knn = mgp.NearestNeighbors(x)
+        knn.search(x, k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            knn.search(x, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        info = knn.last_search
+        research = int(info["stats"][0]) if "stats" in info else None
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            a @ b
+        e0.record()
+        for _ in range(10):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        torch.backends.cuda.matmul.allow_tf32 = old
+        peak = 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) / 10) / 1e9
+        del a, b, x
+        flops = 2.0 * n * n * d
+        return {"workload": f"rmnist_shape_{n}x{d}_k{k}", "kernel": info["kernel"], "ms": round(ms, 3),
+                "useful_tflops": round(flops / ms / 1e9, 1), "issued_tf32_tflops": round(3 * flops / ms / 1e9, 1),
+                "peak_tf32_tflops_cublas_measured": round(peak, 1), "frac_issued_of_peak": round(3 * flops / ms / 1e9 / peak, 4),
+                "research_queries": research, "timed": "whole search (prep + sweep + re-rank + re-search), CUDA events"}
+    except Exception as e:      # reported, never hidden
+        return {"error": repr(e)[:300]}
 
 
 # =====================================================================================================================

@@ -217,28 +217,41 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         }
         if (own_contig) bulk_g2s(xs, g.x + row0 * g.ldx + g.c0, (uint32_t)nrows * ROW_BYTES, &full_bar[s]);
       }
-      if (g.sync_flags && !peers_ready && nscat > nown) {           // first remote rows of this launch: all peers have signalled?
-        if (lane < g.npeers) {
-          const unsigned int* f = g.sync_flags[g.rank] + lane;
-          unsigned int spins = 0;
-          while ((int)(ld_acquire_sys(f) - sync_epoch) < 0) {
-            if (++spins > (1u << 25)) __trap();
-          }
-        }
-        __syncwarp();
-        peers_ready = true;
-      }
-      // scattered X rows: 4 consecutive lanes copy the four 16-byte chunks of one row (8 whole rows per warp instruction)
-      for (int rr = 8 * pw + sub; rr < nscat; rr += 8 * kWiProducerWarps) {
-        int sr = rr < nown ? (int)(row0 + rr) : ids[rr - nown];
-        if (g.xmap) sr = __ldg(g.xmap + sr);
-        const int dstrow = rr < nown ? rr : R + (rr - nown);
+      // scattered X rows: 4 consecutive lanes copy the four 16-byte chunks of one row (8 whole rows per warp instruction).
+      // Fused cross-GPU barrier: a warp waits for the peers' flags only when it reaches the first row that actually lives
+      // on ANOTHER rank -- tiles away from the partition boundaries (most of them) never wait, so the NVLink round trip
+      // of the barrier hides behind the interior tiles.
+      for (int rb = 8 * pw; rb < nscat; rb += 8 * kWiProducerWarps) {
+        const int rr = rb + sub;
+        const bool valid = rr < nscat;
+        int sr = 0;
         const unsigned char* xb = xbase;
-        if (g.peer_x && rr >= nown) {                            // halo row of another rank: its X over NVLink
-          xb = peer_tab[sr >> 26] + xoff;
-          sr &= (1 << 26) - 1;
+        if (valid) {
+          sr = rr < nown ? (int)(row0 + rr) : ids[rr - nown];
+          if (g.xmap) sr = __ldg(g.xmap + sr);
         }
-        cp_async16(xs + (size_t)dstrow * ROW_BYTES + ch * 16, xb + (int64_t)sr * ldxb);
+        bool remote = false;
+        if (valid && g.peer_x && rr >= nown) {                     // halo row: read it from its owner's X (NVLink if remote)
+          const int owner = sr >> 26;
+          xb = peer_tab[owner] + xoff;
+          sr &= (1 << 26) - 1;
+          remote = owner != g.rank;
+        }
+        if (g.sync_flags && !peers_ready && __any_sync(0xffffffffu, remote)) {
+          if (lane < g.npeers) {
+            const unsigned int* f = g.sync_flags[g.rank] + lane;
+            unsigned int spins = 0;
+            while ((int)(ld_acquire_sys(f) - sync_epoch) < 0) {
+              if (++spins > (1u << 25)) __trap();
+            }
+          }
+          __syncwarp();
+          peers_ready = true;
+        }
+        if (valid) {
+          const int dstrow = rr < nown ? rr : R + (rr - nown);
+          cp_async16(xs + (size_t)dstrow * ROW_BYTES + ch * 16, xb + (int64_t)sr * ldxb);
+        }
       }
       cp_async_arrive_noinc(&full_bar[s]);
       if (tid <= 16) rp[tid] = wp[tid] - base;

@@ -538,9 +538,13 @@ def bench_main(args, CFG):
                        "d2h_bytes_per_step": int(Xh.numel() * 4 * world)},
                "gpu_launches": int(launches),
                "transport": transport,
-               "collectives_per_iteration": ({"peer_barrier": CFG["nu"], "peer_allreduce_fused_with_scalars": 2,
-                                              "halo": "read from the owners' vectors over NVLink inside the SpMM"}
-                                             if transport == "peer" else {"halo_all_to_all": CFG["nu"], "all_reduce": 2})}
+               "collectives_per_iteration": (
+                   ({"launches": CFG["nu"] + 2, "barrier": "inside the SpMM launches (flags over NVLink, waited on at the first remote halo row)",
+                     "all_reduce": "2, inside the r / (p, x) update kernels (partials shipped to every peer)",
+                     "halo": "read from the owners' vectors over NVLink inside the SpMM"} if getattr(cg, "fused", False) else
+                    {"peer_barrier": CFG["nu"], "peer_allreduce_fused_with_scalars": 2,
+                     "halo": "read from the owners' vectors over NVLink inside the SpMM"})
+                   if transport == "peer" else {"halo_all_to_all": CFG["nu"], "all_reduce": 2})}
         print(json.dumps(out))
     dist.barrier()
     return None
