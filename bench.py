@@ -34,7 +34,7 @@ CFG = dict(workload="torus_R3_N1M_k32_nu2_cg16rhs", n=1_000_000, k=32, nu=2, kap
            max_iter=4000, normalization="symmetric", self_loops=True, seed=0, rhs_seed=1)
 # CG iterations the GPU solve of exactly this configuration needs (deterministic; measured on B200, see profiles/).
 # Used only by the CPU arms to scale their bounded sample (a few iterations) to a full solve.
-CG_ITERS_FULL_SOLVE = 1696
+CG_ITERS_FULL_SOLVE = 1690
 # dram__bytes_read.sum + dram__bytes_write.sum of one lap_spmm_wi_kernel<float,16> launch (C=16, cfg-C) from the
 # ncu --set full capture committed as profiles/r01_ncu_spmm_wi_pw16_c16.txt (306.2 MB read + 53.6 MB written)
 NCU_DRAM_BYTES_PER_SPMM16 = 359_816_192

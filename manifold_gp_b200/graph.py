@@ -60,6 +60,63 @@ def attach_permutation(idx: torch.Tensor, perm: torch.Tensor) -> None:
         pass
 
 
+# ---- graph persistence ----------------------------------------------------------------------------------
+# The kNN graph is the most expensive setup step (O(N^2 d)) and is hyper-parameter independent, but the reference rebuilds
+# it in every run (riemann_kernel.py:40-42 builds it in __init__, nothing is written to disk).  One file holds what a
+# later run needs to skip the search: the coalesced upper-triangular edge list, its mean squared distances, the Morton row
+# order the operators use, and a fingerprint of the point cloud it was built from.
+GRAPH_FILE_FORMAT = "mgp_b200.knn_graph"
+GRAPH_FILE_VERSION = 1
+
+
+def points_fingerprint(x: torch.Tensor) -> str:
+    """SHA-256 over shape, dtype and the raw bytes of up to 2 x 1 MiB of the point cloud (head and tail)."""
+    import hashlib
+    xc = x.detach().contiguous().cpu()
+    raw = xc.view(torch.uint8).reshape(-1)
+    h = hashlib.sha256()
+    h.update(repr((tuple(xc.shape), str(xc.dtype))).encode())
+    lim = 1 << 20
+    h.update(raw[:lim].numpy().tobytes())
+    h.update(raw[-lim:].numpy().tobytes())
+    return h.hexdigest()
+
+
+def save_knn_graph(path: str, edge_index: torch.Tensor, edge_value: torch.Tensor, n: int, k: int, x: torch.Tensor = None) -> None:
+    """Write the graph ``NearestNeighbors.graph`` returned (plus its attached row order) to ``path``."""
+    idx = edge_index.detach().cpu()
+    perm = getattr(edge_index, _PERM_ATTR, None)
+    payload = {
+        "format": GRAPH_FILE_FORMAT, "version": GRAPH_FILE_VERSION, "n": int(n), "k": int(k),
+        "edge_index": idx.to(torch.int32) if n < 2 ** 31 else idx,        # int32 on disk halves the file; int64 in memory
+        "edge_value": edge_value.detach().cpu(),
+        "perm": None if perm is None else perm.detach().cpu().to(torch.int32 if n < 2 ** 31 else torch.int64),
+        "points_fingerprint": None if x is None else points_fingerprint(x),
+    }
+    torch.save(payload, path)
+
+
+def load_knn_graph(path: str, device, x: torch.Tensor = None, k: int = None):
+    """(edge_index [2,M] int64, edge_value [M]) on ``device`` with the row order re-attached.  Raises if the file was
+    built from a different point cloud (``x`` given) or a different neighbour count (``k`` given)."""
+    payload = torch.load(path, map_location="cpu", weights_only=True)
+    if payload.get("format") != GRAPH_FILE_FORMAT or payload.get("version") != GRAPH_FILE_VERSION:
+        raise ValueError(f"{path}: not a {GRAPH_FILE_FORMAT} v{GRAPH_FILE_VERSION} file")
+    if k is not None and int(payload["k"]) != int(k):
+        raise ValueError(f"{path}: built with k={payload['k']}, requested k={k}")
+    if x is not None:
+        if int(payload["n"]) != int(x.shape[0]):
+            raise ValueError(f"{path}: built for {payload['n']} points, got {x.shape[0]}")
+        fp = payload.get("points_fingerprint")
+        if fp is not None and fp != points_fingerprint(x):
+            raise ValueError(f"{path}: point cloud fingerprint mismatch (the graph was built from different data)")
+    idx = payload["edge_index"].to(device=device, dtype=torch.int64)
+    val = payload["edge_value"].to(device)
+    if payload["perm"] is not None:
+        attach_permutation(idx, payload["perm"].to(device=device, dtype=torch.int64))
+    return idx, val
+
+
 def padded_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int):
     """Padded entry streams for the pipelined kernel (csrc/lap_spmm_pipe.cu): every row holds a multiple of 4 entries, every
     tile of ``R`` rows starts at a multiple of 8 (the last row of a tile absorbs the tile's slack); padding entries carry

@@ -50,12 +50,23 @@ class RiemannKernel(_KernelBase):
                  bump_decay: Optional[float] = 0.01,
                  graphbandwidth_prior=None,
                  graphbandwidth_constraint=None,
+                 graph_file: Optional[str] = None,
                  **kwargs):
         super(RiemannKernel, self).__init__(**kwargs)
 
         self.knn = NearestNeighbors(x, nlist=1)
         self.nearest_neighbors = nearest_neighbors
-        self.edge_index, self.edge_value = self.knn.graph(self.nearest_neighbors, nprobe=1)
+        # graph_file (extension): reuse a graph saved by an earlier run instead of searching again; the
+        # file is written after the first build.  None = the reference's behaviour (always rebuild, :40-42).
+        import os
+        from .. import graph as _graph
+        if graph_file is not None and os.path.exists(graph_file):
+            self.edge_index, self.edge_value = _graph.load_knn_graph(graph_file, x.device, x=x, k=nearest_neighbors)
+            self.edge_value = self.edge_value.to(x.dtype)
+        else:
+            self.edge_index, self.edge_value = self.knn.graph(self.nearest_neighbors, nprobe=1)
+            if graph_file is not None:
+                _graph.save_knn_graph(graph_file, self.edge_index, self.edge_value, x.shape[0], nearest_neighbors, x=x)
         self.laplacian_normalization = laplacian_normalization
         self.num_modes = num_modes
         self.bump_scale = bump_scale

@@ -144,3 +144,23 @@ def test_training_loss_matches_dense_reference_and_decreases(dumbbell):
         l_cg = manifold_informed_train(model, frozen, max_iter=0, tolerance=0.0, max_cholesky=100, cg_tolerance=1e-6, cg_max_iter=4000)
     l_ch = manifold_informed_train(model, frozen, max_iter=0, tolerance=0.0, max_cholesky=4000)
     assert abs(l_cg - l_ch) < 0.05 * max(1.0, abs(l_ch))
+
+
+def test_graph_file_reuse(dumbbell, tmp_path):
+    """graph_file: the second kernel loads the saved graph instead of searching and produces the same
+    operator (edge list, values, row order -> identical precision matvec)."""
+    import manifold_gp_b200 as mgp
+    x = dumbbell["train_x"].double().to(DEV)
+    path = str(tmp_path / "dumbbell_k10.pt")
+    kw = dict(nu=NU, x=x, nearest_neighbors=K, laplacian_normalization="symmetric", num_modes=MODES, graph_file=path)
+    k1 = mgp.RiemannMaternKernel(**kw).to(DEV).double()
+    import os
+    assert os.path.exists(path)
+    k2 = mgp.RiemannMaternKernel(**kw).to(DEV).double()
+    assert k2.knn.last_search is None, "the second kernel searched again instead of loading the graph file"
+    assert torch.equal(k1.edge_index, k2.edge_index) and torch.equal(k1.edge_value, k2.edge_value)
+    for kk in (k1, k2):
+        kk.graphbandwidth = torch.tensor([[EPS]], dtype=torch.float64, device=DEV)
+        kk.lengthscale = torch.tensor([[KAPPA]], dtype=torch.float64, device=DEV)
+    v = torch.randn(x.shape[0], 3, dtype=torch.float64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    assert torch.equal(k1.precision()._matmul(v), k2.precision()._matmul(v))

@@ -78,3 +78,28 @@ def test_wi_halo_lists_padding():
             assert torch.equal(hc[a:a + L], hcol[int(hptr[k]):int(hptr[k]) + L])
             if L:
                 assert bool((hc[a + L:b] == hcol[int(hptr[k]) + L - 1]).all())   # padding repeats the last (valid) id
+
+
+def test_knn_graph_file_round_trip(tmp_path):
+    """graph.save_knn_graph / load_knn_graph: the edge list, values and the attached row order survive,
+    and a file built from other points or another k is refused."""
+    import pytest
+    from manifold_gp_b200 import graph
+    g = torch.Generator().manual_seed(0)
+    n, k = 500, 6
+    x = torch.randn(n, 3, generator=g)
+    idx = torch.stack([torch.randint(0, n - 1, (900,), generator=g), torch.randint(0, n, (900,), generator=g)])
+    val = torch.rand(900, generator=g)
+    perm = torch.randperm(n, generator=g)
+    graph.attach_permutation(idx, perm)
+    path = str(tmp_path / "g.pt")
+    graph.save_knn_graph(path, idx, val, n, k, x=x)
+    idx2, val2 = graph.load_knn_graph(path, "cpu", x=x, k=k)
+    assert idx2.dtype == torch.int64 and torch.equal(idx2, idx) and torch.equal(val2, val)
+    assert torch.equal(getattr(idx2, graph._PERM_ATTR), perm)
+    with pytest.raises(ValueError):
+        graph.load_knn_graph(path, "cpu", x=x + 1.0, k=k)
+    with pytest.raises(ValueError):
+        graph.load_knn_graph(path, "cpu", x=x, k=k + 1)
+    with pytest.raises(ValueError):
+        graph.load_knn_graph(path, "cpu", x=x[:-1], k=k)
