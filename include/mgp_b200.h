@@ -203,6 +203,17 @@ int mgp_lap_spmm_pipe_f64(const int32_t* prowptr, const uint16_t* plcol, const d
  * and the producer warps wait for all ranks' flags before fetching the first remote row (local copies start at once).
  * Replaces graph_laplacian_operator.py:117-119 / precision_matern_operator.py:28-32 like the kernels above.
  * Returns MGP_EUNSUPPORTED (nothing launched) when the call does not qualify. */
+/* Single-column SpMV on the same warp-interleaved streams (lap_spmv_tile.cu): 6 bytes per nonzero streamed, the tile's slice
+ * of x in shared memory.  Same operation and reference lines as above for one right-hand side (Lanczos, single-RHS CG).
+ * x / y: column vectors with row strides ldx / ldy.  MGP_EUNSUPPORTED when tile_rows != 128 or the halo does not fit. */
+int mgp_lap_spmv_tile_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
+                          const int32_t* hcol, int32_t tile_rows, int32_t hmax, const float* shift, const float* post,
+                          const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n,
+                          void* stream);
+int mgp_lap_spmv_tile_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag, const int32_t* hptr,
+                          const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift, const double* post,
+                          const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
+                          void* stream);
 int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const float* a, int64_t n, float* aw, void* stream);
 int mgp_lap_wi_values_f64(const int32_t* rowptr, const int32_t* wptr, const double* a, int64_t n, double* aw, void* stream);
 int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,

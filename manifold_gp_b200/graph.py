@@ -429,7 +429,7 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
 LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call launched (bench.py reports it)
-SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi"  (tests force each; "auto": wi, else pipe, else tiled, else csr)
+SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv"  (tests force each; "auto": wi, else pipe, else tiled, else csr)
 
 
 def _note_kernel(name):
@@ -518,6 +518,24 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
         # a pass wider than estimated (unaligned leading dimension): the CSR kernel handles it
     if peer_x is not None:
         raise RuntimeError("lap_spmm: peer-memory halo reads requested but the tile structure does not fit this call")
+    # one column, no fused dot / pre scaling: the streamed single-column kernel on the tile streams (lap_spmv_tile.cu)
+    if c == 1 and pre is None and dot_out is None and SPMM_KERNEL in ("auto", "spmv") and slack_ok:
+        t = st.build_tiles()
+        if t is not None and "wptr" in t:
+            if out is None:
+                out = torch.empty((st.n, 1), dtype=dt, device=x.device)
+            aw = st.wi_values(a)
+            rc = _lib.call_rc("mgp_lap_spmv_tile_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag), ptr(t["hptr"]),
+                              ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
+                              ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
+                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), stream())
+            if rc == 0:
+                _note_kernel("lap_spmv_tile_kernel")
+                return out
+            if rc != _lib.MGP_EUNSUPPORTED:
+                raise RuntimeError(f"mgp_lap_spmv_tile_{sfx} failed ({rc}): {_lib.last_error()}")
+    if SPMM_KERNEL == "spmv":
+        raise RuntimeError("lap_spmm: single-column tile kernel requested but this call does not qualify")
     # v1 CSR kernel works in the structure's order only
     if x_external:
         x = x.index_select(0, st.perm)

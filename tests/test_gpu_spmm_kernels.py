@@ -142,3 +142,42 @@ def test_tile_statistics_cfgc_like(problem):
     mean_halo = t["halo_total"] / ntiles
     assert mean_halo < 6 * t["rows"], mean_halo
     assert lap.structure.tiled_ok(torch.float32, 16)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_single_column_tile_spmv_matches_dense(problem, dtype):
+    """lap_spmv_tile_kernel (one right-hand side: Lanczos, single-RHS CG) against the dense operator, in the structure's
+    order, in the caller's order (xmap / ymap) and on a strided column of a wider buffer."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph
+    x, idx, val = problem
+    n = 6000
+    xs = x[:n].contiguous()
+    idx6, val6 = mgp.NearestNeighbors(xs).graph(12)
+    lap = mgp.GraphLaplacianOperator(val6.to(dtype), idx6, n, torch.tensor([[0.15]], dtype=dtype, device=DEV), "symmetric")
+    st = lap.structure
+    _, deg, diag, a = lap._values()
+    D, A = _dense(st, a, diag, n)
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    post = torch.rand(n, dtype=dtype, device=DEV, generator=gen) + 0.5
+    shift = torch.tensor([2.3], dtype=dtype, device=DEV)
+    wide = torch.randn(n, 8, dtype=dtype, device=DEV, generator=gen)
+    for X in (torch.randn(n, 1, dtype=dtype, device=DEV, generator=gen), wide[:, 3:4]):
+        ref = ((D + float(shift) * torch.eye(n, dtype=torch.float64, device=DEV)) @ X.double() - A @ X.double()) * post.double().unsqueeze(1)
+        graph.SPMM_KERNEL = "spmv"
+        try:
+            Y = graph.lap_spmm(st, a, diag, X, shift=shift, post=post)
+            assert graph.LAST_SPMM_KERNEL == "lap_spmv_tile_kernel"
+            # caller's row order in and out: P^T M P applied to the un-permuted vector
+            Xe = st.to_external(X.contiguous())
+            Ye = graph.lap_spmm(st, a, diag, Xe, shift=shift, post=post, x_external=True, y_external=True)
+        finally:
+            graph.SPMM_KERNEL = "auto"
+        assert rel_err(Y, ref) < tol
+        assert rel_err(st.to_internal(Ye), ref) < tol
+    # the operator-level matvec (auto dispatch) uses it for one column
+    v = torch.randn(n, dtype=dtype, device=DEV, generator=gen)
+    out = lap._matmul(v)
+    assert graph.LAST_SPMM_KERNEL == "lap_spmv_tile_kernel"
+    assert rel_err(out, (lap.to_dense().double() @ v.double())) < tol
