@@ -428,6 +428,7 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 
 
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
+TILE64_MODES = ("tile64",)   # add "auto" to make the one-block-per-tile kernel the default for 64-byte-row passes
 LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call launched (bench.py reports it)
 SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv"  (tests force each; "auto": wi, else pipe, else tiled, else csr)
 
@@ -461,8 +462,8 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
     # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
     # kernel (X served from L1/L2) is faster
-    use_tiled = SPMM_KERNEL != "csr" and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi"))
-    if SPMM_KERNEL in ("tiled", "pipe", "wi") and not use_tiled:
+    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64"))
+    if SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64") and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
         t = st.tiles
@@ -470,6 +471,20 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
         if peer_x is not None and not (pre is None and "wptr" in t):
             raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
+        if pre is None and "wptr" in t and SPMM_KERNEL in TILE64_MODES and peer_x is None:
+            aw = st.wi_values(a)
+            rc = _lib.call_rc("mgp_lap_spmm_tile64_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag), ptr(t["hptr"]),
+                              ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
+                              ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
+                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with),
+                              ptr(dot_out), ptr(ws), stream())
+            if rc == 0:
+                _note_kernel("lap_spmm_tile64_kernel")
+                return out
+            if rc != _lib.MGP_EUNSUPPORTED:
+                raise RuntimeError(f"mgp_lap_spmm_tile64_{sfx} failed ({rc}): {_lib.last_error()}")
+            if SPMM_KERNEL == "tile64":
+                raise RuntimeError("lap_spmm: tile64 kernel requested but this call does not qualify")
         if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi") or peer_x is not None):
             aw = st.wi_values(a)
             hcol = t["hcol_peer"] if peer_x is not None else t["hcol"]

@@ -79,28 +79,30 @@ def test_tiled_and_csr_kernels_agree_with_dense(problem, dtype):
                 assert torch.equal(Y, Y2)
                 assert rel_err(dot, (X.double() * ref).sum(0)) < tol * 10, ("pipe", c)
             if not use_pre and c % (16 if dtype == torch.float32 else 8) == 0:
-                # v5 warp-interleaved kernel (64-byte rows of X, entry streams in lane-consumption order)
-                graph.SPMM_KERNEL = "wi"
-                try:
-                    dot = torch.zeros(c, dtype=dtype, device=DEV)
-                    Y = graph.lap_spmm(st, a, diag, X, shift=shift if use_shift else None, post=post if use_post else None,
-                                       dot_with=X, dot_out=dot)
-                    Y2 = graph.lap_spmm(st, a, diag, X, shift=shift if use_shift else None, post=post if use_post else None)
-                    dot3 = torch.zeros(c, dtype=dtype, device=DEV)
-                    Z = torch.randn(n, c, dtype=dtype, device=DEV, generator=gen)
-                    graph.lap_spmm(st, a, diag, X, shift=shift if use_shift else None, post=post if use_post else None,
-                                   dot_with=Z, dot_out=dot3)
-                finally:
-                    graph.SPMM_KERNEL = "auto"
-                assert rel_err(Y, ref) < tol, ("wi", c, use_post)
-                assert torch.equal(Y, Y2)
-                assert rel_err(dot, (X.double() * ref).sum(0)) < tol * 10, ("wi", c)
-                assert (dot3.double() - (Z.double() * ref).sum(0)).abs().max() < tol * 10 * (Z.double().norm() * ref.norm()) / c ** 0.5
+                # v5 warp-interleaved kernel (64-byte rows of X, entry streams in lane-consumption order) and the
+                # one-block-per-tile kernel on the same streams
+                for kern64 in ("wi", "tile64"):
+                    graph.SPMM_KERNEL = kern64
+                    try:
+                        dot = torch.zeros(c, dtype=dtype, device=DEV)
+                        Y = graph.lap_spmm(st, a, diag, X, shift=shift if use_shift else None, post=post if use_post else None,
+                                           dot_with=X, dot_out=dot)
+                        Y2 = graph.lap_spmm(st, a, diag, X, shift=shift if use_shift else None, post=post if use_post else None)
+                        dot3 = torch.zeros(c, dtype=dtype, device=DEV)
+                        Z = torch.randn(n, c, dtype=dtype, device=DEV, generator=gen)
+                        graph.lap_spmm(st, a, diag, X, shift=shift if use_shift else None, post=post if use_post else None,
+                                       dot_with=Z, dot_out=dot3)
+                    finally:
+                        graph.SPMM_KERNEL = "auto"
+                    assert rel_err(Y, ref) < tol, (kern64, c, use_post)
+                    assert torch.equal(Y, Y2)
+                    assert rel_err(dot, (X.double() * ref).sum(0)) < tol * 10, (kern64, c)
+                    assert (dot3.double() - (Z.double() * ref).sum(0)).abs().max() < tol * 10 * (Z.double().norm() * ref.norm()) / c ** 0.5
         # caller-order translation: x in external order, y in external order
         Xe = X
         ref_ext = st.to_external((D @ st.to_internal(Xe).double()) - A @ st.to_internal(Xe).double())
         for kern in ("csr", "tiled") + (("pipe",) if c % (4 if dtype == torch.float32 else 2) == 0 else ()) + \
-                (("wi",) if c % (16 if dtype == torch.float32 else 8) == 0 else ()):
+                (("wi", "tile64") if c % (16 if dtype == torch.float32 else 8) == 0 else ()):
             graph.SPMM_KERNEL = kern
             try:
                 Y = graph.lap_spmm(st, a, diag, Xe, x_external=True, y_external=True)
