@@ -266,8 +266,27 @@ def linear_cg(op, rhs, n_tridiag=0, tolerance=None, eps=1e-10, stop_updating_aft
     for c0 in range(0, c, MAX_CG_COLS):
         # NB column chunks converge independently (the published mean-over-columns test is applied per chunk)
         nt = n_tridiag if c0 == 0 else 0
-        o, h, info = _cg_chunk(op, rhs[:, c0:c0 + MAX_CG_COLS], nt, float(tolerance), float(eps), float(stop_updating_after),
-                               int(n_iter), int(n_tridiag_iter))
+        blk = rhs[:, c0:c0 + MAX_CG_COLS]
+        cb = blk.shape[1]
+        # Column counts the 128-bit SpMM kernels cannot take (not a multiple of 4 fp32 / 2 fp64 columns: e.g. the 10 probe
+        # vectors + 1 right-hand side of the training loss) would fall to the un-pipelined tiled kernel (2x slower per
+        # SpMM).  Zero columns are free in a 64-byte-row pass, so the block is padded to the next multiple of 16 (8) columns;
+        # a zero column has residual exactly 0, hence comparing the padded mean with tolerance * cb / cpad is the published
+        # mean-over-columns stopping rule on the original block.
+        vecw, roww = (4, 16) if rhs.dtype == torch.float32 else (2, 8)
+        cpad = (cb + roww - 1) // roww * roww
+        fused = hasattr(op, "_mgp_matvec") and getattr(op, "_native", lambda: True)()
+        if fused and cb >= 5 and cb % vecw != 0 and cpad <= MAX_CG_COLS:
+            blk_p = torch.zeros((n, cpad), dtype=rhs.dtype, device=rhs.device)
+            blk_p[:, :cb] = blk
+            o, h, info = _cg_chunk(op, blk_p, nt, float(tolerance) * cb / cpad, float(eps), float(stop_updating_after),
+                                   int(n_iter), int(n_tridiag_iter))
+            o = o[:, :cb]
+            info["mean_residual"] = info["mean_residual"] * cpad / cb
+            info["residual_norm"] = info["residual_norm"][:cb]
+        else:
+            o, h, info = _cg_chunk(op, blk, nt, float(tolerance), float(eps), float(stop_updating_after),
+                                   int(n_iter), int(n_tridiag_iter))
         outs.append(o)
         infos.append(info)
         if c0 == 0:
