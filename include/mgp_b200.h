@@ -55,14 +55,14 @@ size_t mgp_knn_search_ws_bytes(int64_t n, int64_t nq, int32_t d, int32_t k);
 int mgp_knn_search_f32(const float* db, int64_t n, const float* q, int64_t nq, int32_t d, int32_t k,
                        float* dist2, int64_t* idx, void* ws, size_t ws_bytes, void* stream);
 
-/* Same contract and bit-identical results, for d >= 16 and k <= 48: the q.x distance tiles are TF32 tcgen05.mma
+/* Same contract and bit-identical results, for any d and k <= 48 (n >= 256): the q.x distance tiles are TF32 tcgen05.mma
  * contractions (TMA-fed, TMEM accumulators, 3xTF32 split) with a fused top-(k+margin) selection in the epilogue warps;
  * candidates are re-ranked with the exact fp32 form above and every query is certified (all discarded points provably
  * farther than its k-th neighbour) or re-searched exhaustively on the CUDA cores -- no host synchronisation.
  * Replaces the same faiss call (nearest_neighbors.py:37; faiss' own large-batch path is the |q|^2+|x|^2-2q.x BLAS form).
  * stats (device uint32[4]): [0] queries that needed the exhaustive re-search, [1] float bits of the largest
- * |approximate - exact| candidate distance seen, [2] queries processed.  `same` != 0 (or db == q) shares the prepared
- * database with the queries.  Returns MGP_EUNSUPPORTED (nothing launched; ws_bytes query returns 0) outside that range. */
+ * |approximate - exact| candidate distance seen, [2] queries processed.  `same` is a sizing hint only (the query-role copy
+ * of the points differs from the database-role copy in the norm column and is always prepared).  Returns MGP_EUNSUPPORTED (nothing launched; ws_bytes query returns 0) outside that range. */
 size_t mgp_knn_search_tc_ws_bytes(int64_t n, int64_t nq, int32_t d, int32_t k, int32_t same);
 int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq, int32_t d, int32_t k,
                           float* dist2, int64_t* idx, void* ws, size_t ws_bytes, uint32_t* stats, void* stream);

@@ -1,4 +1,4 @@
-// Exact brute-force kNN for large d on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
+// Exact brute-force kNN on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.  Any d >= 1, k <= 48.
 //
 // Reference: NearestNeighbors.search, manifold_gp/utils/nearest_neighbors.py:35-37 -> faiss Index{Flat,IVFFlat(nlist=1)}
 // .search, whose large-batch path is the BLAS form |q|^2 + |x|^2 - 2 q.x.  Here the q.x tiles are
@@ -6,22 +6,25 @@
 // "direct" form) by a certified re-rank:
 //
 //   1. knn_tc_colsum / knn_tc_prep   centre the points on the database mean, split every coordinate into two TF32-exact
-//                                    terms hi + lo (hi = top 19 bits, lo = x - hi), |x|^2 accumulated in fp64.
+//                                    terms hi + lo (hi = top 19 bits, lo = x - hi); one extra K column carries the norm
+//                                    term (-|x|^2 / 2 on the database side, 1 on the query side; |x|^2 in fp64).
 //   2. knn_tc_sweep_kernel           persistent, warp-specialised: one TMA producer thread, one tcgen05.mma issuer thread,
-//                                    four epilogue warps.  Per (128 queries x 128 points) tile and 32-wide k-block it issues
-//                                    hi.hi + hi.lo + lo.hi (3xTF32: the dropped lo.lo term is 2^-22 relative) into a
-//                                    double-buffered TMEM accumulator; the epilogue warps read the accumulator with
-//                                    tcgen05.ld (one query row per thread), form d~ = |q|^2 + |x|^2 - 2 q.x and run the
-//                                    fused selection: an in-register threshold test per candidate, survivors appended to the
-//                                    row's candidate list, warp-cooperative rank-and-compact when a list fills.  Output: the
-//                                    K' = k + margin best candidates per (query, database split) and the threshold tau that
-//                                    every discarded point exceeded.
-//   3. knn_tc_rerank_kernel          exact fp32 distances of the candidates (sum_d (q_d - x_d)^2, ascending d, mul-then-add:
-//                                    bit-identical to knn.cu), top-k by (distance, index), and the certificate
-//                                    tau_min - b - E > d_k with b = mean of d~ - d over the query's candidates (the tensor cores accumulate with
-//                                    truncation: a bias proportional to q.x) and E = |b|/4 + 8 x max |d~ - d - b| + floor.
+//                                    eight epilogue warps (two per TMEM lane quadrant).  Per (128 queries x BN points) tile
+//                                    and k-block it issues hi.hi + hi.lo + lo.hi (3xTF32: the dropped lo.lo term is 2^-22
+//                                    relative) into a double-buffered TMEM accumulator, which then holds q.x - |x|^2 / 2; the
+//                                    epilogue warps read it with tcgen05.ld (one query row per thread) and run the fused
+//                                    selection: d~ <= tau  <=>  acc >= (|q|^2 - tau) / 2, tested 8 columns at a time through
+//                                    a max chain + warp vote, survivors appended to the row's candidate list, bisection
+//                                    pruning when a list fills.  Output: the K' = k + margin best candidates per (query,
+//                                    database split, epilogue warp) and the threshold tau every discarded point exceeded.
+//   3. knn_tc_rerank_kernel          the candidate union is pruned to K' by approximate distance, then exact fp32
+//                                    distances (sum_d (q_d - x_d)^2, ascending d, mul-then-add: bit-identical to knn.cu),
+//                                    top-k by (distance, index), and the certificate tau_min - b - E > d_k with b = mean of
+//                                    d~ - d over the query's candidates (the tensor cores accumulate with truncation: a bias
+//                                    proportional to q.x) and E = |b|/4 + 8 x max |d~ - d - b| + floor.
 //                                    A query that fails it is appended to a list ...
-//   4. knn_kernel (knn.cu)           ... and re-searched exhaustively on the CUDA cores (device-side count, no host sync).
+//   4. knn_kernel<LIST> (knn.cu)     ... and re-searched exhaustively on the CUDA cores (device-side count, database split
+//                                    over the spare blocks + merge, no host synchronisation).
 #include <cuda.h>
 #include <float.h>
 

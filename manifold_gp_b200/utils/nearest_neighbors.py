@@ -46,7 +46,7 @@ class NearestNeighbors():
         same = q.data_ptr() == self._db.data_ptr() and nq == n
         self.last_search = {"kernel": "cuda_core"}
         if self.tensor_core:
-            # d >= 16, k <= 48: TF32 tcgen05 distance tiles + fused top-(k+margin) + exact certified re-rank (knn_tc.cu);
+            # k <= 48, n >= 256: TF32 tcgen05 distance tiles + fused top-(k+margin) + exact certified re-rank (knn_tc.cu);
             # bit-identical results to the CUDA-core kernel below.
             nb = _lib.query("mgp_knn_search_tc_ws_bytes", c_int64(n), c_int64(nq), c_int32(d), c_int32(k), c_int32(int(same)))
             if nb > 0:
