@@ -205,15 +205,17 @@ int mgp_lap_spmm_pipe_f64(const int32_t* prowptr, const uint16_t* plcol, const d
  * Returns MGP_EUNSUPPORTED (nothing launched) when the call does not qualify. */
 /* Single-column SpMV on the same warp-interleaved streams (lap_spmv_tile.cu): 6 bytes per nonzero streamed, the tile's slice
  * of x in shared memory.  Same operation and reference lines as above for one right-hand side (Lanczos, single-RHS CG).
- * x / y: column vectors with row strides ldx / ldy.  MGP_EUNSUPPORTED when tile_rows != 128 or the halo does not fit. */
+ * x / y: column vectors with row strides ldx / ldy; optional fused dot_out[0] = dot_with^T y (dot_with strided like x; dot_ws
+ * from mgp_lap_spmm_dot_ws_bytes).  MGP_EUNSUPPORTED when tile_rows != 128, the halo does not fit, or the dot workspace cannot
+ * hold one partial per tile. */
 int mgp_lap_spmv_tile_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
                           const int32_t* hcol, int32_t tile_rows, int32_t hmax, const float* shift, const float* post,
                           const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n,
-                          void* stream);
+                          const float* dot_with, float* dot_out, void* dot_ws, void* stream);
 int mgp_lap_spmv_tile_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag, const int32_t* hptr,
                           const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift, const double* post,
                           const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
-                          void* stream);
+                          const double* dot_with, double* dot_out, void* dot_ws, void* stream);
 /* The same one-block-per-tile shape for 64-byte rows (ncols a multiple of 16 fp32 / 8 fp64): X rows staged with cp.async by the
  * whole block, streams read straight from global memory, overlap from the blocks resident per SM (no producer warps).
  * Same operation, reference lines, dot epilogue and alignment rules as mgp_lap_spmm_wi (no peer-memory mode). */

@@ -20,6 +20,8 @@ namespace mgp {
 
 constexpr int kSvRows = 128;
 constexpr int kSvThreads = 256;
+// capacity of the partial-sum area of the dot workspace (mgp_lap_spmm_dot_ws_bytes = 256 + kNumSMs * 8 * 32 * 8 bytes)
+constexpr size_t kDotWsPartialBytes = (size_t)kNumSMs * 8 * 32 * 8;
 
 template <typename T>
 __global__ void __launch_bounds__(kSvThreads)
@@ -27,9 +29,11 @@ lap_spmv_tile_kernel(const int* __restrict__ wptr, const unsigned short* __restr
                      const T* __restrict__ diag, const int* __restrict__ hptr, const int* __restrict__ hcol,
                      const T* __restrict__ shift_p, const T* __restrict__ post, const int* __restrict__ xmap,
                      const int* __restrict__ ymap, const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy,
-                     int64_t n) {
+                     int64_t n, const T* __restrict__ dot_with, T* __restrict__ dot_out, T* __restrict__ partials,
+                     unsigned int* __restrict__ counter, int dot_is_x) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xs = reinterpret_cast<T*>(smem_raw);                 // [128 own rows | halo rows]
+  T dsum = T(0);                                          // this thread's share of dot_with^T y (optional epilogue)
   const int t = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)t * kSvRows;
@@ -75,6 +79,39 @@ lap_spmv_tile_kernel(const int* __restrict__ wptr, const unsigned short* __restr
       if (post) out *= __ldg(post + row);
       const int64_t yrow = ymap ? (int64_t)__ldg(ymap + row) : row;
       y[yrow * ldy] = out;
+      if (dot_out) {
+        T dw = xs[r];
+        if (!dot_is_x) {
+          const int64_t drow = xmap ? (int64_t)__ldg(xmap + row) : row;
+          dw = __ldg(dot_with + drow * ldx);
+        }
+        dsum = fma(dw, out, dsum);
+      }
+    }
+  }
+  if (dot_out) {
+    // block sum -> partials[block]; the last block to arrive adds the partials in a fixed order (deterministic)
+    __shared__ T red[kSvThreads];
+    dsum = warp_sum(dsum);
+    __syncthreads();
+    if (lane == 0) red[warp] = dsum;
+    __syncthreads();
+    if (tid == 0) {
+      T s = T(0);
+#pragma unroll
+      for (int w = 0; w < kSvThreads / 32; ++w) s += red[w];
+      partials[blockIdx.x] = s;
+    }
+    if (last_block_ticket(counter)) {
+      T s = T(0);
+      for (int b = tid; b < (int)gridDim.x; b += kSvThreads) s += __ldcg(partials + b);
+      red[tid] = s;
+      __syncthreads();
+      if (tid == 0) {
+        T tot = T(0);
+        for (int i = 0; i < kSvThreads; ++i) tot += red[i];
+        dot_out[0] = tot;
+      }
     }
   }
 }
@@ -218,6 +255,7 @@ static int lap_spmm_tile64(const int* wptr, const unsigned short* wcol, const T*
     configured = smem;
   }
   const int64_t ntiles = ceil_div(n, (int64_t)kSvRows);
+  if (dot_out && (size_t)ntiles * CW * sizeof(T) > kDotWsPartialBytes) return MGP_EUNSUPPORTED;   // per-tile partials must fit dot_ws
   unsigned int* counter = dot_out ? reinterpret_cast<unsigned int*>(dot_ws) : nullptr;
   T* partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
   for (int c0 = 0; c0 < ncols; c0 += CW) {
@@ -232,16 +270,21 @@ static int lap_spmm_tile64(const int* wptr, const unsigned short* wcol, const T*
 template <typename T>
 static int lap_spmv_tile(const int* wptr, const unsigned short* wcol, const T* aw, const T* diag, const int* hptr, const int* hcol,
                          int tile_rows, int hmax, const T* shift, const T* post, const int* xmap, const int* ymap, const T* x,
-                         int64_t ldx, T* y, int64_t ldy, int64_t n, cudaStream_t st) {
+                         int64_t ldx, T* y, int64_t ldy, int64_t n, const T* dot_with, T* dot_out, void* dot_ws, cudaStream_t st) {
   MGP_CHECK_ARG(wptr && wcol && aw && diag && hptr && hcol && x && y, "lap_spmv_tile: null pointer");
+  MGP_CHECK_ARG((dot_out == nullptr) || (dot_with && dot_ws), "lap_spmv_tile: dot epilogue needs dot_with and dot_ws");
   MGP_CHECK_ARG(n > 0 && ldx >= 1 && ldy >= 1 && hmax >= 0, "lap_spmv_tile: bad shape");
   MGP_CHECK_ARG(x != y, "lap_spmv_tile: X and Y must not alias");
   if (tile_rows != kSvRows) return MGP_EUNSUPPORTED;
   const size_t smem = (size_t)(kSvRows + hmax + 4) * sizeof(T);
   if (smem > 48 * 1024) return MGP_EUNSUPPORTED;
   const int64_t ntiles = ceil_div(n, (int64_t)kSvRows);
+  if (dot_out && (size_t)ntiles * sizeof(T) > kDotWsPartialBytes) return MGP_EUNSUPPORTED;   // one partial per tile must fit dot_ws
+  unsigned int* counter = dot_out ? reinterpret_cast<unsigned int*>(dot_ws) : nullptr;
+  T* partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
   lap_spmv_tile_kernel<T><<<(unsigned)ntiles, kSvThreads, smem, st>>>(wptr, wcol, aw, diag, hptr, hcol, shift, post, xmap, ymap, x,
-                                                                       ldx, y, ldy, n);
+                                                                       ldx, y, ldy, n, dot_out ? dot_with : nullptr, dot_out,
+                                                                       partials, counter, (dot_out && dot_with == x) ? 1 : 0);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }
@@ -253,16 +296,16 @@ extern "C" {
 int mgp_lap_spmv_tile_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
                           const int32_t* hcol, int32_t tile_rows, int32_t hmax, const float* shift, const float* post,
                           const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n,
-                          void* stream) {
+                          const float* dot_with, float* dot_out, void* dot_ws, void* stream) {
   return mgp::lap_spmv_tile<float>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, hmax, shift, post, xmap, ymap, x, ldx, y, ldy, n,
-                                   (cudaStream_t)stream);
+                                   dot_with, dot_out, dot_ws, (cudaStream_t)stream);
 }
 int mgp_lap_spmv_tile_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag, const int32_t* hptr,
                           const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift, const double* post,
                           const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
-                          void* stream) {
+                          const double* dot_with, double* dot_out, void* dot_ws, void* stream) {
   return mgp::lap_spmv_tile<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, hmax, shift, post, xmap, ymap, x, ldx, y, ldy, n,
-                                    (cudaStream_t)stream);
+                                   dot_with, dot_out, dot_ws, (cudaStream_t)stream);
 }
 
 int mgp_lap_spmm_tile64_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,

@@ -533,8 +533,8 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
         # a pass wider than estimated (unaligned leading dimension): the CSR kernel handles it
     if peer_x is not None:
         raise RuntimeError("lap_spmm: peer-memory halo reads requested but the tile structure does not fit this call")
-    # one column, no fused dot / pre scaling: the streamed single-column kernel on the tile streams (lap_spmv_tile.cu)
-    if c == 1 and pre is None and dot_out is None and SPMM_KERNEL in ("auto", "spmv") and slack_ok:
+    # one column, no pre scaling: the streamed single-column kernel on the tile streams (lap_spmv_tile.cu)
+    if c == 1 and pre is None and SPMM_KERNEL in ("auto", "spmv") and slack_ok:
         t = st.build_tiles()
         if t is not None and "wptr" in t:
             if out is None:
@@ -543,7 +543,8 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
             rc = _lib.call_rc("mgp_lap_spmv_tile_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag), ptr(t["hptr"]),
                               ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
                               ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
-                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), stream())
+                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), ptr(dot_with), ptr(dot_out),
+                              ptr(ws), stream())
             if rc == 0:
                 _note_kernel("lap_spmv_tile_kernel")
                 return out

@@ -178,6 +178,21 @@ def test_single_column_tile_spmv_matches_dense(problem, dtype):
             graph.SPMM_KERNEL = "auto"
         assert rel_err(Y, ref) < tol
         assert rel_err(st.to_internal(Ye), ref) < tol
+        # fused dot epilogue: dot_with = x itself, and another vector with the same row stride
+        graph.SPMM_KERNEL = "spmv"
+        try:
+            dot = torch.zeros(1, dtype=dtype, device=DEV)
+            Yd = graph.lap_spmm(st, a, diag, X, shift=shift, post=post, dot_with=X, dot_out=dot)
+            Z = torch.randn(n, 8, dtype=dtype, device=DEV, generator=gen)[:, 2:3] if X.stride(0) == 8 else \
+                torch.randn(n, 1, dtype=dtype, device=DEV, generator=gen)
+            dot2 = torch.zeros(1, dtype=dtype, device=DEV)
+            graph.lap_spmm(st, a, diag, X, shift=shift, post=post, dot_with=Z, dot_out=dot2)
+            assert graph.LAST_SPMM_KERNEL == "lap_spmv_tile_kernel"
+        finally:
+            graph.SPMM_KERNEL = "auto"
+        assert torch.equal(Yd, Y)
+        assert rel_err(dot, (X.double() * ref).sum(0)) < tol * 10
+        assert (dot2.double() - (Z.double() * ref).sum(0)).abs().max() < tol * 10 * Z.double().norm() * ref.norm()
     # the operator-level matvec (auto dispatch) uses it for one column
     v = torch.randn(n, dtype=dtype, device=DEV, generator=gen)
     out = lap._matmul(v)
