@@ -159,7 +159,7 @@ def run_ours(args):
     rank, world, local = dist_info()
     if world > 1:
         from manifold_gp_b200 import distributed
-        return distributed.bench_main(args, CFG)
+        return distributed.bench_main(args, CFG, clock_sampler=ClockSampler)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     n, k, c = args.n, CFG["k"], CFG["rhs"]

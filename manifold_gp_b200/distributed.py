@@ -445,7 +445,7 @@ def sharded_knn(x: torch.Tensor, k: int, part_queries: RowPartition, rank: int, 
 # ---------------------------------------------------------------------------------------------------------------------------
 # bench entry (called by bench.py under torchrun)
 # ---------------------------------------------------------------------------------------------------------------------------
-def bench_main(args, CFG):
+def bench_main(args, CFG, clock_sampler=None):
     import manifold_gp_b200 as mgp
     from manifold_gp_b200 import _lib, graph
     from manifold_gp_b200.utils import synthetic
@@ -501,11 +501,25 @@ def bench_main(args, CFG):
     torch.cuda.synchronize(); dist.barrier()
     _lib.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk = None
+    if clock_sampler is not None and rank == 0:            # SM clocks / throttle reasons during the timed region (rank 0's GPU)
+        try:
+            clk = clock_sampler(local)
+            clk.__enter__()
+        except Exception:
+            clk = None
     ev0.record()
     for _ in range(args.steps):
         xs, info = solve()
     ev1.record()
     torch.cuda.synchronize(); dist.barrier()
+    clocks = None
+    if clk is not None:
+        try:
+            clk.__exit__(None, None, None)
+            clocks = clk.summary()
+        except Exception:
+            clocks = None
     ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = _lib.launch_count()
@@ -537,6 +551,7 @@ def bench_main(args, CFG):
                "e2e": {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": int(Bh.numel() * 4 * world),
                        "d2h_bytes_per_step": int(Xh.numel() * 4 * world)},
                "gpu_launches": int(launches),
+               "clocks": clocks,
                "transport": transport,
                "collectives_per_iteration": (
                    ({"launches": CFG["nu"] + 2, "barrier": "inside the SpMM launches (flags over NVLink, waited on at the first remote halo row)",
