@@ -60,6 +60,56 @@ def attach_permutation(idx: torch.Tensor, perm: torch.Tensor) -> None:
         pass
 
 
+# ---- quad-row union lists (groundwork for the next SpMM generation) ------------------------------
+def quad_union_lists(rowptr: torch.Tensor, col: torch.Tensor, n: int, R: int = 128, row_pos: torch.Tensor = None):
+    """Group the rows of every ``R``-row tile into quads and merge the column lists of each quad.
+
+    Morton-adjacent rows of a kNN graph share most of their neighbours (measured: the union of a quad's column sets is 0.44
+    of the sum of their sizes, ``profiles/pair_stats.py``), so a kernel that walks UNION columns loads an X row once for four
+    matrix rows.  This is the layout-independent half of that format (pure index plumbing, any device; not used by the
+    current kernels):
+
+      qrows [Q, 4]  int64   rows of each quad (-1 = padding in the last tile), Q = ntiles * R / 4
+      qptr  [Q + 1] int64   offsets into the union lists
+      qcol  [U]     int64   union columns of each quad, ascending
+      qsrc  [U, 4]  int64   CSR entry that holds A[qrows[q, s], qcol[u]], or -1 if that row does not have the column
+                            (per-bandwidth values are then ``qval = where(qsrc >= 0, a[qsrc], 0)``)
+
+    ``row_pos`` [n]: position of each row inside its tile used to form the quads (rows at positions 4j .. 4j+3 share a
+    quad); default = the row's own order.  Pass a spatially coherent order (e.g. the Morton position before the in-tile
+    degree sort) to maximise the sharing."""
+    dev = rowptr.device
+    rp = rowptr.to(torch.int64)
+    nnz = int(rp[-1])
+    ntiles = (n + R - 1) // R
+    rows = torch.arange(n, device=dev, dtype=torch.int64)
+    if row_pos is None:
+        pos = rows % R
+    else:
+        # rank of the row inside its tile under the given order
+        tile = rows // R
+        order = torch.argsort(tile * (int(row_pos.max()) + 1) + row_pos.to(torch.int64), stable=True)
+        pos = torch.empty(n, dtype=torch.int64, device=dev)
+        pos[order] = rows - (rows // R) * R                     # consecutive ranks inside each tile (tiles are contiguous)
+    quad_of_row = (rows // R) * (R // 4) + pos // 4
+    slot_of_row = pos % 4
+    Q = ntiles * (R // 4)
+    qrows = torch.full((Q, 4), -1, dtype=torch.int64, device=dev)
+    qrows[quad_of_row, slot_of_row] = rows
+    erow = torch.repeat_interleave(rows, rp[1:] - rp[:-1])
+    ecol = col.to(torch.int64)[:nnz]
+    key = quad_of_row[erow] * n + ecol
+    ukey, inv = torch.unique(key, sorted=True, return_inverse=True)
+    U = int(ukey.numel())
+    qcol = ukey % n
+    counts = torch.bincount(ukey // n, minlength=Q)
+    qptr = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=qptr[1:])
+    qsrc = torch.full((U, 4), -1, dtype=torch.int64, device=dev)
+    qsrc[inv, slot_of_row[erow]] = torch.arange(nnz, device=dev, dtype=torch.int64)
+    return {"qrows": qrows, "qptr": qptr, "qcol": qcol, "qsrc": qsrc, "union_per_nonzero": U / max(nnz, 1)}
+
+
 # ---- graph persistence (SURVEY.md 8(f-3)) ----------------------------------------------------------------------------------
 # The kNN graph is the most expensive setup step (O(N^2 d)) and is hyper-parameter independent, but the reference rebuilds
 # it in every run (riemann_kernel.py:40-42 builds it in __init__, nothing is written to disk).  One file holds what a
