@@ -1,11 +1,22 @@
-"""``ScaleWrapperOperator`` -- manifold_gp/operators/scale_wrapper_operator.py: Q*s (default) or Q/s (inverse_scale)."""
+"""``ScaleWrapperOperator`` -- manifold_gp/operators/scale_wrapper_operator.py: ``Q * s`` (default) or ``Q / s``
+(``inverse_scale``), where Q is the wrapped operator and s the kernel's output scale (``RiemannGP.precision``).
+
+Besides the reference's ``_matmul`` (one inner product + one scaling), the wrapper can run on the solver drivers' caller-owned
+buffers (``_mgp_matvec``: no temporaries, CUDA-graph capturable, fused dot product), which is what lets the training loss's
+mBCG on ``Noise(Scale(Precision))`` use the same fused iteration as a bare precision operator.  That path is switched on with
+``MGP_FUSED_WRAPPERS=1`` (off by default until it has been validated on the GPU; the generic path is the tested one)."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 from torch import Tensor
 
 from .._compat.linear_operator import LinearOperator
+
+
+def fused_wrappers_enabled() -> bool:
+    return os.environ.get("MGP_FUSED_WRAPPERS", "0") == "1"
 
 
 class ScaleWrapperOperator(LinearOperator):
@@ -26,3 +37,29 @@ class ScaleWrapperOperator(LinearOperator):
         # the reference passes the bound method instead of calling it (:34, Appendix C.4); every operator on this
         # path is symmetric, so the transpose is the operator built on the transposed inner operator
         return ScaleWrapperOperator(self.operator._transpose_nonbatch(), self.scale, self.inverse_scale)
+
+    # ---- solver-driver interface (see PrecisionMaternOperator._mgp_matvec) ---------------------------------------------------
+    def _native(self) -> bool:
+        inner = self.operator
+        return fused_wrappers_enabled() and hasattr(inner, "_mgp_matvec") and getattr(inner, "_native", lambda: True)()
+
+    def _mgp_structure(self):
+        return self.operator._mgp_structure()
+
+    def _mgp_cache_key(self, dtype):
+        return ("scale", bool(self.inverse_scale), self.scale.data_ptr(), self.scale._version) + tuple(self.operator._mgp_cache_key(dtype))
+
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None):
+        """out[:, :ncols] <- s * (Q x) (or / s) in place on the caller's buffers; the fused dot product is scaled alike."""
+        self.operator._mgp_matvec(x, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols)
+        s = self.scale.detach().to(out.dtype)
+        view = out if ncols is None else out[:, :ncols]
+        if self.inverse_scale:
+            view.div_(s)
+            if dot_out is not None:
+                dot_out.div_(s)
+        else:
+            view.mul_(s)
+            if dot_out is not None:
+                dot_out.mul_(s)
+        return out

@@ -1,4 +1,15 @@
-"""``test_model`` -- manifold_gp/utils/test_model.py:10-30: RMSE and NLL of the posterior on held-out points."""
+"""``test_model`` -- manifold_gp/utils/test_model.py:10-30.
+
+Scores a trained model on held-out points: the posterior (geometric kernel, optionally blended with a Euclidean base model)
+is evaluated once, then
+
+    rmse = sqrt(mean((y - mean)^2))
+    nll  = 1/2 [ e^T K^-1 e + log|K| + m log 2 pi ] / m        with e = y - mean, K the posterior covariance of the m points
+
+where ``inv_quad_logdet`` of the posterior covariance takes the Cholesky branch for m <= ``max_cholesky`` and the CUDA
+mBCG + stochastic-Lanczos branch beyond it.  The settings contexts are the ones the reference enters (fast_pred_var,
+max_cholesky_size, cg_tolerance, max_cg_iterations), from ``manifold_gp_b200.settings`` (gpytorch's when installed).
+"""
 from __future__ import annotations
 
 import math
