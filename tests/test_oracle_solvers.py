@@ -107,3 +107,25 @@ def test_lanczos_vs_reference_dense_eigh(golden_k10):
     assert evals.shape[0] == sub
     assert torch.allclose(evals[1:], wa[1:], rtol=1e-6, atol=1e-8)
     assert float((A @ evecs[:, 1:] - evecs[:, 1:] * evals[1:]).abs().max()) < 1e-6
+
+
+def test_zero_padded_block_with_rescaled_tolerance_is_the_same_solve():
+    """The identity manifold_gp_b200.solvers.linear_cg relies on when it pads an 11-column block to 16 columns so that the
+    128-bit SpMM kernels apply: zero right-hand sides have residual exactly 0, so the published mean-over-columns stopping
+    rule on the padded block with tolerance * c / c_pad makes the same decisions as on the original block."""
+    torch.manual_seed(1)
+    n, c, cpad = 80, 11, 16
+    A = torch.randn(n, n, dtype=torch.float64)
+    A = A @ A.T + n * torch.eye(n, dtype=torch.float64)
+    b = torch.randn(n, c, dtype=torch.float64)
+    bp = torch.zeros(n, cpad, dtype=torch.float64)
+    bp[:, :c] = b
+    mm = lambda v: A @ v
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for tol in (1e-2, 1e-5, 1e-8):
+            x, info = oracle.linear_cg(mm, b, tolerance=tol, max_iter=200, return_info=True)
+            xp, infop = oracle.linear_cg(mm, bp, tolerance=tol * c / cpad, max_iter=200, return_info=True)
+            assert info["iterations"] == infop["iterations"], tol
+            assert torch.equal(xp[:, c:], torch.zeros(n, cpad - c, dtype=torch.float64))
+            assert rel_err(xp[:, :c], x) < 1e-13
