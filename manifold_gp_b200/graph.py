@@ -110,6 +110,49 @@ def quad_union_lists(rowptr: torch.Tensor, col: torch.Tensor, n: int, R: int = 1
     return {"qrows": qrows, "qptr": qptr, "qcol": qcol, "qsrc": qsrc, "union_per_nonzero": U / max(nnz, 1)}
 
 
+def quad_streams(q: dict, lcol_of_entry: torch.Tensor, n: int, R: int = 128, warps: int = 16):
+    """Lane-consumption-order streams of the quad-row SpMM from ``quad_union_lists`` output.
+
+    Kernel shape this layout is for: ``warps`` consumer warps per tile, each owning R / 4 / warps quads (2 at R = 128, 16
+    warps); a quad is served by 16 / (quads per warp) ... concretely, at 2 quads per warp, by 16 lanes = 4 lane groups x 4
+    lanes: lane group g of the warp (g = lane >> 2, 0..7) works for quad 2w + (g >> 2) and takes every 4th union column of
+    it (sub-list g & 3); the 4 lanes of a group own the four 16-byte chunks of the 64-byte X row / output row.  Per step a
+    group needs ONE tile-local column index and ONE 4-wide value slot (the values of the quad's 4 rows for that column):
+
+      position(w, t, g) = qwptr[tile * warps + w] + 8 t + g          (steps t = 0 .. steps_w - 1, padded per warp)
+      qidx [P]     int32 (stored as uint16 by the kernel)  tile-local column of the union column, or 0 for padding
+      qent [P, 4]  int64  CSR entry of (row slot, that column) or -1  ->  values = where(qent >= 0, a[qent], 0)
+      qwptr [ntiles * warps + 1]  int64
+
+    ``lcol_of_entry`` [nnz]: the tile-local column (own rows 0 .. R-1, halo R ..) of every CSR entry, as the tile structure
+    already stores it.  Pure index plumbing (any device)."""
+    dev = q["qptr"].device
+    Q = q["qptr"].numel() - 1
+    qpw = (R // 4) // warps                       # quads per warp
+    assert qpw * warps * 4 == R and 8 % qpw == 0
+    gpq = 8 // qpw                                # lane groups (sub-lists) per quad
+    ulen = q["qptr"][1:] - q["qptr"][:-1]         # union columns per quad
+    steps_q = (ulen + gpq - 1) // gpq             # steps a quad needs
+    nw = Q // qpw
+    steps_w = steps_q.view(nw, qpw).max(dim=1).values
+    qwptr = torch.zeros(nw + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(steps_w * 8, 0, out=qwptr[1:])
+    P = int(qwptr[-1])
+    qidx = torch.zeros(P, dtype=torch.int32, device=dev)
+    qent = torch.full((P, 4), -1, dtype=torch.int64, device=dev)
+    # every union column u of quad k sits at sub-list (u_local % gpq), step (u_local // gpq)
+    U = q["qcol"].numel()
+    quad_of_u = torch.repeat_interleave(torch.arange(Q, device=dev, dtype=torch.int64), ulen)
+    u_local = torch.arange(U, device=dev, dtype=torch.int64) - q["qptr"][quad_of_u]
+    w_of_u = quad_of_u // qpw
+    g_of_u = (quad_of_u % qpw) * gpq + u_local % gpq
+    pos = qwptr[w_of_u] + 8 * (u_local // gpq) + g_of_u
+    qent[pos] = q["qsrc"]
+    first = q["qsrc"].clamp_min(-1).max(dim=1).values           # any valid entry of the union column carries its local column id
+    qidx[pos] = lcol_of_entry.to(torch.int64)[first].to(torch.int32)
+    return {"qwptr": qwptr, "qidx": qidx, "qent": qent, "entries": P, "padding": 1.0 - U / max(P, 1)}
+
+
 # ---- graph persistence (SURVEY.md 8(f-3)) ----------------------------------------------------------------------------------
 # The kNN graph is the most expensive setup step (O(N^2 d)) and is hyper-parameter independent, but the reference rebuilds
 # it in every run (riemann_kernel.py:40-42 builds it in __init__, nothing is written to disk).  One file holds what a
