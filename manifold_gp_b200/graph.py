@@ -319,6 +319,7 @@ class GraphStructure:
             raise ValueError("edge index must be [2, M]")
         idx = idx.to(torch.int64)
         self.perm = self.inv = None
+        self.morton_pos = None
         if perm is not None:
             perm = perm.to(device=idx.device, dtype=torch.int64)
             # balance the tiled kernel's sub-warps: inside every tile of TILE_ROWS consecutive rows, order the rows by
@@ -326,7 +327,9 @@ class GraphStructure:
             deg = torch.bincount(idx.reshape(-1), minlength=int(n))
             tile_id = torch.arange(perm.numel(), device=idx.device, dtype=torch.int64) // self.TILE_ROWS
             key = (tile_id << 20) | ((1 << 20) - 1 - deg[perm].clamp_max((1 << 20) - 1))
-            perm = perm[torch.argsort(key, stable=True)]
+            order = torch.argsort(key, stable=True)
+            perm = perm[order]
+            self.morton_pos = order                     # position of each final row in the spatial order (quad forming)
             self.perm = perm.contiguous()
             self.inv = torch.empty_like(self.perm)
             self.inv[self.perm] = torch.arange(self.perm.numel(), device=idx.device)
@@ -433,6 +436,36 @@ class GraphStructure:
         del cache[:-4]
         return out
 
+    # -- experimental quad-row streams (lap_spmm_quad.cu; SPMM_KERNEL = "quad" only) -------------------------------------
+    def quad_tiles(self):
+        q = self.__dict__.get("_quad_tiles")
+        if q is None:
+            t = self.build_tiles()
+            if t is None or "lcol" not in t or t["rows"] != 128:
+                return None
+            ul = quad_union_lists(self.rowptr, self.col, self.n, t["rows"], row_pos=self.morton_pos)
+            qs = quad_streams(ul, t["lcol"][:self.nnz], self.n, t["rows"], 16)
+            if int(qs["qwptr"][-1]) >= 2 ** 31:
+                return None
+            q = {"qwptr": qs["qwptr"].to(torch.int32).contiguous(), "qidx": qs["qidx"].to(torch.int16).contiguous(),
+                 "qent": qs["qent"], "qrows": ul["qrows"].to(torch.int32).contiguous(), "entries": qs["entries"],
+                 "union_per_nonzero": ul["union_per_nonzero"], "padding": qs["padding"]}
+            self._quad_tiles = q
+        return q
+
+    def quad_values(self, a: torch.Tensor) -> torch.Tensor:
+        """4-wide value slots of the quad streams for one value array (cached like the other layouts)."""
+        cache = self.__dict__.setdefault("_quad_value_cache", [])
+        for ref, ver, out in cache:
+            if ref.data_ptr() == a.data_ptr() and ver == a._version and ref.dtype == a.dtype:
+                return out
+        q = self.quad_tiles()
+        ent = q["qent"]
+        out = torch.where(ent >= 0, a.detach()[ent.clamp_min(0)], torch.zeros((), dtype=a.dtype, device=a.device)).contiguous()
+        cache.append((a.detach(), a._version, out))
+        del cache[:-2]
+        return out
+
     def padded_values(self, a: torch.Tensor) -> torch.Tensor:
         return self._value_layout(a, "pad")
 
@@ -523,7 +556,7 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
 TILE64_MODES = ("tile64",)   # add "auto" to make the one-block-per-tile kernel the default for 64-byte-row passes
 LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call launched (bench.py reports it)
-SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv"  (tests force each; "auto": wi, else pipe, else tiled, else csr)
+SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv" | "tile64" | "quad" (experimental)  (tests force each; "auto": wi, else pipe, else tiled, else csr)
 
 
 def _note_kernel(name):
@@ -555,8 +588,8 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
     # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
     # kernel (X served from L1/L2) is faster
-    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64"))
-    if SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64") and not use_tiled:
+    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad"))
+    if SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad") and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
         t = st.tiles
@@ -564,6 +597,19 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
         if peer_x is not None and not (pre is None and "wptr" in t):
             raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
+        if SPMM_KERNEL == "quad":
+            q = st.quad_tiles() if (pre is None and peer_x is None) else None
+            if q is None:
+                raise RuntimeError("lap_spmm: quad kernel requested but this call / structure does not qualify")
+            rc = _lib.call_rc("mgp_lap_spmm_quad_" + sfx, ptr(q["qwptr"]), ptr(q["qidx"]), ptr(st.quad_values(a)), ptr(q["qrows"]),
+                              ptr(diag), ptr(t["hptr"]), ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["hmax"]), ptr(shift_t),
+                              ptr(post), ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
+                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with),
+                              ptr(dot_out), ptr(ws), stream())
+            if rc != 0:
+                raise RuntimeError(f"mgp_lap_spmm_quad_{sfx} failed ({rc}): {_lib.last_error()}")
+            _note_kernel("lap_spmm_quad_kernel")
+            return out
         if pre is None and "wptr" in t and SPMM_KERNEL in TILE64_MODES and peer_x is None:
             aw = st.wi_values(a)
             rc = _lib.call_rc("mgp_lap_spmm_tile64_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag), ptr(t["hptr"]),

@@ -198,3 +198,40 @@ def test_single_column_tile_spmv_matches_dense(problem, dtype):
     out = lap._matmul(v)
     assert graph.LAST_SPMM_KERNEL == "lap_spmv_tile_kernel"
     assert rel_err(out, (lap.to_dense().double() @ v.double())) < tol
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MGP_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental quad-row kernel: written without GPU access at the end of round 1, not yet validated "
+                           "(set MGP_TEST_EXPERIMENTAL=1 to run)")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_experimental_quad_row_kernel_matches_dense(problem, dtype):
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph
+    x, idx, val = problem
+    n = 6000
+    xs = x[:n].contiguous()
+    idx6, val6 = mgp.NearestNeighbors(xs).graph(12)
+    lap = mgp.GraphLaplacianOperator(val6.to(dtype), idx6, n, torch.tensor([[0.15]], dtype=dtype, device=DEV), "symmetric")
+    st = lap.structure
+    _, deg, diag, a = lap._values()
+    D, A = _dense(st, a, diag, n)
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    post = torch.rand(n, dtype=dtype, device=DEV, generator=gen) + 0.5
+    shift = torch.tensor([1.9], dtype=dtype, device=DEV)
+    q = st.quad_tiles()
+    assert q is not None and q["union_per_nonzero"] < 0.7
+    for c in ((16, 32) if dtype == torch.float32 else (8, 16)):
+        X = torch.randn(n, c, dtype=dtype, device=DEV, generator=gen)
+        ref = ((D + float(shift) * torch.eye(n, dtype=torch.float64, device=DEV)) @ X.double() - A @ X.double()) * post.double().unsqueeze(1)
+        graph.SPMM_KERNEL = "quad"
+        try:
+            dot = torch.zeros(c, dtype=dtype, device=DEV)
+            Y = graph.lap_spmm(st, a, diag, X, shift=shift, post=post, dot_with=X, dot_out=dot)
+            Ye = graph.lap_spmm(st, a, diag, st.to_external(X), shift=shift, post=post, x_external=True, y_external=True)
+            assert graph.LAST_SPMM_KERNEL == "lap_spmm_quad_kernel"
+        finally:
+            graph.SPMM_KERNEL = "auto"
+        assert rel_err(Y, ref) < tol
+        assert rel_err(st.to_internal(Ye), ref) < tol
+        assert rel_err(dot, (X.double() * ref).sum(0)) < tol * 10
