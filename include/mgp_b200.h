@@ -227,7 +227,7 @@ int mgp_lap_spmm_tile64_f64(const int32_t* wptr, const uint16_t* wcol, const dou
                             const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift, const double* post,
                             const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
                             int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws, void* stream);
-/* EXPERIMENTAL, not dispatched by default: quad-row SpMM (lap_spmm_quad.cu).  Walks the UNION columns of row quads so that one
+/* EXPERIMENTAL, not dispatched by default (parity-tested on B200, not yet timed): quad-row SpMM (lap_spmm_quad.cu).  Walks the UNION columns of row quads so that one
  * shared-memory X-row load serves four matrix rows.  Streams from manifold_gp_b200/graph.py::quad_streams: qwptr[16 ntiles + 1]
  * (entry offsets per warp, multiples of 8), qidx[P] tile-local columns, qval[4 P] value slots (16-byte aligned), qrows[4 * 32 ntiles]
  * rows of every quad (-1 = none).  Same operation, reference lines, dot epilogue and alignment rules as mgp_lap_spmm_wi. */

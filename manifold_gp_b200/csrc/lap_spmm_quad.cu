@@ -1,4 +1,6 @@
-// EXPERIMENTAL (not dispatched by default, not yet run on a GPU): quad-row SpMM for 64-byte rows of X.
+// EXPERIMENTAL (not dispatched by default): quad-row SpMM for 64-byte rows of X.  Parity-tested on B200 against the dense
+// operator (tests/test_gpu_spmm_kernels.py::test_experimental_quad_row_kernel_matches_dense, fp32 1e-5 / fp64 1e-12, fused dot,
+// caller-order translation); NOT yet timed -- the last GPU seconds of round 1 went into that test.
 //
 //   Y = post .* ( (diag + shift) .* X  -  A X )        16 fp32 / 8 fp64 columns per pass
 //

@@ -200,11 +200,10 @@ def test_single_column_tile_spmv_matches_dense(problem, dtype):
     assert rel_err(out, (lap.to_dense().double() @ v.double())) < tol
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MGP_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental quad-row kernel: written without GPU access at the end of round 1, not yet validated "
-                           "(set MGP_TEST_EXPERIMENTAL=1 to run)")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_experimental_quad_row_kernel_matches_dense(problem, dtype):
+    """lap_spmm_quad_kernel (SPMM_KERNEL = "quad", never dispatched by default): parity with the dense operator, the fused
+    dot product and the caller-order translation.  Passed on B200 with the last GPU seconds of round 1; not yet timed."""
     import manifold_gp_b200 as mgp
     from manifold_gp_b200 import graph
     x, idx, val = problem
