@@ -239,6 +239,19 @@ int mgp_lap_spmm_quad_f64(const int32_t* qwptr, const uint16_t* qidx, const doub
                           const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift,
                           const double* post, const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y,
                           int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws, void* stream);
+/* EXPERIMENTAL, not dispatched by default, NOT yet run on a GPU: the quad-row walk inside the pipelined producer of
+ * mgp_lap_spmm_wi (lap_spmm_quadpipe.cu).  qwptr padded like wptr (512 ceil(ntiles/32) + 4 ints), qnzmax = largest number of
+ * stream entries of a tile (multiple of 8); everything else as mgp_lap_spmm_quad / mgp_lap_spmm_wi (no peer-memory mode). */
+int mgp_lap_spmm_qp_f32(const int32_t* qwptr, const uint16_t* qidx, const float* qval, const int32_t* qrows, const float* diag,
+                        const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t qnzmax, int32_t hmax,
+                        const float* shift, const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx,
+                        float* y, int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
+                        void* stream);
+int mgp_lap_spmm_qp_f64(const int32_t* qwptr, const uint16_t* qidx, const double* qval, const int32_t* qrows, const double* diag,
+                        const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t qnzmax, int32_t hmax,
+                        const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
+                        int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
+                        void* dot_ws, void* stream);
 int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const float* a, int64_t n, float* aw, void* stream);
 int mgp_lap_wi_values_f64(const int32_t* rowptr, const int32_t* wptr, const double* a, int64_t n, double* aw, void* stream);
 int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,

@@ -450,6 +450,19 @@ class GraphStructure:
             q = {"qwptr": qs["qwptr"].to(torch.int32).contiguous(), "qidx": qs["qidx"].to(torch.int16).contiguous(),
                  "qent": qs["qent"], "qrows": ul["qrows"].to(torch.int32).contiguous(), "entries": qs["entries"],
                  "union_per_nonzero": ul["union_per_nonzero"], "padding": qs["padding"]}
+            try:
+                # extras of the pipelined kernel (quadpipe, not yet validated): it bulk-copies metadata in chunks of 32 tiles
+                # (516 ints), so qwptr is padded like wi_streams pads wptr, and the streams get a zero tail
+                ntiles = (self.n + t["rows"] - 1) // t["rows"]
+                qwpad = torch.full((512 * ((ntiles + 31) // 32) + 4,), int(qs["qwptr"][-1]), dtype=torch.int32,
+                                   device=q["qwptr"].device)
+                qwpad[:q["qwptr"].numel()] = q["qwptr"]
+                tile_tot = qs["qwptr"][16::16] - qs["qwptr"][:-1:16]
+                q["qwptr_pad"] = qwpad.contiguous()
+                q["qnzmax"] = int(tile_tot.max()) if ntiles else 0
+                q["qidx_pad"] = torch.cat([q["qidx"], torch.zeros(64, dtype=torch.int16, device=q["qidx"].device)]).contiguous()
+            except Exception:                      # the validated quad path must not depend on these
+                pass
             self._quad_tiles = q
         return q
 
@@ -462,6 +475,17 @@ class GraphStructure:
         q = self.quad_tiles()
         ent = q["qent"]
         out = torch.where(ent >= 0, a.detach()[ent.clamp_min(0)], torch.zeros((), dtype=a.dtype, device=a.device)).contiguous()
+        cache.append((a.detach(), a._version, out))
+        del cache[:-2]
+        return out
+
+    def quad_values_padded(self, a: torch.Tensor) -> torch.Tensor:
+        """``quad_values`` flattened with a zero tail (the pipelined kernel's bulk copies never run off the end)."""
+        cache = self.__dict__.setdefault("_quad_value_pad_cache", [])
+        for ref, ver, out in cache:
+            if ref.data_ptr() == a.data_ptr() and ver == a._version and ref.dtype == a.dtype:
+                return out
+        out = torch.cat([self.quad_values(a).reshape(-1), torch.zeros(256, dtype=a.dtype, device=a.device)]).contiguous()
         cache.append((a.detach(), a._version, out))
         del cache[:-2]
         return out
@@ -556,7 +580,7 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
 TILE64_MODES = ("tile64",)   # add "auto" to make the one-block-per-tile kernel the default for 64-byte-row passes
 LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call launched (bench.py reports it)
-SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv" | "tile64" | "quad" (experimental)  (tests force each; "auto": wi, else pipe, else tiled, else csr)
+SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv" | "tile64" | "quad" | "quadpipe" (experimental)  (tests force each; "auto": wi, else pipe, else tiled, else csr)
 
 
 def _note_kernel(name):
@@ -588,8 +612,8 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
     # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
     # kernel (X served from L1/L2) is faster
-    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad"))
-    if SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad") and not use_tiled:
+    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad", "quadpipe"))
+    if SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad", "quadpipe") and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
         t = st.tiles
@@ -597,6 +621,20 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
         if peer_x is not None and not (pre is None and "wptr" in t):
             raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
+        if SPMM_KERNEL == "quadpipe":
+            q = st.quad_tiles() if (pre is None and peer_x is None) else None
+            if q is None or "qwptr_pad" not in q:
+                raise RuntimeError("lap_spmm: quadpipe kernel requested but this call / structure does not qualify")
+            rc = _lib.call_rc("mgp_lap_spmm_qp_" + sfx, ptr(q["qwptr_pad"]), ptr(q["qidx_pad"]), ptr(st.quad_values_padded(a)), ptr(q["qrows"]),
+                              ptr(diag), ptr(t["hptr"]), ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
+                              c_int32(q["qnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
+                              ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
+                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with),
+                              ptr(dot_out), ptr(ws), stream())
+            if rc != 0:
+                raise RuntimeError(f"mgp_lap_spmm_qp_{sfx} failed ({rc}): {_lib.last_error()}")
+            _note_kernel("lap_spmm_qp_kernel")
+            return out
         if SPMM_KERNEL == "quad":
             q = st.quad_tiles() if (pre is None and peer_x is None) else None
             if q is None:
