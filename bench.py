@@ -285,7 +285,8 @@ def run_ours(args):
                     "achieved_gbs": round(ach1, 1), "frac": round(ach1 / hbm_peak, 4),
                     "traffic": 231_084_032,   # ncu dram read + write per launch, profiles/r01_ncu_spmv_tile_c1.txt
                     "algorithmic_bytes_per_launch": b1},
-        "knn_build_s": round(t_search, 4), "graph_symmetrize_s": round(max(t_graph - t_search, 0.0), 4),
+        "knn_build_s": round(t_search, 4), "knn_build_candidates_per_s": round(float(n) * float(n) / max(t_search, 1e-9), 1),
+        "graph_symmetrize_s": round(max(t_graph - t_search, 0.0), 4),
         "structure_build_s": round(t_struct, 4), "laplacian_values_ms": round(t_values_ms, 3),
         "knn_tensor": knn_tensor,
         "clocks": clk.summary(),
