@@ -267,6 +267,43 @@ int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double*
                         void* dot_ws, const void* peer_x, int32_t npeers, int32_t rank, const void* sync_flags,
                         const double* sync_epoch, void* stream);
 
+/* Extended form of mgp_lap_spmm_wi for solver loops (CG past convergence, fused cross-GPU sync points).  All members optional
+ * (NULL / 0 = off); the flag and reduction tables are DEVICE arrays of npeers pointers to the ranks' peer-mapped buffers:
+ *   done_flag      device scalar (T): the launch is a no-op when it is non-zero (every CG kernel is, once converged);
+ *   wait_flags     producers wait -- lazily, at the first halo row that lives on another rank -- until
+ *                  wait_flags[rank][src] >= epoch for every src; nothing is published at kernel start;
+ *   publish_flags  after ALL rows of Y are written (last block to finish, last column pass): publish_flags[dst][rank] = epoch
+ *                  ("my Y is complete") -- the consumer of Y on another rank waits on it with wait_flags;
+ *   ticket         device uint32 counter for that completion ticket (zeroed once; resets itself);
+ *   red_ptrs/red_flags/ship_extra/ship_ncols  with dot_out: the block that completes the local dot products ships
+ *                  dot_out[0..ship_ncols) (kind 0) and ship_extra[0..ship_ncols) (kind 1, may be NULL) to
+ *                  red_ptrs[dst][kind][epoch & 1][rank][128] of every rank, then red_flags[dst][rank] = epoch
+ *                  (first half of a fused all-reduce; mgp_cg_peer_cgstep is the second half).
+ * epoch = (unsigned)*sync_epoch + 1 (the CG iteration counter in the solver state).  No reference counterpart. */
+typedef struct mgp_wi_ext {
+  const void* done_flag;
+  const void* wait_flags;
+  const void* publish_flags;
+  void* ticket;
+  const void* red_ptrs;
+  const void* red_flags;
+  const void* ship_extra;
+  int32_t ship_ncols;
+  int32_t reserved;
+} mgp_wi_ext;
+int mgp_lap_spmm_wi_ex_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
+                           const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
+                           const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
+                           int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
+                           const void* peer_x, int32_t npeers, int32_t rank, const float* sync_epoch, const mgp_wi_ext* ext,
+                           void* stream);
+int mgp_lap_spmm_wi_ex_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag, const int32_t* hptr,
+                           const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const double* shift,
+                           const double* post, const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y,
+                           int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws,
+                           const void* peer_x, int32_t npeers, int32_t rank, const double* sync_epoch, const mgp_wi_ext* ext,
+                           void* stream);
+
 /* ----------------------------------------------------------------------------------------------------------
  * Backward of the SpMM w.r.t. the matrix entries (what autograd through torch_sparse.spmm computes for `value`,
  * graph_laplacian_operator.py:117-119, reached via linear_operator's _bilinear_derivative):
@@ -377,6 +414,22 @@ int mgp_cg_peer_pxupdate_f32(float* x, float* p, const float* r, int64_t ld, int
                              int32_t max_hist, void* ws, void* red_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream);
 int mgp_cg_peer_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, double* state, double* hist,
                              int32_t max_hist, void* ws, void* red_ptrs, void* flag3_ptrs, int32_t rank, int32_t world, void* stream);
+/* Single-reduction (Chronopoulos-Gear) iteration of the peer-memory path: an iteration is [mgp_lap_spmm_wi_ex x nu with r as the
+ * source, the last launch shipping this rank's (r.w, |r|^2) partials] + this ONE vector kernel, which waits for all ranks'
+ * partials (dflag), forms beta and alpha, applies p = r + beta p, s = w + beta s, x += alpha p, r -= alpha s, stores the local
+ * |r_new|^2 in gamma_loc[ncols], advances the scalar state / history like mgp_cg_rupdate and publishes "r complete"
+ * (iteration + 2) in rflag for the peers' next SpMM.  Same iterates, masks and stopping rules as linear_cg; convergence is noticed
+ * one matvec later (the tested residual norm is the one entering the iteration) and no update is applied then.  s must be
+ * zeroed, rflag published as 1 (mgp_peer_publish) and gamma_loc filled with the local |r_0|^2 before the first iteration.
+ * red_ptrs[r] -> T[2][2][world][128]; flags zeroed + barrier before each solve.  ld as mgp_cg_peer_rupdate. */
+int mgp_cg_peer_cgstep_f32(float* x, float* r, float* p, float* s, const float* w, int64_t ld, int64_t n, int32_t ncols, float* state,
+                           float* hist, int32_t max_hist, void* ws, float* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
+                           int32_t rank, int32_t world, void* stream);
+int mgp_cg_peer_cgstep_f64(double* x, double* r, double* p, double* s, const double* w, int64_t ld, int64_t n, int32_t ncols, double* state,
+                           double* hist, int32_t max_hist, void* ws, double* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
+                           int32_t rank, int32_t world, void* stream);
+/* flags[dst][rank] = value on every rank, after everything enqueued before on this stream (no waiting). */
+int mgp_peer_publish(void* flag_ptrs, uint32_t value, int32_t rank, int32_t world, void* stream);
 int mgp_peer_barrier(void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream);
 int mgp_cg_pupdate_f32(float* p, const float* r, int64_t ld, int64_t n, int32_t ncols, const float* state, void* stream);
 int mgp_cg_pupdate_f64(double* p, const double* r, int64_t ld, int64_t n, int32_t ncols, const double* state, void* stream);

@@ -57,17 +57,30 @@ __device__ __forceinline__ void block_col_reduce(const T* acc, int ncb, int CP, 
 }
 
 // Fixed-order reduction of partials over blocks by the calling (last) block; result for column c in smem out[c].
+// The loads of a thread are independent (8 in flight): the r01 version chained ~74 dependent L2 round trips per thread
+// (~10 us of serial tail in every r-update launch, ncu launch list profiles/r01_*).
 template <typename T>
 __device__ __forceinline__ void last_block_reduce(const T* partials, int ncols, T* out /* smem [kCgMaxCols] */) {
   __shared__ T red[kCgBlock];
   const int tid = threadIdx.x;
+  const int nb = (int)gridDim.x;
   for (int cbase = 0; cbase < ncols; cbase += 32) {
     const int cw = min(32, ncols - cbase);
     const int per = kCgBlock / cw;
     const int c = tid % cw, r = tid / cw;
     T s = T(0);
-    if (r < per)
-      for (int b = r; b < (int)gridDim.x; b += per) s += __ldcg(partials + (int64_t)b * ncols + cbase + c);
+    if (r < per) {
+      const T* q = partials + cbase + c;
+      int b = r;
+      for (; b + 7 * per < nb; b += 8 * per) {
+        T t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = __ldcg(q + (int64_t)(b + u * per) * ncols);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += t[u];
+      }
+      for (; b < nb; b += per) s += __ldcg(q + (int64_t)b * ncols);
+    }
     __syncthreads();
     red[tid] = (r < per) ? s : T(0);
     __syncthreads();
@@ -78,6 +91,57 @@ __device__ __forceinline__ void last_block_reduce(const T* partials, int ncols, 
     }
   }
   __syncthreads();
+}
+
+// sum of one value per thread over the block, result valid in thread 0 (fixed order: lanes by shuffle tree, then warps 0..7)
+template <typename T>
+__device__ __forceinline__ T block_sum_t0(T v) {
+  __shared__ T wsum[kCgBlock / 32];
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T s = T(0);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < kCgBlock / 32; ++w) s += wsum[w];
+  }
+  return s;
+}
+
+// per-thread accumulators of the vectorised kernels (thread t holds columns (t*N) % ld .. +N-1) -> one partial per column of
+// the block: lanes with equal columns are combined by a shuffle tree, the 8 warps through shared memory (fixed order)
+template <typename T, int N>
+__device__ __forceinline__ void vec_block_partials(const T (&acc)[N], int ld, int ncols, T* dst /* partials of this block */) {
+  __shared__ T wpart[kCgBlock / 32][kCgMaxCols];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = ld / N;                       // threads per row of the vector; a power of two
+  T a[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    a[u] = acc[u];
+    for (int o = groups; o < 32; o <<= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
+  }
+  if (groups >= 32) {
+    // a warp covers 32 * N consecutive columns starting at ((warp * 32) % groups) * N: warps with equal start are combined below
+#pragma unroll
+    for (int u = 0; u < N; ++u) wpart[warp][(tid * N) % ld + u] = a[u];
+  } else if (lane < groups) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) wpart[warp][lane * N + u] = a[u];
+  }
+  __syncthreads();
+  if (tid < ncols) {
+    T s = T(0);
+    if (groups >= 32) {
+      const int wpr = groups / 32;                 // warps per row of the vector
+      for (int w = (tid / (32 * N)) % wpr; w < kCgBlock / 32; w += wpr) s += wpart[w][tid];
+    } else {
+#pragma unroll
+      for (int w = 0; w < kCgBlock / 32; ++w) s += wpart[w][tid];
+    }
+    dst[tid] = s;
+  }
 }
 
 template <typename T>
@@ -108,7 +172,6 @@ __device__ __forceinline__ void cg_finish_norm(T* state, const T* tot, int ncols
 template <typename T>
 __device__ __forceinline__ void cg_finish_init(T* state, const T* tot, int ncols, T tol, T eps, T stop, int max_iter,
                                                int n_tridiag_iter) {
-  __shared__ T msum_i[kCgBlock];
   const int tid = threadIdx.x;
   T local = T(0);
   int all_conv = 1;
@@ -123,11 +186,9 @@ __device__ __forceinline__ void cg_finish_init(T* state, const T* tot, int ncols
     local += rn;
     if (!(rn < stop)) all_conv = 0;
   }
-  msum_i[tid] = local;
   const int any_unconv = __syncthreads_or(!all_conv);
+  const T s = block_sum_t0<T>(local);
   if (tid == 0) {
-    T s = T(0);
-    for (int i = 0; i < kCgBlock; ++i) s += msum_i[i];
     T* k = state + S_NARR * ncols;
     k[K_MEAN] = s / T(ncols);
     // published: "if has_converged.all() and not n_tridiag: n_iter = 0"
@@ -148,7 +209,6 @@ __device__ __forceinline__ T cg_alpha_of(const T* state, int ncols, int c, T eps
 
 template <typename T>
 __device__ __forceinline__ void cg_finish_update(T* state, const T* tot, int ncols, T* hist, int max_hist) {
-  __shared__ T msum_u[kCgBlock];
   const int tid = threadIdx.x;
   T* k = state + S_NARR * ncols;
   const T eps = k[K_EPS];
@@ -174,11 +234,8 @@ __device__ __forceinline__ void cg_finish_update(T* state, const T* tot, int nco
     }
     local += rn;
   }
-  msum_u[tid] = local;
-  __syncthreads();
+  const T s = block_sum_t0<T>(local);
   if (tid == 0) {
-    T s = T(0);
-    for (int i = 0; i < kCgBlock; ++i) s += msum_u[i];
     const T mean = s / T(ncols);
     k[K_MEAN] = mean;
     k[K_ITER] = T(it + 1);
@@ -377,7 +434,6 @@ cg_update_vec_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__
   if (k[K_DONE] != T(0)) return;
   CgWs<T> w = cg_ws<T>(ws);
   __shared__ T al[kCgMaxCols];
-  __shared__ T sm[kCgBlock][N];
   const int tid = threadIdx.x;
   const T eps = k[K_EPS];
   for (int c = tid; c < ld; c += kCgBlock) al[c] = c < ncols ? cg_alpha_of<T>(state, ncols, c, eps) : T(0);
@@ -405,16 +461,7 @@ cg_update_vec_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__
     r4[e] = v16_pack<T>(rv);
     x4[e] = v16_pack<T>(xv);
   }
-#pragma unroll
-  for (int u = 0; u < N; ++u) sm[tid][u] = acc[u];
-  __syncthreads();
-  if (tid < ncols) {
-    // threads t with (t*N) % ld == (tid / N) * N hold column tid in slot tid % N; fixed summation order
-    const int groups = ld / N;
-    T s = T(0);
-    for (int t = tid / N; t < kCgBlock; t += groups) s += sm[t][tid % N];
-    w.partials[(int64_t)blockIdx.x * ncols + tid] = s;
-  }
+  vec_block_partials<T, N>(acc, ld, ncols, w.partials + (int64_t)blockIdx.x * ncols);
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);
@@ -573,7 +620,6 @@ cg_rupdate_vec_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_
   }
   CgWs<T> w = cg_ws<T>(ws);
   __shared__ T al[kCgMaxCols];
-  __shared__ T sm[kCgBlock][N];
   const int tid = threadIdx.x;
   const T eps = k[K_EPS];
   for (int c = tid; c < ld; c += kCgBlock) al[c] = c < ncols ? cg_alpha_of<T>(state, ncols, c, eps) : T(0);
@@ -597,15 +643,7 @@ cg_rupdate_vec_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_
     }
     r4[e] = v16_pack<T>(rv);
   }
-#pragma unroll
-  for (int u = 0; u < N; ++u) sm[tid][u] = acc[u];
-  __syncthreads();
-  if (tid < ncols) {
-    const int groups = ld / N;
-    T s = T(0);
-    for (int t = tid / N; t < kCgBlock; t += groups) s += sm[t][tid % N];
-    w.partials[(int64_t)blockIdx.x * ncols + tid] = s;
-  }
+  vec_block_partials<T, N>(acc, ld, ncols, w.partials + (int64_t)blockIdx.x * ncols);
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);
@@ -846,7 +884,6 @@ cg_peer_rupdate_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64
   if (k[K_DONE] != T(0)) return;
   CgWs<T> w = cg_ws<T>(ws);
   __shared__ T al[kCgMaxCols];
-  __shared__ T sm[kCgBlock][N];
   const int tid = threadIdx.x;
   const unsigned int epoch = (unsigned int)k[K_ITER] + 1u;
   const int buf = (int)(epoch & 1u);
@@ -893,15 +930,7 @@ cg_peer_rupdate_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64
     }
     r4[e] = v16_pack<T>(rv);
   }
-#pragma unroll
-  for (int u = 0; u < N; ++u) sm[tid][u] = acc[u];
-  __syncthreads();
-  if (tid < ncols) {
-    const int groups = ld / N;
-    T s = T(0);
-    for (int t = tid / N; t < kCgBlock; t += groups) s += sm[t][tid % N];
-    w.partials[(int64_t)blockIdx.x * ncols + tid] = s;
-  }
+  vec_block_partials<T, N>(acc, ld, ncols, w.partials + (int64_t)blockIdx.x * ncols);
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);
@@ -972,6 +1001,146 @@ cg_peer_pxupdate_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restric
     __syncthreads();
     if (tid == 0) k[K_XPEND] = T(0);
   }
+}
+
+
+// ---- multi-GPU, single-reduction iteration (Chronopoulos & Gear): ONE vector kernel, ONE all-reduce per iteration --------------
+// Standard CG needs p^T A p before the r update and |r|^2 before the p update: two cross-GPU reductions per iteration, each
+// a sync point (~4 us of NVLink round trip + a launch).  The Chronopoulos-Gear recurrences produce the same iterates from
+//     w = A r,   gamma = r.r,   delta = r.w        (both dots known as soon as the matvec is done -> one reduction)
+//     beta_k  = gamma_k / gamma_{k-1}              (beta_0 = 0)
+//     alpha_k = gamma_k / (delta_k - beta_k gamma_k / alpha_{k-1})          (= gamma_k / p_k^T A p_k in exact arithmetic)
+//     p = r + beta p ;  s = w + beta s (= A p) ;  x += alpha p ;  r -= alpha s
+// so an iteration is [SpMM x nu with r as the source] + this kernel.  The last SpMM launch ships this rank's (delta, gamma)
+// partials to every peer when its last block finishes (mgp_lap_spmm_wi_ex: red_ptrs / red_flags); every block here waits
+// for all ranks' partials, adds them in rank order (bit-identical scalars on every rank), applies the four updates and
+// accumulates |r_new|^2; the last block to finish stores that local sum for the next shipment, advances the scalar state
+// (same masks / stopping rules / history as cg_finish_update; the residual norm tested is the one ENTERING the iteration,
+// so convergence is noticed one matvec later than in the two-reduction form and no update is applied then) and publishes
+// "r complete" (epoch + 1) to the peers, whose next SpMM waits for it at its first remote halo row.
+// Measured in fp32 on the cfg-C-conditioned torus (30k points, CPU experiment of round 2): same iteration count as the
+// two-reduction form, solution error vs fp64 1.2e-5 (3.2e-6 for the standard recurrences).
+template <typename T>
+__global__ void __launch_bounds__(kCgBlock)
+cg_peer_cgstep_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T* __restrict__ s, const T* __restrict__ wv_,
+                      int ld, int64_t n, int ncols, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws,
+                      T* __restrict__ gamma_loc, T* const* __restrict__ red_ptrs, unsigned int* const* __restrict__ dflag_ptrs,
+                      unsigned int* const* __restrict__ rflag_ptrs, int rank, int world) {
+  using V = typename V16<T>::type;
+  constexpr int N = V16<T>::N;
+  T* k = state + S_NARR * ncols;
+  if (k[K_DONE] != T(0)) return;
+  CgWs<T> w = cg_ws<T>(ws);
+  __shared__ T al[kCgMaxCols], be[kCgMaxCols], gam[kCgMaxCols], den[kCgMaxCols], rnm[kCgMaxCols];
+  __shared__ T s_mean;
+  __shared__ int s_done;
+  const int tid = threadIdx.x;
+  const int it = (int)k[K_ITER];
+  const unsigned int epoch = (unsigned int)it + 1u;
+  const int buf = (int)(epoch & 1u);
+  wait_flags(dflag_ptrs[rank], world, epoch);
+  const T eps = k[K_EPS], stop = k[K_STOP];
+  T local = T(0);
+  for (int c = tid; c < ld; c += kCgBlock) {
+    T a = T(0), b = T(0), gm = T(0), dn = T(0), rn = T(0);
+    if (c < ncols) {
+      T dl = T(0);
+      for (int src = 0; src < world; ++src) {
+        dl += __ldcv(peer_red_slot<T>(red_ptrs[rank], 0, buf, world, src) + c);
+        gm += __ldcv(peer_red_slot<T>(red_ptrs[rank], 1, buf, world, src) + c);
+      }
+      rn = dev_sqrt<T>(gm);
+      if (state[S_RHSZERO * ncols + c] != T(0)) rn = T(0);
+      const T g_old = state[S_RZ * ncols + c], a_old = state[S_ALPHA * ncols + c];
+      b = (it == 0 || g_old < eps) ? T(0) : gm / g_old;
+      dn = (it == 0 || a_old == T(0)) ? dl : dl - b * gm / a_old;
+      a = (dn < eps) ? T(0) : gm / dn;
+      if (rn < stop) a = T(0);
+      local += rn;
+    }
+    al[c] = a; be[c] = b; gam[c] = gm; den[c] = dn; rnm[c] = rn;
+  }
+  const T tot = block_sum_t0<T>(local);
+  if (tid == 0) {
+    const T mean = tot / T(ncols);
+    s_mean = mean;
+    int done = 0;
+    if (it >= 1) {
+      const bool tri_pending = (k[K_NTRIMIN] > T(0)) && (T(it - 1) < k[K_NTRIMIN]);
+      if (T(it - 1) >= k[K_MINITER] && mean < k[K_TOL] && !tri_pending) done = 1;
+      else if (T(it) >= k[K_MAXITER]) done = 2;
+    }
+    s_done = done;
+  }
+  __syncthreads();
+  if (s_done) {
+    // every block reaches the same verdict from the same totals; block 0 records it.  x already is the answer.
+    if (blockIdx.x == 0) {
+      for (int c = tid; c < ncols; c += kCgBlock) {
+        state[S_RESID * ncols + c] = rnm[c];
+        state[S_CONV * ncols + c] = (rnm[c] < stop) ? T(1) : T(0);
+        if (hist && it >= 1 && it - 1 < max_hist) hist[((int64_t)(it - 1) * 2 + 1) * ncols + c] = be[c];
+      }
+      __syncthreads();
+      if (tid == 0) { k[K_MEAN] = s_mean; __threadfence(); k[K_DONE] = T(s_done); }
+    }
+    return;
+  }
+  const int c0 = (tid * N) % ld;
+  T a[N], b[N], acc[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) { a[u] = al[c0 + u]; b[u] = be[c0 + u]; acc[u] = T(0); }
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* x4 = reinterpret_cast<V*>(x);
+  V* r4 = reinterpret_cast<V*>(r);
+  V* p4 = reinterpret_cast<V*>(p);
+  V* s4 = reinterpret_cast<V*>(s);
+  const V* w4 = reinterpret_cast<const V*>(wv_);
+#pragma unroll 2
+  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + tid; e < total; e += stride) {
+    T pv[N], sv[N], rv[N], wv[N], xv[N];
+    v16_unpack<T>(p4[e], pv); v16_unpack<T>(s4[e], sv); v16_unpack<T>(r4[e], rv); v16_unpack<T>(w4[e], wv); v16_unpack<T>(x4[e], xv);
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      pv[u] = fma(b[u], pv[u], rv[u]);
+      sv[u] = fma(b[u], sv[u], wv[u]);
+      xv[u] = fma(a[u], pv[u], xv[u]);
+      rv[u] = fma(-a[u], sv[u], rv[u]);
+      acc[u] = fma(rv[u], rv[u], acc[u]);
+    }
+    p4[e] = v16_pack<T>(pv); s4[e] = v16_pack<T>(sv); x4[e] = v16_pack<T>(xv); r4[e] = v16_pack<T>(rv);
+  }
+  vec_block_partials<T, N>(acc, ld, ncols, w.partials + (int64_t)blockIdx.x * ncols);
+  if (last_block_ticket(w.counter)) {
+    __shared__ T tot2[kCgMaxCols];
+    last_block_reduce<T>(w.partials, ncols, tot2);
+    for (int c = tid; c < ncols; c += kCgBlock) {
+      gamma_loc[c] = tot2[c];                               // this rank's |r_{k+1}|^2: shipped by the next matvec
+      state[S_RZ * ncols + c] = gam[c];
+      state[S_PAP * ncols + c] = den[c];
+      state[S_ALPHA * ncols + c] = al[c];
+      state[S_BETA * ncols + c] = be[c];
+      state[S_RESID * ncols + c] = rnm[c];
+      state[S_CONV * ncols + c] = (rnm[c] < stop) ? T(1) : T(0);
+      if (hist) {
+        if (it < max_hist) hist[((int64_t)it * 2 + 0) * ncols + c] = al[c];
+        if (it >= 1 && it - 1 < max_hist) hist[((int64_t)(it - 1) * 2 + 1) * ncols + c] = be[c];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { k[K_MEAN] = s_mean; k[K_ITER] = T(it + 1); }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(rflag_ptrs[tid] + rank, epoch + 1u);     // r_{k+1} complete on this rank
+  }
+}
+
+// flags[dst][rank] = value on every rank: "everything this rank enqueued before is complete" without waiting for anybody
+__global__ void __launch_bounds__(32)
+peer_publish_kernel(unsigned int* const* __restrict__ flag_ptrs, unsigned int value, int rank, int world) {
+  __threadfence_system();
+  if ((int)threadIdx.x < world) st_release_sys(flag_ptrs[threadIdx.x] + rank, value);
 }
 
 }  // namespace mgp
@@ -1133,6 +1302,36 @@ int mgp_cg_peer_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, 
   int64_t g = ceil_div(n * ld / V16<double>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
   cg_peer_pxupdate_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, p, r, (int)ld, n, ncols, state, hist, max_hist, ws,
       (double* const*)red_ptrs, (unsigned int* const*)flag3_ptrs, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_cgstep_f32(float* x, float* r, float* p, float* s, const float* w, int64_t ld, int64_t n, int32_t ncols, float* state,
+                           float* hist, int32_t max_hist, void* ws, float* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
+                           int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(x && r && p && s && w && state && ws && gamma_loc && red_ptrs && dflag_ptrs && rflag_ptrs && n > 0 && ncols > 0 &&
+                    world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_cgstep: bad arguments");
+  if (!cg_vec_ok<float>(ld, x, r, p, s) || (((uintptr_t)w) % 16) != 0) return MGP_EUNSUPPORTED;
+  int64_t g = ceil_div(n * ld / V16<float>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
+  cg_peer_cgstep_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, r, p, s, w, (int)ld, n, ncols, state, hist, max_hist, ws,
+      gamma_loc, (float* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_cg_peer_cgstep_f64(double* x, double* r, double* p, double* s, const double* w, int64_t ld, int64_t n, int32_t ncols, double* state,
+                           double* hist, int32_t max_hist, void* ws, double* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
+                           int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(x && r && p && s && w && state && ws && gamma_loc && red_ptrs && dflag_ptrs && rflag_ptrs && n > 0 && ncols > 0 &&
+                    world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_cgstep: bad arguments");
+  if (!cg_vec_ok<double>(ld, x, r, p, s) || (((uintptr_t)w) % 16) != 0) return MGP_EUNSUPPORTED;
+  int64_t g = ceil_div(n * ld / V16<double>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
+  cg_peer_cgstep_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, r, p, s, w, (int)ld, n, ncols, state, hist, max_hist, ws,
+      gamma_loc, (double* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+int mgp_peer_publish(void* flag_ptrs, uint32_t value, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(flag_ptrs && world >= 1 && world <= 32 && rank >= 0 && rank < world, "peer_publish: bad arguments");
+  peer_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned int* const*)flag_ptrs, value, rank, world);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

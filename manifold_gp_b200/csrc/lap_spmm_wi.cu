@@ -71,6 +71,18 @@ struct WiArgs {
   unsigned int* counter;
   int dot_is_x;
   int stages;
+  // ---- extended multi-GPU / solver hooks (mgp_lap_spmm_wi_ex; all optional) ----
+  const T* done;                       // device scalar: the launch is a no-op when *done != 0 (CG past convergence)
+  unsigned int* const* wait_flags;     // like sync_flags but WITHOUT the publish at kernel start: producers wait (lazily, at the
+                                        // first remote halo row) until wait_flags[rank][src] >= epoch for every src
+  unsigned int* const* publish_flags;  // after ALL rows of Y are written (last block to finish, last column pass):
+                                        // publish_flags[dst][rank] = epoch for every dst ("my Y is complete")
+  unsigned int* ticket;                // device counter for the completion ticket (zeroed once by the caller; self-resetting)
+  T* const* red_ptrs;                  // with dot_out on the last column pass: the last block ships [dot_out | ship_extra] to slot
+  unsigned int* const* red_flags;      //   [kind][epoch & 1][rank] of every rank's reduction buffer, then red_flags[dst][rank] = epoch
+  const T* ship_extra;                 // second local sum to ship (kind 1), e.g. |r|^2 partials of the vector kernel; may be NULL
+  int ship_ncols;                      // total number of columns to ship
+  int last_pass;                       // 1 on the launch of the last column pass
   int debug;     // timing experiments only (MGP_WI_DEBUG bit mask): 1 = consumers skip the row walk, 2 = producers skip the halo rows
                  // (same-process A/B on B200, cfg-C: 150 us full, 104 without halo copies, 90 without the walk, 62 with neither)
 };
@@ -120,6 +132,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
   unsigned char* const ring = smem_raw + (size_t)nstages * stage_bytes;
   int* const ids_ring = reinterpret_cast<int*>(ring + 2 * kWiMetaBytes);
 
+  if (g.done && *g.done != T(0)) return;          // uniform: CG converged, nothing to compute, publish or wait for
   if (g.peer_x && tid < g.npeers) peer_tab[tid] = g.peer_x[tid];
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) {
@@ -134,13 +147,14 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
   __syncthreads();
 
   unsigned int sync_epoch = 0u;
+  if (g.sync_epoch) sync_epoch = (unsigned int)(*g.sync_epoch) + 1u;
   if (g.sync_flags) {
-    sync_epoch = (unsigned int)(*g.sync_epoch) + 1u;
     if (blockIdx.x == 0 && warp == 1 && lane < g.npeers) {      // "everything enqueued before this launch is done on my side"
       __threadfence_system();
       st_release_sys(g.sync_flags[lane] + g.rank, sync_epoch);
     }
   }
+  unsigned int* const* const wait_tab = g.wait_flags ? g.wait_flags : g.sync_flags;
 
   // contiguous tile range of this block
   const int t0 = (int)(((int64_t)blockIdx.x * g.ntiles) / gridDim.x);
@@ -237,9 +251,9 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
           sr &= (1 << 26) - 1;
           remote = owner != g.rank;
         }
-        if (g.sync_flags && !peers_ready && __any_sync(0xffffffffu, remote)) {
+        if (wait_tab && !peers_ready && __any_sync(0xffffffffu, remote)) {
           if (lane < g.npeers) {
-            const unsigned int* f = g.sync_flags[g.rank] + lane;
+            const unsigned int* f = wait_tab[g.rank] + lane;
             unsigned int spins = 0;
             while ((int)(ld_acquire_sys(f) - sync_epoch) < 0) {
               if (++spins > (1u << 25)) __trap();
@@ -371,7 +385,39 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
 
   if (g.dot_out) {
     __syncthreads();
-    spmm_dot_epilogue<T, VEC, 4, CW, kWiThreads>(dsum, CW, g.c0, g.partials, g.counter, g.dot_out);
+    const bool last = spmm_dot_epilogue<T, VEC, 4, CW, kWiThreads>(dsum, CW, g.c0, g.partials, g.counter, g.dot_out);
+    // Fused all-reduce, first half: the block that completed the LOCAL sums ships them (and the caller's second sum) to every
+    // rank's reduction buffer and raises this rank's flag there -- the consumer kernel only has to wait and add.
+    if (last && g.red_ptrs && g.last_pass) {
+      __syncthreads();                                      // dot_out of this pass is written (earlier passes: stream order)
+      const int buf = (int)(sync_epoch & 1u);
+      for (int i = tid; i < g.npeers * g.ship_ncols; i += kWiThreads) {
+        const int dst = i / g.ship_ncols, c = i - dst * g.ship_ncols;
+        T* base = g.red_ptrs[dst];
+        base[(((size_t)0 * 2 + buf) * g.npeers + g.rank) * 128 + c] = g.dot_out[c];
+        if (g.ship_extra) base[(((size_t)1 * 2 + buf) * g.npeers + g.rank) * 128 + c] = g.ship_extra[c];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid < g.npeers) st_release_sys(g.red_flags[tid] + g.rank, sync_epoch);
+    }
+  }
+  if (g.publish_flags && g.last_pass) {
+    // "Y complete" flag from the producing kernel itself (not from the first block of the consumer launch: that costs a
+    // launch latency per sync point).  Every thread's stores are fenced, the last block to arrive publishes.
+    __shared__ int publish_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int tk = atomicAdd(g.ticket, 1u);
+      publish_last = (tk == gridDim.x - 1);
+      if (publish_last) *g.ticket = 0u;
+    }
+    __syncthreads();
+    if (publish_last && tid < g.npeers) {
+      __threadfence_system();
+      st_release_sys(g.publish_flags[tid] + g.rank, sync_epoch);
+    }
   }
 }
 
@@ -408,7 +454,7 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
                        const int* hcol, int tile_rows, int lmax, int wnzmax, int hmax, const T* shift, const T* post, const int* xmap,
                        const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int ncols, const T* dot_with,
                        T* dot_out, void* dot_ws, const void* peer_x, int npeers, int rank, const void* sync_flags, const T* sync_epoch,
-                       cudaStream_t st) {
+                       cudaStream_t st, const mgp_wi_ext* ext = nullptr) {
   constexpr int R = kWiRows;
   constexpr int VEC = 16 / sizeof(T);
   constexpr int CW = 4 * VEC;
@@ -433,6 +479,24 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   g.sync_flags = reinterpret_cast<unsigned int* const*>(const_cast<void*>(sync_flags)); g.sync_epoch = sync_epoch;
   MGP_CHECK_ARG(sync_flags == nullptr || (peer_x && sync_epoch && rank >= 0 && rank < npeers), "lap_spmm_wi: fused barrier needs peer X, an epoch pointer and a valid rank");
   MGP_CHECK_ARG(peer_x == nullptr || (npeers >= 1 && npeers <= 32 && xmap == nullptr), "lap_spmm_wi: peer X needs 1..32 ranks and no xmap");
+  g.done = nullptr; g.wait_flags = nullptr; g.publish_flags = nullptr; g.ticket = nullptr; g.red_ptrs = nullptr;
+  g.red_flags = nullptr; g.ship_extra = nullptr; g.ship_ncols = 0; g.last_pass = 0;
+  if (ext) {
+    g.done = reinterpret_cast<const T*>(ext->done_flag);
+    g.wait_flags = reinterpret_cast<unsigned int* const*>(const_cast<void*>(ext->wait_flags));
+    g.publish_flags = reinterpret_cast<unsigned int* const*>(const_cast<void*>(ext->publish_flags));
+    g.ticket = reinterpret_cast<unsigned int*>(ext->ticket);
+    g.red_ptrs = reinterpret_cast<T* const*>(const_cast<void*>(ext->red_ptrs));
+    g.red_flags = reinterpret_cast<unsigned int* const*>(const_cast<void*>(ext->red_flags));
+    g.ship_extra = reinterpret_cast<const T*>(ext->ship_extra);
+    g.ship_ncols = ext->ship_ncols;
+    const bool sync_any = g.wait_flags || g.publish_flags || g.red_ptrs;
+    MGP_CHECK_ARG(!sync_any || (peer_x && sync_epoch && rank >= 0 && rank < npeers), "lap_spmm_wi_ex: flags need peer X, an epoch pointer and a valid rank");
+    MGP_CHECK_ARG(g.publish_flags == nullptr || g.ticket != nullptr, "lap_spmm_wi_ex: publish_flags needs a ticket counter");
+    MGP_CHECK_ARG(g.red_ptrs == nullptr || (g.red_flags && dot_out && g.ship_ncols > 0 && g.ship_ncols <= 128 && g.ship_ncols <= ncols),
+                  "lap_spmm_wi_ex: shipping the dot partials needs red_flags, dot_out and 0 < ship_ncols <= min(128, ncols)");
+    MGP_CHECK_ARG(sync_flags == nullptr || g.wait_flags == nullptr, "lap_spmm_wi_ex: sync_flags and wait_flags are exclusive");
+  }
   g.ntiles = (int)ceil_div(n, (int64_t)R);
   g.lmax = (lmax + 3) & ~3;
   g.nzcap = wnzmax + 32;                       // the consumers' look-ahead loads read one step past a warp block
@@ -467,6 +531,7 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   if (blocks > g.ntiles) blocks = g.ntiles;
   for (int c0 = 0; c0 < ncols; c0 += CW) {
     g.c0 = c0;
+    g.last_pass = (c0 + CW >= ncols) ? 1 : 0;
     kern<<<(unsigned)blocks, kWiThreads, smem, st>>>(g);
     MGP_LAUNCH_CHECK();
   }
@@ -501,6 +566,24 @@ int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double*
                         void* stream) {
   return mgp::lap_spmm_wi<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
                                   ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, rank, sync_flags, sync_epoch, (cudaStream_t)stream);
+}
+int mgp_lap_spmm_wi_ex_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
+                           const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
+                           const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
+                           int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
+                           const void* peer_x, int32_t npeers, int32_t rank, const float* sync_epoch, const mgp_wi_ext* ext,
+                           void* stream) {
+  return mgp::lap_spmm_wi<float>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
+                                 ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, rank, nullptr, sync_epoch, (cudaStream_t)stream, ext);
+}
+int mgp_lap_spmm_wi_ex_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag, const int32_t* hptr,
+                           const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const double* shift,
+                           const double* post, const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y,
+                           int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws,
+                           const void* peer_x, int32_t npeers, int32_t rank, const double* sync_epoch, const mgp_wi_ext* ext,
+                           void* stream) {
+  return mgp::lap_spmm_wi<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, lmax, wnzmax, hmax, shift, post, xmap, ymap, x,
+                                  ldx, y, ldy, n, ncols, dot_with, dot_out, dot_ws, peer_x, npeers, rank, nullptr, sync_epoch, (cudaStream_t)stream, ext);
 }
 
 }  // extern "C"

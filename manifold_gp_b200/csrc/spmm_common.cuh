@@ -49,7 +49,7 @@ __device__ __forceinline__ void st_vec(T* p, const Vec<T, VEC>& r) {
 
 // block-level column reduction + deterministic last-block reduction used by the dot-product epilogues
 template <typename T, int VEC, int LPN, int CWMAX, int BLOCK>
-__device__ __forceinline__ void spmm_dot_epilogue(T (&dsum)[VEC], int cw, int c0, T* partials, unsigned int* counter,
+__device__ __forceinline__ bool spmm_dot_epilogue(T (&dsum)[VEC], int cw, int c0, T* partials, unsigned int* counter,
                                                   T* dot_out) {
   __shared__ T sm_dot[BLOCK / 32][CWMAX];
   __shared__ T red_dot[BLOCK];
@@ -67,7 +67,8 @@ __device__ __forceinline__ void spmm_dot_epilogue(T (&dsum)[VEC], int cw, int c0
     for (int w = 0; w < BLOCK / 32; ++w) s += sm_dot[w][tid];
     partials[(int64_t)blockIdx.x * cw + tid] = s;
   }
-  if (last_block_ticket(counter)) {
+  const bool is_last_block = last_block_ticket(counter);
+  if (is_last_block) {
     const int c = tid % cw;
     const int lanes_per_col = BLOCK / cw;  // cw <= 32
     const int r = tid / cw;
@@ -82,6 +83,7 @@ __device__ __forceinline__ void spmm_dot_epilogue(T (&dsum)[VEC], int cw, int c0
       dot_out[c0 + tid] = t;
     }
   }
+  return is_last_block;     // block-uniform: true in the block that wrote dot_out
 }
 
 }  // namespace mgp

@@ -163,6 +163,10 @@ class DistPrecision:
         self.nu = nu
         self.n_loc = hi - lo
         self.n_ext = self.n_loc + int(self.plan.halo_ids.numel())
+        # the solvers' captured CUDA graphs bake in the pointer of the value layout: own it here (the structure's cache is a
+        # 4-deep LRU and may drop it while this operator is alive)
+        t = gst.tiles
+        self._layout_keep = gst.wi_values(a) if (t is not None and "wptr" in t) else None
 
     def matvec(self, p, out, tmp, ncols, dot_out=None):
         """out[:n_loc, :ncols] <- P p  (p, tmp: [n_ext, ld] with halo rows; out: [>= n_loc, ld])."""
@@ -209,6 +213,9 @@ class DistCG:
     def _allreduce_rbuf(self):
         dist.all_reduce(self.rbuf, group=self.group)
 
+    def _after_init(self):
+        pass
+
     def _scalars(self, what):
         from . import _lib
         from ._lib import c_double, c_float, c_int32, ptr, stream
@@ -245,6 +252,7 @@ class DistCG:
                   c_int64(n_loc), c_int32(c), ptr(self.state), ptr(self.rbuf), ptr(self.ws), stream())
         self._allreduce_rbuf()
         self._scalars(1)
+        self._after_init()
         scal = solvers.S_NARR * c
         k, done = 0, 0.0
         if self.use_graph and self.graph is None and self.max_iter >= 2 * self.check:
@@ -294,15 +302,23 @@ class PeerMemory:
     device pointers of all ranks' copies (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once at
     rendezvous, NVLink P2P loads / stores afterwards).  Plumbing only -- the data path is the kernels that use the pointers."""
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, world=None):
+        self.device = device
+        self.world = int(world) if world is not None else dist.get_world_size(group)
+        self.handles = []
+        if self.world == 1:
+            self._sm, self.group = None, group
+            return
         import torch.distributed._symmetric_memory as symm_mem
         self._sm = symm_mem
-        self.device = device
         self.group = group if group is not None else dist.group.WORLD
-        self.handles = []
 
     def alloc(self, shape, dtype):
         """(local tensor, int64 device tensor with the world's base pointers)."""
+        if self.world == 1:      # one rank: its own memory is the whole "symmetric" allocation
+            t = torch.zeros(*shape, dtype=dtype, device=self.device)
+            self.handles.append(t)
+            return t, torch.tensor([t.data_ptr()], dtype=torch.int64, device=self.device)
         t = self._sm.empty(*shape, dtype=dtype, device=self.device)
         hdl = self._sm.rendezvous(t, self.group)
         t.zero_()
@@ -312,29 +328,51 @@ class PeerMemory:
 
     def sync(self):
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
+        if self.world > 1:
+            dist.barrier(group=self.group)
 
 
 class PeerCG(DistCG):
-    """DistCG whose every exchange is a hand-written peer-memory kernel instead of an NCCL call (8 x B200 behind NVSwitch):
+    """DistCG whose every exchange is a hand-written peer-memory kernel instead of an NCCL call (8 x B200 behind NVSwitch).
 
-    * halo rows are not exchanged at all: ``p`` and the intermediate vectors live in peer-mapped memory and the SpMM's
-      producer warps cp.async the halo rows straight from the owning rank's vector (``peer_x`` of mgp_lap_spmm_wi);
-      producer and consumer launches are separated by ``mgp_peer_barrier`` (one tiny kernel, epoch flags over NVLink);
-    * the two inner products of an iteration are all-reduced inside the scalar kernels (``mgp_cg_peer_scalars``).
+    Halo rows are not exchanged at all: the vectors the SpMM reads live in peer-mapped memory and its producer warps cp.async
+    the halo rows straight from the owning rank's vector (``peer_x`` of mgp_lap_spmm_wi).  Three generations, ``mode``:
 
-    An iteration is 8 kernel launches and no library call; NCCL's launch + protocol latency (~37 us per 16-float
-    all-reduce, ~2 x that per halo all-to-all on this box) was ~2/3 of the 8-GPU iteration time."""
+    * ``"cg1"`` (default) -- single-reduction iteration (Chronopoulos-Gear recurrences, csrc/cg.cu::cg_peer_cgstep_kernel):
+      nu SpMM launches with r as the source + ONE vector kernel = nu + 1 launches and nu + 1 sync points, every one of
+      them published by the LAST block of the producing kernel (no launch latency on the critical path) and waited for
+      only where the data is needed (first remote halo row / start of the vector kernel).  Same iterates, masks, stopping
+      rules and tridiagonal history as ``solvers.linear_cg``.
+    * ``"fused"`` (round 1) -- standard two-reduction CG: barriers inside the SpMM launches (published at kernel start), the
+      two all-reduces inside the r / (p, x) update kernels: nu + 2 launches, nu + 2 sync points.
+    * ``"unfused"`` -- separate barrier / all-reduce kernels (8 launches), kept as the simplest correct form.
+    """
 
     def __init__(self, op: DistPrecision, ncols: int, dtype=torch.float32, tolerance=1e-6, eps=1e-10,
-                 stop_updating_after=1e-10, max_iter=1000, check_interval=16, group=None, use_cuda_graph=True):
+                 stop_updating_after=1e-10, max_iter=1000, check_interval=16, group=None, use_cuda_graph=True, mode=None,
+                 n_tridiag=0, max_tridiag_iter=20):
         super().__init__(op, ncols, dtype, tolerance, eps, stop_updating_after, max_iter, check_interval, group, use_cuda_graph)
         from . import solvers
         dev = self.dev
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         part = op.plan.part
         n_sym = max(b1 - b0 for b0, b1 in zip(part.bounds[:-1], part.bounds[1:]))       # same allocation size on every rank
-        self.mem = PeerMemory(dev, group)
+        self.mem = PeerMemory(dev, group, self.world)
+        if mode is None:
+            mode = os.environ.get("MGP_PEER_MODE", "cg1")
+            if os.environ.get("MGP_PEER_FUSED") == "0":
+                mode = "unfused"
+        pow2 = self.ld <= 128 and (self.ld & (self.ld - 1)) == 0
+        if mode in ("cg1", "fused") and not pow2:
+            mode = "unfused"
+        self.mode = mode
+        self.fused = mode == "fused"
+        self.n_tridiag = int(n_tridiag)
+        self.n_tridiag_iter = int(min(max_tridiag_iter, part.n)) if n_tridiag else 0
+        self.max_hist = max(1, min(max_iter, self.n_tridiag_iter)) if n_tridiag else 0
+        self.hist = torch.zeros((self.max_hist, 2, ncols), dtype=dtype, device=dev) if n_tridiag else None
+        if n_tridiag and mode != "cg1":
+            raise RuntimeError("PeerCG: the tridiagonal history is recorded by the single-reduction mode only")
         self.p, self.p_ptrs = self.mem.alloc((n_sym, self.ld), dtype)
         self.tmps = [self.mem.alloc((n_sym, self.ld), dtype) for _ in range(max(op.nu - 1, 0))]
         self.red, self.red_ptrs = self.mem.alloc((2 * self.world * 128,), dtype)
@@ -342,16 +380,20 @@ class PeerCG(DistCG):
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.rbuf_pap = torch.zeros(ncols, dtype=dtype, device=dev)
         self.tmp = None
-        # fused iteration (default): the cross-GPU barriers ride inside the SpMM launches and the two all-reduces inside the
-        # r / (p, x) update kernels, all keyed by the iteration counter in ``state`` -> 2 nu + 2... = nu + 2 launches.
-        import os
-        self.fused = os.environ.get("MGP_PEER_FUSED", "1") != "0" and self.ld <= 128 and (self.ld & (self.ld - 1)) == 0
-        if self.fused:
+        scal = solvers.S_NARR * ncols
+        self.iter_scalar = self.state[scal + solvers.K_ITER:]
+        self.done_scalar = self.state[scal + solvers.K_DONE:]
+        if mode in ("cg1", "fused"):
             self.red2, self.red2_ptrs = self.mem.alloc((2 * 2 * self.world * 128,), dtype)
-            nflag = op.nu + 2                                        # one flag array per SpMM stage + p^T A p + |r|^2
+            nflag = op.nu + 2
             self.flags2, base = self.mem.alloc((nflag, 64), torch.int32)
             self.flag_tabs = [(base + 64 * 4 * i).contiguous() for i in range(nflag)]
-            self.iter_scalar = self.state[solvers.S_NARR * ncols + solvers.K_ITER:]
+        if mode == "cg1":
+            # r is the vector the peers read (source of the first SpMM); p, s, x, w stay local
+            self.r, self.r_ptrs = self.mem.alloc((n_sym, self.ld), dtype)
+            self.s = torch.zeros((op.n_loc, self.ld), dtype=dtype, device=dev)
+            self.gamma_loc = torch.zeros(ncols, dtype=dtype, device=dev)
+            self.tickets = torch.zeros(8 * max(op.nu, 1), dtype=torch.int32, device=dev)     # one 32-byte slot per SpMM stage
         self.mem.sync()
 
     # -- building blocks -----------------------------------------------------------------------------------------------
@@ -366,7 +408,7 @@ class PeerCG(DistCG):
         fl = c_float if self.dt == torch.float32 else c_double
         rbuf = self.rbuf if rbuf is None else rbuf
         _lib.call("mgp_cg_peer_scalars_" + _lib.suffix(self.dt), ptr(self.state), ptr(rbuf), c_int32(self.c), c_int32(what),
-                  fl(self.tol), fl(self.eps), fl(self.stop), c_int32(self.max_iter), c_int32(0), None, c_int32(0),
+                  fl(self.tol), fl(self.eps), fl(self.stop), c_int32(self.max_iter), c_int32(self.n_tridiag_iter), None, c_int32(0),
                   ptr(self.red_ptrs), ptr(self.flag_ptrs), ptr(self.epoch), c_int32(self.rank), c_int32(self.world), stream())
 
     def _matvec(self):
@@ -385,11 +427,37 @@ class PeerCG(DistCG):
                            peer_sync=(self.rank, self.flag_tabs[s], self.iter_scalar) if self.fused else None)
             src, src_ptrs = dst, dst_ptrs
 
+    def _matvec_cg1(self):
+        """w (= self.v) <- P r; the last launch ships (r.w, |r|^2) partials to every rank.  Flag tables: [0] "r complete",
+        [1 .. nu-1] "intermediate vector s complete", [nu] "dot partials shipped"."""
+        from . import _lib, graph
+        op, c, n_loc, nu = self.op, self.c, self.op.n_loc, self.op.nu
+        src, src_ptrs = self.r, self.r_ptrs
+        for s in range(nu):
+            last = s == nu - 1
+            dst, dst_ptrs = (self.v, None) if last else self.tmps[s]
+            ext = _lib.wi_ext(done_flag=self.done_scalar, wait_flags=self.flag_tabs[s],
+                              publish_flags=None if last else self.flag_tabs[s + 1], ticket=self.tickets[8 * s:],
+                              red_ptrs=self.red2_ptrs if last else None, red_flags=self.flag_tabs[nu] if last else None,
+                              ship_extra=self.gamma_loc if last else None, ship_ncols=c if last else 0)
+            graph.lap_spmm(op.st, op.a, op.diag, src[:n_loc, :c], shift=op.shift, out=dst[:n_loc, :c],
+                           dot_with=self.r[:n_loc, :c] if last else None, dot_out=self.rbuf_pap if last else None,
+                           peer_x=src_ptrs, peer_ext=(self.rank, self.iter_scalar, ext))
+            src, src_ptrs = dst, dst_ptrs
+
     def _iteration(self):
         from . import _lib
         from ._lib import c_int32, c_int64, ptr, stream
         sfx = _lib.suffix(self.dt)
         n_loc, c, ld = self.op.n_loc, self.c, self.ld
+        if self.mode == "cg1":
+            nu = self.op.nu
+            self._matvec_cg1()
+            _lib.call("mgp_cg_peer_cgstep_" + sfx, ptr(self.x), ptr(self.r), ptr(self.p), ptr(self.s), ptr(self.v), c_int64(ld),
+                      c_int64(n_loc), c_int32(c), ptr(self.state), ptr(self.hist), c_int32(self.max_hist), ptr(self.ws),
+                      ptr(self.gamma_loc), ptr(self.red2_ptrs), ptr(self.flag_tabs[nu]), ptr(self.flag_tabs[0]),
+                      c_int32(self.rank), c_int32(self.world), stream())
+            return
         self._matvec()
         if self.fused:
             nu = self.op.nu
@@ -410,14 +478,53 @@ class PeerCG(DistCG):
     def _allreduce_rbuf(self):
         pass                                                     # fused into _scalars
 
+    def _after_init(self):
+        """cg1: the initial residual is complete on this rank -> local |r_0|^2 for the first shipment, s = 0, publish r."""
+        if self.mode != "cg1":
+            return
+        from . import _lib
+        from ._lib import c_int32, ptr, stream
+        import ctypes
+        self.gamma_loc.copy_(self.rbuf)                          # cg_dist_init left this rank's |r_0|^2 column sums there
+        self.s.zero_()
+        _lib.call("mgp_peer_publish", ptr(self.flag_tabs[0]), ctypes.c_uint32(1), c_int32(self.rank), c_int32(self.world), stream())
+
     def solve(self, b_loc: torch.Tensor):
-        if self.fused:
+        if self.mode in ("cg1", "fused"):
             # the iteration-keyed flags restart from zero every solve: nobody may still be publishing into them (barrier),
             # and nobody may publish before everyone has zeroed (barrier)
             self._barrier()
             self.flags2.zero_()
+            if self.hist is not None:
+                self.hist.zero_()
             self._barrier()
         return super().solve(b_loc)
+
+    def tridiagonals(self, info):
+        """Lanczos tridiagonals of the first ``n_tridiag`` columns from the recorded CG coefficients (identical on every rank)."""
+        from . import solvers
+        k_done = info["iterations"]
+        rows = k_done - 1 if info["converged"] else k_done
+        rows = max(1, min(rows, self.n_tridiag_iter))
+        return solvers._tridiag_from_hist(self.hist.cpu(), rows, self.n_tridiag, self.dt).to(self.dev)
+
+
+def _collectives_note(cg, transport, nu):
+    if transport != "peer":
+        return {"halo_all_to_all": nu, "all_reduce": 2}
+    mode = getattr(cg, "mode", "unfused")
+    halo = "read from the owners' vectors over NVLink inside the SpMM"
+    if mode == "cg1":
+        return {"launches": nu + 1, "sync_points": nu + 1,
+                "all_reduce": "1 (Chronopoulos-Gear single-reduction CG): (r.w, |r|^2) partials shipped by the last block of the last "
+                              "SpMM launch, added in rank order at the start of the one vector kernel",
+                "barrier": f"{nu} 'vector complete' flags, published by the last block of the PRODUCING kernel, waited for at the "
+                           "consumer's first remote halo row", "halo": halo}
+    if mode == "fused":
+        return {"launches": nu + 2, "sync_points": nu + 2,
+                "barrier": "inside the SpMM launches (flags over NVLink, published at kernel start, waited on at the first remote halo row)",
+                "all_reduce": "2, inside the r / (p, x) update kernels (partials shipped to every peer)", "halo": halo}
+    return {"peer_barrier": nu, "peer_allreduce_fused_with_scalars": 2, "halo": halo}
 
 
 def dist_cg(op: DistPrecision, b_loc: torch.Tensor, tolerance=1e-6, eps=1e-10, stop_updating_after=1e-10, max_iter=1000,
@@ -523,11 +630,22 @@ def bench_main(args, CFG, clock_sampler=None):
     ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = _lib.launch_count()
-    # check against the global residual
+    # check against the global residual and against the SINGLE-GPU solve of the same system (every rank holds the replicated
+    # operator; rank 0 runs solvers.linear_cg on it after the timed region)
     x_all = [torch.empty((part.range(r)[1] - part.range(r)[0], c), device=dev) for r in range(world)]
     dist.all_gather(x_all, xs.contiguous())
     sol = gst.to_external(torch.cat(x_all))
     true_rel = float(((prec.matmul(sol) - B).double().norm(dim=0) / B.double().norm(dim=0)).mean())
+    vs_single = None
+    if rank == 0:
+        from . import settings, solvers
+        with settings.cg_polish(False):
+            ref, rinfo = solvers.linear_cg(prec, B, tolerance=CFG["tol"], max_iter=CFG["max_iter"], return_info=True)
+        err = ((sol - ref).double().norm(dim=0) / ref.double().norm(dim=0))
+        vs_single = {"single_gpu_iterations": int(rinfo["iterations"]), "solution_rel_diff_max": float(err.max()),
+                     "solution_rel_diff_mean": float(err.mean()), "within_1e-4": bool(float(err.max()) <= 1e-4)}
+        del ref
+    dist.barrier()
     # e2e: host buffers in, host result out (each rank moves its own block)
     Bh = b_loc.cpu().pin_memory(); Xh = torch.empty_like(Bh).pin_memory()
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
@@ -539,27 +657,26 @@ def bench_main(args, CFG, clock_sampler=None):
     dist.barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, min(args.steps, 2))
     if rank == 0:
-        out = {"metric": "precision_cg_solve_time", "value": round(float(ms), 3), "unit": "ms", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(ms), 3), "higher_is_better": False,
+        iters = int(info["iterations"])
+        unit = "CG iterations/s (N=1M, k=32, nu=2, 16 RHS per iteration)"
+        out = {"metric": "precision_cg_iterations_per_s", "value": round(iters / (float(ms) * 1e-3), 1), "unit": unit, "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(ms), 3), "solve_ms": round(float(ms), 3),
+               "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": CFG["workload"], "n": n, "k": k, "edges_M": m, "nu": CFG["nu"], "kappa": CFG["kappa"],
-                          "eps": round(eps, 6), "rhs": c, "tol": CFG["tol"], "partition": "contiguous row blocks of the Morton order",
+               "config": {"workload": CFG["workload"], "n": n, "k": k, "edges_M": m, "nnz": 2 * m, "nu": CFG["nu"], "kappa": CFG["kappa"],
+                          "eps": round(eps, 6), "rhs": c, "tol": CFG["tol"], "normalization": CFG["normalization"],
+                          "self_loops": CFG["self_loops"], "partition": "contiguous row blocks of the Morton order",
                           "halo_rows_rank0": int(op.plan.halo_ids.numel()), "rows_rank0": int(op.n_loc),
                           "l2": "inputs larger than L2 at 1-2 GPUs; at 8 GPUs a rank's share (~50 MB) is L2 resident (strong scaling)"},
-               "cg_iterations": info["iterations"], "cg_converged": bool(info["converged"]),
-               "cg_true_relative_residual": true_rel, "knn_build_s": round(t_knn, 4),
-               "e2e": {"value": round(e2e_ms, 3), "unit": "ms", "h2d_bytes_per_step": int(Bh.numel() * 4 * world),
-                       "d2h_bytes_per_step": int(Xh.numel() * 4 * world)},
+               "cg_iterations": iters, "cg_converged": bool(info["converged"]),
+               "cg_true_relative_residual": true_rel, "parity_vs_single_gpu": vs_single, "knn_build_s": round(t_knn, 4),
+               "e2e": {"value": round(iters / (e2e_ms * 1e-3), 1), "unit": unit, "solve_ms": round(e2e_ms, 3),
+                       "h2d_bytes_per_step": int(Bh.numel() * 4 * world), "d2h_bytes_per_step": int(Xh.numel() * 4 * world)},
                "gpu_launches": int(launches),
                "clocks": clocks,
                "transport": transport,
-               "collectives_per_iteration": (
-                   ({"launches": CFG["nu"] + 2, "barrier": "inside the SpMM launches (flags over NVLink, waited on at the first remote halo row)",
-                     "all_reduce": "2, inside the r / (p, x) update kernels (partials shipped to every peer)",
-                     "halo": "read from the owners' vectors over NVLink inside the SpMM"} if getattr(cg, "fused", False) else
-                    {"peer_barrier": CFG["nu"], "peer_allreduce_fused_with_scalars": 2,
-                     "halo": "read from the owners' vectors over NVLink inside the SpMM"})
-                   if transport == "peer" else {"halo_all_to_all": CFG["nu"], "all_reduce": 2})}
+               "peer_mode": getattr(cg, "mode", None),
+               "collectives_per_iteration": _collectives_note(cg, transport, CFG["nu"])}
         print(json.dumps(out))
     dist.barrier()
     return None

@@ -421,6 +421,9 @@ class GraphStructure:
         cache = self.__dict__.setdefault("_layout_cache", [])
         for k, ref, ver, out in cache:
             if k == kind and ref.data_ptr() == a.data_ptr() and ver == a._version and ref.dtype == a.dtype and ref.numel() == a.numel():
+                log = self.__dict__.get("_layout_log")
+                if log is not None:
+                    log.append(out)
                 return out
         t = self.tiles
         sfx = _lib.suffix(a.dtype)
@@ -434,6 +437,9 @@ class GraphStructure:
             _lib.call("mgp_lap_wi_values_" + sfx, ptr(self.rowptr), ptr(t["wptr"]), ptr(a), c_int64(self.n), ptr(out), stream())
         cache.append((kind, a.detach(), a._version, out))
         del cache[:-4]
+        log = self.__dict__.get("_layout_log")
+        if log is not None:
+            log.append(out)
         return out
 
     # -- experimental quad-row streams (lap_spmm_quad.cu; SPMM_KERNEL = "quad" only) -------------------------------------
@@ -516,11 +522,15 @@ class GraphStructure:
         """Per-directed-entry copy of the per-edge squared distances (cached per (storage, dtype))."""
         key = (val.data_ptr(), val.dtype, val._version)
         hit = self._d2.get(key)
+        if hit is not None:
+            hit = hit[0]
         if hit is None:
             v = val.detach().reshape(-1).contiguous()
             out = torch.empty(self.nnz, dtype=v.dtype, device=self.device)
             _lib.call("mgp_gather_edge_" + _lib.suffix(v.dtype), ptr(v), ptr(self.eid), c_int64(self.nnz), ptr(out), stream())
-            self._d2 = {key: out}  # keep only the latest
+            # keep only the latest; the entry holds ``val`` itself so its address cannot be recycled (by the caching
+            # allocator, for another edge-value tensor of the same size) while the key is live
+            self._d2 = {key: (out, val)}
             hit = out
         return hit
 
@@ -589,11 +599,14 @@ def _note_kernel(name):
 
 
 def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
-             x_external=False, y_external=False, peer_x=None, peer_sync=None):
+             x_external=False, y_external=False, peer_x=None, peer_sync=None, peer_ext=None, done_flag=None):
     """Y = post .* ((diag + shift) .* (pre .* X) - A (pre .* X)).  ``x``: [n, C] CUDA tensor with unit column stride.
 
     ``peer_x``: int64 device tensor of every rank's X base pointer (row-partitioned multi-GPU, see distributed.PeerCG);
-    ``peer_sync`` = (rank, flag pointer table, epoch scalar) fuses the cross-GPU barrier into the launch.
+    ``peer_sync`` = (rank, flag pointer table, epoch scalar) fuses the cross-GPU barrier into the launch;
+    ``peer_ext`` = (rank, epoch scalar, ``_lib.wi_ext(...)``) selects the extended hooks of mgp_lap_spmm_wi_ex instead (lazy
+    wait / publish-at-end flags, shipping of the dot partials); ``done_flag``: device scalar that turns the launch into a
+    no-op when non-zero (warp-interleaved kernel only; other kernels ignore it and compute).
     ``a, diag, pre, post`` are in the structure's row order.  ``x_external`` / ``y_external``: X (and ``dot_with``) / Y are
     in the caller's row order (only matters when the structure is internally permuted)."""
     if x.dim() != 2 or x.shape[0] < st.n:   # a row-partitioned structure reads [own rows | halo rows]: more rows than it writes
@@ -665,15 +678,28 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
         if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi") or peer_x is not None):
             aw = st.wi_values(a)
             hcol = t["hcol_peer"] if peer_x is not None else t["hcol"]
-            rc = _lib.call_rc("mgp_lap_spmm_wi_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag),
-                              ptr(t["hptr"]), ptr(hcol), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
-                              c_int32(t["wnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
-                              ptr(st.perm32 if x_external else None),
-                              ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
-                              c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws),
-                              ptr(peer_x), c_int32(0 if peer_x is None else int(peer_x.numel())),
-                              c_int32(0 if peer_sync is None else int(peer_sync[0])), ptr(None if peer_sync is None else peer_sync[1]),
-                              ptr(None if peer_sync is None else peer_sync[2]), stream())
+            if peer_ext is not None or done_flag is not None:
+                import ctypes
+                ext = peer_ext[2] if peer_ext is not None else _lib.wi_ext(done_flag=done_flag)
+                rc = _lib.call_rc("mgp_lap_spmm_wi_ex_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag),
+                                  ptr(t["hptr"]), ptr(hcol), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
+                                  c_int32(t["wnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
+                                  ptr(st.perm32 if x_external else None),
+                                  ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
+                                  c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws),
+                                  ptr(peer_x), c_int32(0 if peer_x is None else int(peer_x.numel())),
+                                  c_int32(0 if peer_ext is None else int(peer_ext[0])),
+                                  ptr(None if peer_ext is None else peer_ext[1]), ctypes.byref(ext), stream())
+            else:
+                rc = _lib.call_rc("mgp_lap_spmm_wi_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag),
+                                  ptr(t["hptr"]), ptr(hcol), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
+                                  c_int32(t["wnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
+                                  ptr(st.perm32 if x_external else None),
+                                  ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
+                                  c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws),
+                                  ptr(peer_x), c_int32(0 if peer_x is None else int(peer_x.numel())),
+                                  c_int32(0 if peer_sync is None else int(peer_sync[0])), ptr(None if peer_sync is None else peer_sync[1]),
+                                  ptr(None if peer_sync is None else peer_sync[2]), stream())
             if rc == 0:
                 _note_kernel("lap_spmm_wi_kernel")
                 return out

@@ -61,25 +61,39 @@ class GraphLaplacianOperator(LinearOperator):
             self._mgp_cache["structure"] = st
         return st
 
+    def _grad_mode(self) -> bool:
+        """True when results must carry the autograd graph back to ``graphbandwidth``."""
+        eps = self.graphbandwidth
+        return torch.is_grad_enabled() and torch.is_tensor(eps) and eps.requires_grad
+
     def _values(self):
-        """(deg_unnorm, deg, diag, a_csr) for the current bandwidth; differentiable w.r.t. ``graphbandwidth``."""
+        """(deg_unnorm, deg, diag, a_csr) for the current bandwidth; differentiable w.r.t. ``graphbandwidth``.
+
+        Two cache slots: the differentiable build (grad mode, bandwidth requires grad) and the plain one.  A result built
+        under ``no_grad`` (the CG / Lanczos drivers) is never handed to a differentiable caller -- that silently dropped
+        the bandwidth gradient of ``solve`` / ``inv_quad_logdet`` / ``logdet`` on a fresh operator."""
+        if self._grad_mode():
+            v = self._mgp_cache.get("values_grad")
+            if v is None:
+                from ..autograd import lap_values_autograd
+                st = self.structure
+                v = lap_values_autograd(st, st.d2csr(self.x), self.graphbandwidth, bool(self.self_loops))
+                self._mgp_cache["values_grad"] = v
+                self._mgp_cache.setdefault("values", tuple(t.detach() for t in v))   # same memory: one value build serves both
+            return v
         v = self._mgp_cache.get("values")
         if v is None:
             st = self.structure
-            d2 = st.d2csr(self.x)
-            eps = self.graphbandwidth
-            if torch.is_grad_enabled() and torch.is_tensor(eps) and eps.requires_grad:
-                from ..autograd import lap_values_autograd
-                v = lap_values_autograd(st, d2, eps, bool(self.self_loops))
-            else:
-                v = graph.lap_values(st, d2, eps, bool(self.self_loops))
+            v = graph.lap_values(st, st.d2csr(self.x), self.graphbandwidth, bool(self.self_loops))
             self._mgp_cache["values"] = v
         return v
 
     def _memo(self, name, fn):
-        if name not in self._mgp_cache:
-            self._mgp_cache[name] = fn()
-        return self._mgp_cache[name]
+        # results derived from the value build exist per grad mode, like the values themselves
+        key = name + "#g" if self._grad_mode() else name
+        if key not in self._mgp_cache:
+            self._mgp_cache[key] = fn()
+        return self._mgp_cache[key]
 
     # ---- the reference's cached properties (:52-106) -----------------------------------------------------------------
     @property
@@ -150,14 +164,14 @@ class GraphLaplacianOperator(LinearOperator):
     def _mgp_structure(self):
         return self.structure
 
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp=None, dot_with=None, dot_out=None, ncols=None):
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp=None, dot_with=None, dot_out=None, ncols=None, done_flag=None):
         if ncols is not None:
             x, out = x[:, :ncols], out[:, :ncols]
         with torch.no_grad():
             _, _, diag, a = self._values()
             pre, post = self._pre_post()
             graph.lap_spmm(self.structure, a.detach(), diag.detach(), x, pre=pre, post=post, out=out,
-                           dot_with=dot_with, dot_out=dot_out)
+                           dot_with=dot_with, dot_out=dot_out, done_flag=done_flag)
         return out
 
     def _size(self):
@@ -171,8 +185,9 @@ class GraphLaplacianOperator(LinearOperator):
 
     def _symmetric_twin(self):
         tw = GraphLaplacianOperator(self.x, self.idx, self.operator_dimension, self.graphbandwidth, "symmetric", self.self_loops)
-        if "values" in self._mgp_cache:   # the value build does not depend on the normalisation
-            tw._mgp_cache["values"] = self._mgp_cache["values"]
+        for k in ("values", "values_grad"):   # the value build does not depend on the normalisation
+            if k in self._mgp_cache:
+                tw._mgp_cache[k] = self._mgp_cache[k]
         return tw
 
     # ---- eigendecomposition (:132-144) -------------------------------------------------------------------------------

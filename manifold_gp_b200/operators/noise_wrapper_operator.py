@@ -48,15 +48,15 @@ class NoiseWrapperOperator(LinearOperator):
             self._mgp_scratch = (key, torch.zeros_like(like), torch.zeros_like(like))
         return self._mgp_scratch[1], self._mgp_scratch[2]
 
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None):
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None):
         """out <- Q (x - s Q (x - s Q x)) on caller-owned [n, ld] buffers; the dot product comes out of the last inner product."""
         inner = self.operator._mgp_matvec
         u, w = self._scratch(x)
         s = self.noise.detach().to(x.dtype)
         c = x.shape[1] if ncols is None else ncols
-        inner(x, u, tmp, ncols=ncols)                                   # u = Q x
+        inner(x, u, tmp, ncols=ncols, done_flag=done_flag)                                   # u = Q x
         u[:, :c].mul_(-s).add_(x[:, :c])                                # u = x - s Q x
-        inner(u, w, tmp, ncols=ncols)                                   # w = Q u
+        inner(u, w, tmp, ncols=ncols, done_flag=done_flag)                                   # w = Q u
         w[:, :c].mul_(-s).add_(x[:, :c])                                # w = x - s Q u
-        inner(w, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols)
+        inner(w, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols, done_flag=done_flag)
         return out

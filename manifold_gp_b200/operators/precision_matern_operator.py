@@ -85,10 +85,11 @@ class PrecisionMaternOperator(LinearOperator):
         return out.squeeze(-1) if squeeze else out
 
     # ---- fused path used by the CUDA CG / Lanczos drivers (no autograd, caller-owned buffers) -------------------------
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None):
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None):
         """out[:, :ncols] <- P x[:, :ncols] on caller-owned [n, ld] buffers (unit column stride); ``tmp`` is scratch of the
         same shape (used when nu > 1).  If ``dot_out`` is given, dot_out[c] = sum_i dot_with[i,c] * out[i,c] comes out of
-        the last launch (``dot_with`` must share x's leading dimension)."""
+        the last launch (``dot_with`` must share x's leading dimension).  ``done_flag``: device scalar of the solver state; the
+        launches are no-ops once it is non-zero (CG chunks replayed past convergence)."""
         lap = self.laplacian
         st = lap.structure
         if ncols is not None:
@@ -104,7 +105,7 @@ class PrecisionMaternOperator(LinearOperator):
                 dst = out if ((self.nu - 1 - s) % 2 == 0) else tmp
                 graph.lap_spmm(st, a.detach(), diag.detach(), src, shift=shift, pre=sq if (rw and s == 0) else None,
                                post=sq if (rw and last) else None, out=dst,
-                               dot_with=dot_with if last else None, dot_out=dot_out if last else None)
+                               dot_with=dot_with if last else None, dot_out=dot_out if last else None, done_flag=done_flag)
                 src = dst
         return out
 

@@ -49,9 +49,9 @@ class ScaleWrapperOperator(LinearOperator):
     def _mgp_cache_key(self, dtype):
         return ("scale", bool(self.inverse_scale), self.scale.data_ptr(), self.scale._version) + tuple(self.operator._mgp_cache_key(dtype))
 
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None):
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None):
         """out[:, :ncols] <- s * (Q x) (or / s) in place on the caller's buffers; the fused dot product is scaled alike."""
-        self.operator._mgp_matvec(x, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols)
+        self.operator._mgp_matvec(x, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols, done_flag=done_flag)
         s = self.scale.detach().to(out.dtype)
         view = out if ncols is None else out[:, :ncols]
         if self.inverse_scale:

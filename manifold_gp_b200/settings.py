@@ -127,3 +127,32 @@ class cg_cuda_graph:
     def __exit__(self, *exc):
         cg_cuda_graph._global_value = self.prev
         return False
+
+
+class cg_polish:
+    """One true-residual correction after a converged fp32 CG solve (``"auto"``, default), always (``True``) or never
+    (``False``).
+
+    linear_cg (and the reference's fp32 mBCG with it) stops on the RECURRENCE residual; over ~10^3 fp32 iterations of an
+    operator with condition number ~3 * 10^4 the recurrence drifts from b - A x (cfg-C: recurrence 1e-6, true residual 2.3e-4).
+    The drift sits in the high modes, which CG removes in a handful of iterations: the polish evaluates r = b - A x once,
+    solves A d = r with the same kernels (>= 11 iterations by the published minimum-iteration rule) and returns x + d.
+    ``"auto"`` polishes fp32 solves that converged with tolerance <= 1e-4; the iteration counts / tridiagonals reported are
+    those of the main run (SLQ is unaffected), ``info["polish"]`` carries the extra iterations and the residuals."""
+    _global_value = "auto"
+
+    @classmethod
+    def value(cls):
+        return cls._global_value
+
+    def __init__(self, state="auto"):
+        self.state = state
+
+    def __enter__(self):
+        self.prev = cg_polish._global_value
+        cg_polish._global_value = self.state
+        return self
+
+    def __exit__(self, *exc):
+        cg_polish._global_value = self.prev
+        return False

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import warnings
 
+import math
 import os
 import time
 
@@ -91,11 +92,12 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
               c_int32(n_tridiag_iter if n_tridiag else 0), ptr(state), ptr(ws), stream())
     pap = state[S_PAP * c:(S_PAP + 1) * c]
     hist_p, hist_n = ptr(hist), c_int32(max_hist if n_tridiag else 0)
+    done_flag = state[S_NARR * c + K_DONE:]     # the SpMM launches of chunks replayed past convergence are no-ops too
 
     def iteration():
         # matvec (p^T A p out of the last SpMM launch) -> r -= alpha v, scalars -> x += alpha p, p = r + beta p
         if fused:
-            op._mgp_matvec(p, v, tmp, dot_with=p, dot_out=pap, ncols=c)
+            op._mgp_matvec(p, v, tmp, dot_with=p, dot_out=pap, ncols=c, done_flag=done_flag)
             have_pap = 1
         else:
             with torch.no_grad():
@@ -149,11 +151,19 @@ def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter,
             if use_graph and max_iter - k >= check:
                 _tc = time.perf_counter()
                 before = _lib.launch_count()
-                cuda_graph = _capture(iteration, check)
+                # the captured launches bake in raw pointers to the value layouts the structure hands out (st.wi_values /
+                # padded_values: a 4-deep LRU owned by the structure).  The cache entry must own them, or a layout evicted by
+                # other bandwidths could be freed / recycled under a graph that still replays it.
+                if st is not None:
+                    st.__dict__["_layout_log"] = []
+                try:
+                    cuda_graph = _capture(iteration, check)
+                finally:
+                    keep = st.__dict__.pop("_layout_log", None) if st is not None else None
                 launches_per_replay = _lib.launch_count() - before        # kernels of ours inside one replay
                 _lib._dll.mgp_add_launch_count(-launches_per_replay)      # the capture pass itself executed nothing
                 if entry is not None:
-                    entry["graph"], entry["launches"] = cuda_graph, launches_per_replay
+                    entry["graph"], entry["launches"], entry["keepalive"] = cuda_graph, launches_per_replay, keep
                 if _dbg:
                     _t["capture"] = time.perf_counter() - _tc
         elif len(pending) == _FLAG_DEPTH:
@@ -240,6 +250,32 @@ def _tridiag_from_hist(hist, n_rows, n_tridiag, dtype):
     return t.permute(2, 0, 1).contiguous().to(dtype)
 
 
+_in_polish = [False]
+
+
+def _polish(op, rhs, x, tolerance, max_iter, eps, stop_updating_after):
+    """x + d with A d = b - A x (see ``settings.cg_polish``).  The correction solve runs to ``tolerance * |b| / |r|`` per the
+    published mean-over-columns rule, i.e. until the correction's recurrence residual is ``tolerance`` relative to b."""
+    with torch.no_grad():
+        r = rhs - op._matmul(x)
+        bn = rhs.norm(dim=0).clamp_min(torch.finfo(rhs.dtype).tiny)
+        rel = r.norm(dim=0) / bn
+        before = float(rel.mean())
+        out = {"true_residual_before": before, "iterations": 0}
+        if not (before > tolerance) or not math.isfinite(before):
+            return x, out
+        _in_polish[0] = True
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                d, dinfo = linear_cg(op, r, tolerance=min(0.5, tolerance / before), eps=eps, stop_updating_after=stop_updating_after,
+                                     max_iter=max(1, min(max_iter, 200)), max_tridiag_iter=0, return_info=True)
+        finally:
+            _in_polish[0] = False
+        out["iterations"] = int(dinfo["iterations"])
+        return x + d, out
+
+
 def linear_cg(op, rhs, n_tridiag=0, tolerance=None, eps=1e-10, stop_updating_after=1e-10, max_iter=None,
               max_tridiag_iter=None, return_info=False):
     """CUDA mBCG.  ``op`` is a LinearOperator (``_matmul``; the fused path is used when it offers ``_mgp_matvec``).
@@ -292,10 +328,17 @@ def linear_cg(op, rhs, n_tridiag=0, tolerance=None, eps=1e-10, stop_updating_aft
         if c0 == 0:
             hist0 = h
     result = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+    polish = settings.cg_polish.value()
+    want_polish = (polish is True) or (polish == "auto" and rhs.dtype == torch.float32 and float(tolerance) <= 1e-4)
+    polish_info = None
+    if want_polish and not _in_polish[0] and all(i["converged"] for i in infos) and all(i["iterations"] > 0 for i in infos):
+        result, polish_info = _polish(op, rhs, result, float(tolerance), int(n_iter), float(eps), float(stop_updating_after))
     info = infos[0] if len(infos) == 1 else CGInfo(
         iterations=max(i["iterations"] for i in infos), converged=all(i["converged"] for i in infos),
         mean_residual=sum(i["mean_residual"] for i in infos) / len(infos),
         residual_norm=torch.cat([i["residual_norm"] for i in infos]))
+    if polish_info is not None:
+        info["polish"] = polish_info
     if not info["converged"] and n_iter > 0:
         warnings.warn("CG terminated in {} iterations with average residual norm {} which is larger than the tolerance "
                       "of {} specified by settings.cg_tolerance.".format(info["iterations"], info["mean_residual"], tolerance),

@@ -1,0 +1,98 @@
+"""GPU parity of the multi-GPU CG transports on ONE device (process group of size 1: every flag / reduction / halo path of the
+peer-memory kernels runs, with the rank's own memory as the "peer"): the single-reduction (Chronopoulos-Gear) iteration and the
+round-1 fused two-reduction iteration against solvers.linear_cg and the oracle's mBCG -- iteration counts, solutions, the
+Lanczos tridiagonals recorded from the CG coefficients.  The 2-rank protocol is covered on CPU (tests/test_distributed_cpu.py,
+gloo) and on 2 / 8 GPUs by profiles/dist_check2.py (numbers under profiles/)."""
+import os
+import socket
+import warnings
+
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def pg1():
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+        created = True
+    yield dist
+    if created:
+        dist.destroy_process_group()
+
+
+def _problem(n, k, dtype, nu=2, kappa=0.7, seed=0):
+    import manifold_gp_b200 as mgp
+    x = oracle.datasets.torus(n, seed=seed)
+    knn = mgp.NearestNeighbors(x.to(DEV))
+    idx, val = knn.graph(k)
+    d2, _ = knn.search(x[:2048].to(DEV).contiguous(), k)
+    eps = float(d2[:, k - 1].sqrt().median())
+    lap = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, torch.tensor([[eps]], dtype=dtype, device=DEV), "symmetric", True)
+    prec = mgp.PrecisionMaternOperator(lap, nu, torch.tensor([[kappa]], dtype=dtype, device=DEV))
+    return lap, prec
+
+
+@pytest.mark.parametrize("dtype,mode", [(torch.float64, "cg1"), (torch.float32, "cg1"), (torch.float64, "fused")])
+def test_peer_cg_matches_linear_cg(pg1, dtype, mode):
+    from manifold_gp_b200 import distributed as D, solvers
+    n, k, c, nu = 20000, 12, 16, 2
+    lap, prec = _problem(n, k, dtype, nu=nu)
+    gst = lap.structure
+    assert gst.tiles is not None and "wptr" in gst.tiles        # the peer path needs the warp-interleaved streams
+    _, _, diag, a = lap._values()
+    part = D.RowPartition(n, 1, align=gst.TILE_ROWS)
+    op = D.DistPrecision(gst, diag, a, prec._shift().to(dtype), nu, part, 0)
+    B = torch.randn(n, c, dtype=dtype, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    tol = 1e-6 if dtype == torch.float64 else 1e-5     # (the published eps = 1e-10 masks stall any CG below ~1e-6: |r|^2 < eps)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref, rinfo = solvers.linear_cg(prec, B, tolerance=tol, max_iter=3000, return_info=True)
+    cg = D.PeerCG(op, c, dtype, tolerance=tol, max_iter=3000, mode=mode)
+    assert cg.mode == mode
+    for rep in range(2):                                         # second solve replays the captured graph from the start
+        xs, info = cg.solve(gst.to_internal(B).contiguous())
+        sol = gst.to_external(xs)
+        assert info["converged"]
+        if dtype == torch.float64:
+            assert info["iterations"] == rinfo["iterations"], (info, dict(rinfo))
+            assert rel_err(sol, ref) < 1e-6
+        else:
+            assert abs(info["iterations"] - rinfo["iterations"]) <= max(3, rinfo["iterations"] // 50)
+            assert rel_err(sol, ref) < 2e-3
+        true_rel = ((prec._matmul(sol) - B).norm(dim=0) / B.norm(dim=0)).max()
+        assert float(true_rel) < (1e-5 if dtype == torch.float64 else 5e-3)
+
+
+def test_peer_cg1_tridiagonals_match_linear_cg(pg1):
+    """The CG coefficients recorded by the single-reduction kernel give the same Lanczos tridiagonals (SLQ log-det input) as
+    solvers.linear_cg, which is pinned against the oracle's mBCG in test_gpu_solvers.py."""
+    from manifold_gp_b200 import distributed as D, solvers
+    dtype = torch.float64
+    n, k, c, nu, nt = 12000, 10, 8, 1, 6
+    lap, prec = _problem(n, k, dtype, nu=nu, kappa=1.1, seed=3)
+    gst = lap.structure
+    _, _, diag, a = lap._values()
+    part = D.RowPartition(n, 1, align=gst.TILE_ROWS)
+    op = D.DistPrecision(gst, diag, a, prec._shift().to(dtype), nu, part, 0)
+    B = torch.randn(n, c, dtype=dtype, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref, t_ref, rinfo = solvers.linear_cg(prec, B, n_tridiag=nt, tolerance=1e-6, max_iter=500, max_tridiag_iter=30, return_info=True)
+    cg = D.PeerCG(op, c, dtype, tolerance=1e-6, max_iter=500, mode="cg1", n_tridiag=nt, max_tridiag_iter=30)
+    xs, info = cg.solve(gst.to_internal(B).contiguous())
+    assert info["iterations"] == rinfo["iterations"] and info["converged"]
+    t = cg.tridiagonals(info)
+    assert t.shape == t_ref.shape
+    assert rel_err(t, t_ref) < 1e-8
+    assert rel_err(gst.to_external(xs), ref) < 1e-8
