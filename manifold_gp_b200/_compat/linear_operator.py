@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import torch
 
-try:  # pragma: no cover - not installed in this image
+try:
     from linear_operator import LinearOperator as _RealLinearOperator
     HAVE_LINEAR_OPERATOR = True
 except Exception:
@@ -148,7 +148,17 @@ class LocalLinearOperator:
     def detach(self):
         return self
 
-    # ---- solves ---------------------------------------------------------------------------------------------------
+
+
+class CudaSolverMixin:
+    """``solve / inv_quad_logdet / inv_quad / logdet / diagonalization`` routed to the CUDA drivers of ``manifold_gp_b200.solvers``.
+
+    Placed BEFORE the base class in the MRO of every operator of this package, so the routing also holds when the real
+    ``linear_operator.LinearOperator`` is the base: without it, ``op.solve`` / ``op.inv_quad_logdet`` (utils/train_model.py:55,67-68,
+    precision_matern_operator.py:53, schur_complement_operator.py:28) would run linear_operator's eager ``linear_cg`` -- ten small
+    launches and one host sync per iteration -- over ``_matmul``, bypassing the fused CG / Lanczos / SLQ kernels.  Dispatch rules
+    (dense Cholesky / eigh when size <= ``settings.max_cholesky_size``) are linear_operator's own."""
+
     def solve(self, right_tensor, left_tensor=None):
         from .. import solvers
         out = solvers.solve(self, right_tensor)
@@ -169,10 +179,11 @@ class LocalLinearOperator:
         return solvers.diagonalization(self, method=method)
 
 
-if HAVE_LINEAR_OPERATOR:  # pragma: no cover
-    LinearOperator = _RealLinearOperator
-else:
-    LinearOperator = LocalLinearOperator
+class LinearOperator(CudaSolverMixin, _RealLinearOperator if HAVE_LINEAR_OPERATOR else LocalLinearOperator):
+    """Base class of every operator in ``manifold_gp_b200.operators``: the real ``linear_operator.LinearOperator`` when that
+    package is importable (``isinstance`` checks of gpytorch keep working), the local stand-in otherwise -- in both cases with
+    the solver entry points of ``CudaSolverMixin`` in front (tests/test_host_logic.py runs the real-base branch against a
+    stand-in ``linear_operator`` module)."""
 
 
 class DenseEigenvectors:

@@ -2,8 +2,8 @@
 ``(Q^-1 + s I)^-1``, i.e. ``Q - s Q^2 + s^2 Q^3`` evaluated as three nested products with the wrapped operator Q
 (meaningful while ``s * |Q| < 1``; the reference's dense twin is ``test/_dense_operators.py:56-57``).
 
-Like ``ScaleWrapperOperator`` it also offers the solver drivers' buffer interface (``_mgp_matvec``, behind
-``MGP_FUSED_WRAPPERS=1``): three inner fused products and two in-place axpy passes on two cached scratch blocks."""
+Like ``ScaleWrapperOperator`` it also offers the solver drivers' buffer interface (``_mgp_matvec``; ``MGP_FUSED_WRAPPERS=0``
+switches it off): three inner fused products and two in-place axpy passes on two cached scratch blocks."""
 from __future__ import annotations
 
 from torch import Tensor

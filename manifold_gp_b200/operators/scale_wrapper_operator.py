@@ -3,8 +3,9 @@
 
 Besides the reference's ``_matmul`` (one inner product + one scaling), the wrapper can run on the solver drivers' caller-owned
 buffers (``_mgp_matvec``: no temporaries, CUDA-graph capturable, fused dot product), which is what lets the training loss's
-mBCG on ``Noise(Scale(Precision))`` use the same fused iteration as a bare precision operator.  That path is switched on with
-``MGP_FUSED_WRAPPERS=1`` (off by default until it has been validated on the GPU; the generic path is the tested one)."""
+mBCG on ``Noise(Scale(Precision))`` use the same fused iteration as a bare precision operator.  On by default since round 2
+(GPU parity against the reference's dense operators: tests/test_gpu_operators.py::test_fused_wrapper_paths_vs_reference_dense);
+``MGP_FUSED_WRAPPERS=0`` restores the generic path."""
 from __future__ import annotations
 
 import os
@@ -16,7 +17,7 @@ from .._compat.linear_operator import LinearOperator
 
 
 def fused_wrappers_enabled() -> bool:
-    return os.environ.get("MGP_FUSED_WRAPPERS", "0") == "1"
+    return os.environ.get("MGP_FUSED_WRAPPERS", "1") != "0"
 
 
 class ScaleWrapperOperator(LinearOperator):

@@ -6,6 +6,7 @@ import torch
 from torch import Tensor
 
 from .._compat.linear_operator import LinearOperator
+from .scale_wrapper_operator import fused_wrappers_enabled
 
 
 class MaskedOperator(LinearOperator):
@@ -35,6 +36,65 @@ class MaskedOperator(LinearOperator):
         return MaskedOperator(self.base._transpose_nonbatch(), self.col_mask, self.row_mask)
 
 
+class PrincipalBlockOperator(LinearOperator):
+    """K Q K + (I - K) on the FULL index space, K = diag(keep): the principal block ``Q[keep, keep]`` padded with an identity.
+
+    The reference solves with ``MaskedLinearOperator(base, ~mask, ~mask)`` on the compressed index space
+    (schur_complement_operator.py:28); the same Krylov process runs here on full-size vectors that are zero on the dropped rows
+    (right-hand side zero there => residuals, directions and iterates stay zero there, alpha / beta are identical), which lets
+    the inner solve use the fused CUDA CG (tile streams, dot epilogue, CUDA graph) of the wrapped operator unchanged: a matvec
+    is the base's fused product followed by one masking pass."""
+
+    def __init__(self, base: LinearOperator, keep: Tensor):
+        super().__init__(base, keep)
+        self.base = base
+        self.keep = keep
+        self._mgp_keep = {}
+
+    def _matmul(self, rhs):
+        squeeze = rhs.dim() == 1
+        r = rhs.unsqueeze(-1) if squeeze else rhs
+        k = self.keep.to(r.device).unsqueeze(-1)
+        kf = k.to(r.dtype)
+        out = self.base._matmul((r * kf).contiguous()) * kf + r * (1 - kf)
+        return out.squeeze(-1) if squeeze else out
+
+    def _size(self):
+        return self.base._size()
+
+    def _transpose_nonbatch(self):
+        return PrincipalBlockOperator(self.base._transpose_nonbatch(), self.keep)
+
+    # ---- solver-driver interface (see PrecisionMaternOperator._mgp_matvec) ---------------------------------------------------
+    def _native(self) -> bool:
+        inner = self.base
+        return hasattr(inner, "_mgp_matvec") and getattr(inner, "_native", lambda: True)()
+
+    def _mgp_structure(self):
+        return self.base._mgp_structure()
+
+    def _keep_internal(self, dtype):
+        """0/1 vector [n, 1] in the structure's (permuted) row order."""
+        hit = self._mgp_keep.get(dtype)
+        if hit is None:
+            st = self._mgp_structure()
+            hit = st.to_internal(self.keep.to(st.device).to(dtype).unsqueeze(-1)).contiguous()
+            self._mgp_keep[dtype] = hit
+        return hit
+
+    def _mgp_cache_key(self, dtype):
+        k = self._keep_internal(dtype)
+        return ("principal", k.data_ptr(), k._version) + tuple(self.base._mgp_cache_key(dtype))
+
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None):
+        """out <- K Q x for x that is zero on the dropped rows (the CG invariant); the fused dot product of the base launch is
+        already the masked one when ``dot_with`` is zero there (it is: CG passes p)."""
+        self.base._mgp_matvec(x, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols, done_flag=done_flag)
+        view = out if ncols is None else out[:, :ncols]
+        view.mul_(self._keep_internal(out.dtype))
+        return out
+
+
 class SchurComplementOperator(LinearOperator):
     def __init__(self, base: LinearOperator, mask: Tensor):
         super().__init__(base, mask)
@@ -45,6 +105,17 @@ class SchurComplementOperator(LinearOperator):
         mask = self.mask.to(rhs.device)   # the reference builds its all-ones mask on the CPU (:27, Appendix C.6)
         ones = torch.ones(self.base.shape[0], dtype=torch.bool, device=rhs.device)
         tmp = MaskedOperator(self.base, ones, mask)._matmul(rhs.contiguous())
+        base = self.base
+        if hasattr(base, "_mgp_matvec") and getattr(base, "_native", lambda: True)() and fused_wrappers_enabled():
+            # inner solve on the full index space with the fused CUDA CG (PrincipalBlockOperator); same iterates as :28
+            keep = ~mask
+            z = tmp * keep.unsqueeze(-1).to(tmp.dtype) if tmp.dim() == 2 else tmp * keep.to(tmp.dtype)
+            inner = self.__dict__.get("_mgp_inner")          # kept: its CG buffers / captured graph serve every outer matvec
+            if inner is None or inner.keep.device != keep.device:
+                inner = PrincipalBlockOperator(base, keep)
+                self.__dict__["_mgp_inner"] = inner
+            sol = inner.solve(z)
+            return tmp[mask] - base._matmul(sol.contiguous())[mask]
         out = MaskedOperator(self.base, ~mask, ~mask).solve(tmp[~mask])
         out = MaskedOperator(self.base, mask, ~mask)._matmul(out)
         return tmp[mask] - out

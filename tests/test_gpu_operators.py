@@ -238,6 +238,43 @@ def test_schur_vs_reference_dense(golden_k10, normalization):
         assert rel_err(sch.matmul(V[mask]), g[f"{tag}_PschurV"]) < 1e-4   # inner solve by CUDA CG
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("normalization", NORMALIZATIONS)
+def test_fused_wrapper_paths_vs_reference_dense(golden_k10, normalization, dtype):
+    """The solver drivers' buffer interface of the wrappers (``_mgp_matvec`` of Noise(Scale(Precision)), default on since round 2)
+    against the reference's dense matern_noisy_precision (golden PnoisyV; noise_wrapper_operator.py:21-22,
+    scale_wrapper_operator.py:27-28), its fused dot product, and a CUDA-CG solve through that path against a dense solve."""
+    import manifold_gp_b200 as mgp
+    g = golden_k10
+    tag = gtag(0.5, 1.3, 2, normalization, True)
+    tol = TOL[dtype]
+    _, prec, _, _ = _ops(g, 0.5, 1.3, 2, normalization, True, dtype)
+    V = torch.from_numpy(g["V"]).to(dtype).to(DEV)
+    pdiv = mgp.ScaleWrapperOperator(prec, torch.tensor(1.7, dtype=dtype, device=DEV), inverse_scale=True)
+    pn = mgp.NoiseWrapperOperator(pdiv, torch.tensor(0.02, dtype=dtype, device=DEV))
+    assert pdiv._native() and pn._native()
+    st = pn._mgp_structure()
+    c = V.shape[1]
+    ld = (c + 3) // 4 * 4
+    x = torch.zeros(V.shape[0], ld, dtype=dtype, device=DEV)
+    x[:, :c] = st.to_internal(V)
+    out, tmp = torch.zeros_like(x), torch.zeros_like(x)
+    dot = torch.zeros(c, dtype=dtype, device=DEV)
+    pn._mgp_matvec(x, out, tmp, dot_with=x, dot_out=dot, ncols=c)
+    ref = torch.from_numpy(g[f"{tag}_PnoisyV"]).to(DEV)
+    assert rel_err(st.to_external(out[:, :c]), ref) < tol * 10
+    assert rel_err(dot, (V.double() * ref.double()).sum(0)) < tol * 100
+    pm = mgp.ScaleWrapperOperator(prec, torch.tensor(1.7, dtype=dtype, device=DEV))
+    pm._mgp_matvec(x, out, tmp, dot_with=x, dot_out=dot, ncols=c)
+    assert rel_err(st.to_external(out[:, :c]), g[f"{tag}_PmulV"]) < tol * (1 if dtype == torch.float64 else 2)
+    # CG on the wrapped operator through the fused interface vs a dense solve of the same operator
+    dense = pn.to_dense().double()
+    want = torch.linalg.solve(dense, V.double())
+    with mgp.settings.max_cholesky_size(0), mgp.settings.cg_tolerance(1e-6), mgp.settings.max_cg_iterations(3000):
+        got = pn.solve(V)
+    assert rel_err(got, want) < (1e-5 if dtype == torch.float64 else 2e-3)
+
+
 def test_morton_permutation_equivalence():
     """The internal space-filling-curve reordering (attached by NearestNeighbors.graph) must not change any result:
     same operator built with and without the hint, Laplacian + precision + CG + per-node arrays."""

@@ -199,3 +199,92 @@ def test_quad_streams_lane_walk_reproduces_the_matvec():
                     if int(rows_q[slot]) >= 0:
                         Y[int(rows_q[slot])] = tot[slot]
     assert torch.allclose(Y, ref, rtol=1e-12, atol=1e-12)
+
+
+_FAKE_LINEAR_OPERATOR = '''
+import torch
+
+
+class LinearOperator:
+    """Stand-in for linear_operator.LinearOperator: representation / shape plumbing + EAGER solver entry points that must never run."""
+
+    def __init__(self, *args, **kwargs):
+        self._args, self._kwargs = args, kwargs
+
+    def representation(self):
+        out = []
+        for a in list(self._args) + list(self._kwargs.values()):
+            if torch.is_tensor(a):
+                out.append(a)
+            elif isinstance(a, LinearOperator):
+                out += list(a.representation())
+        return tuple(out)
+
+    @property
+    def shape(self):
+        return torch.Size(self._size())
+
+    @property
+    def dtype(self):
+        return next(t.dtype for t in self.representation() if t.is_floating_point())
+
+    @property
+    def device(self):
+        return self.representation()[0].device
+
+    def matmul(self, rhs):
+        return self._matmul(rhs)
+
+    def solve(self, *a, **k):
+        raise AssertionError("linear_operator's eager solve was reached")
+
+    def inv_quad_logdet(self, *a, **k):
+        raise AssertionError("linear_operator's eager inv_quad_logdet was reached")
+
+    def diagonalization(self, *a, **k):
+        raise AssertionError("linear_operator's eager diagonalization was reached")
+'''
+
+_REAL_BASE_SCRIPT = '''
+import torch, linear_operator
+import manifold_gp_b200 as mgp
+from manifold_gp_b200 import solvers
+from manifold_gp_b200._compat import linear_operator as compat
+assert compat.HAVE_LINEAR_OPERATOR and issubclass(compat.LinearOperator, linear_operator.LinearOperator)
+calls = []
+solvers.solve = lambda op, rhs: calls.append(("solve", type(op).__name__)) or rhs
+solvers.inv_quad_logdet = lambda op, **kw: calls.append(("iql", type(op).__name__)) or (torch.zeros(()), torch.zeros(()))
+solvers.diagonalization = lambda op, method=None: calls.append(("diag", type(op).__name__)) or (torch.zeros(3), compat.DenseEigenvectors(torch.zeros(6, 3)))
+n = 6
+idx = torch.tensor([[0, 1, 2, 3, 4], [1, 2, 3, 4, 5]])
+val = torch.rand(5)
+lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[0.5]]), "symmetric", True)
+prec = mgp.PrecisionMaternOperator(lap, 2, torch.tensor([[1.0]]))
+ops = [lap, prec, mgp.ScaleWrapperOperator(prec, torch.tensor(2.0)), mgp.NoiseWrapperOperator(prec, torch.tensor(0.1)),
+       mgp.SchurComplementOperator(prec, torch.tensor([True, False, True, True, False, True]))]
+rhs = torch.rand(n, 2)
+for op in ops:
+    assert isinstance(op, linear_operator.LinearOperator)
+    op.solve(rhs); op.inv_quad_logdet(inv_quad_rhs=rhs, logdet=True); op.logdet(); op.inv_quad(rhs)
+prec.diagonalization(); lap.diagonalization("lanczos", 2)
+names = [c[0] for c in calls]
+assert names.count("solve") == 5 and names.count("iql") == 15 and names.count("diag") == 2, calls
+print("REAL_BASE_OK")
+'''
+
+
+def test_cuda_solvers_stay_in_front_of_a_real_linear_operator_base(tmp_path):
+    """With ``linear_operator`` importable the operators subclass ITS LinearOperator (gpytorch's isinstance checks hold), and
+    ``solve / inv_quad_logdet / logdet / inv_quad / diagonalization`` must still reach manifold_gp_b200.solvers (the CUDA CG /
+    SLQ / Lanczos drivers), not the base class's eager loops -- reference call sites precision_matern_operator.py:53,
+    schur_complement_operator.py:28, utils/train_model.py:55,67-68."""
+    import os
+    import subprocess
+    import sys
+    pkg = tmp_path / "linear_operator"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text(_FAKE_LINEAR_OPERATOR)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(tmp_path), root, os.environ.get("PYTHONPATH", "")]))
+    r = subprocess.run([sys.executable, "-c", _REAL_BASE_SCRIPT], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "REAL_BASE_OK" in r.stdout, r.stdout + r.stderr
