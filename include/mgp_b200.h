@@ -279,6 +279,10 @@ int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double*
  *                  dot_out[0..ship_ncols) (kind 0) and ship_extra[0..ship_ncols) (kind 1, may be NULL) to
  *                  red_ptrs[dst][kind][epoch & 1][rank][128] of every rank, then red_flags[dst][rank] = epoch
  *                  (first half of a fused all-reduce; mgp_cg_peer_cgstep is the second half).
+ *   ep_coef / ep_add  epilogue algebra of the wrappers folded into the launch: Y <- coef * Y with coef = *ep_coef (device scalar;
+ *                  the dot epilogue then sees the scaled Y), and with ep_add = 1: Y <- ADD + coef * Y where ADD is passed in the
+ *                  dot_with argument (rows strided like X; no dot product on such a launch).  Replaces the elementwise passes of
+ *                  scale_wrapper_operator.py:27-28 and noise_wrapper_operator.py:21-22 (x - s Q x).
  * epoch = (unsigned)*sync_epoch + 1 (the CG iteration counter in the solver state).  No reference counterpart. */
 typedef struct mgp_wi_ext {
   const void* done_flag;
@@ -289,7 +293,8 @@ typedef struct mgp_wi_ext {
   const void* red_flags;
   const void* ship_extra;
   int32_t ship_ncols;
-  int32_t reserved;
+  int32_t ep_add;
+  const void* ep_coef;
 } mgp_wi_ext;
 int mgp_lap_spmm_wi_ex_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
                            const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,

@@ -83,6 +83,8 @@ struct WiArgs {
   const T* ship_extra;                 // second local sum to ship (kind 1), e.g. |r|^2 partials of the vector kernel; may be NULL
   int ship_ncols;                      // total number of columns to ship
   int last_pass;                       // 1 on the launch of the last column pass
+  const T* ep_coef;                    // optional epilogue: Y <- coef * Y (+ ADD) with coef = *ep_coef; the dot epilogue sees the scaled Y
+  int ep_add;                          // 1: ADD = dot_with (rows like X; no dot product on such a launch) -- y = add + coef * (A' x)
   int debug;     // timing experiments only (MGP_WI_DEBUG bit mask): 1 = consumers skip the row walk, 2 = producers skip the halo rows
                  // (same-process A/B on B200, cfg-C: 150 us full, 104 without halo copies, 90 without the walk, 62 with neither)
 };
@@ -313,7 +315,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
       const int64_t row = row0 + r;
       // operands of the epilogue that live in global memory: in flight while the stage is awaited and walked
       Vec<T, VEC> dw;
-      if (g.dot_out && !g.dot_is_x && active) {
+      if ((g.dot_out || g.ep_add) && !g.dot_is_x && active) {
         const int64_t drow = g.xmap ? (int64_t)__ldg(g.xmap + row) : row;
         dw = ldg_vec<T, VEC>(g.dot_with + drow * g.ldx + cbase);
       }
@@ -371,6 +373,12 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         Vec<T, VEC> out;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) out.v[v] = po * (d * xi.v[v] - res[v]);
+        if (g.ep_coef) {                                   // wrapper algebra folded into the launch: y = add + coef * y
+          const T cf = __ldg(g.ep_coef);
+          if (g.dot_is_x) dw = xi;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) out.v[v] = g.ep_add ? fma(cf, out.v[v], dw.v[v]) : cf * out.v[v];
+        }
         st_vec<T, VEC>(g.y + yrow * g.ldy + cbase, out);
         if (g.dot_out) {
           if (g.dot_is_x) dw = xi;
@@ -480,7 +488,7 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   MGP_CHECK_ARG(sync_flags == nullptr || (peer_x && sync_epoch && rank >= 0 && rank < npeers), "lap_spmm_wi: fused barrier needs peer X, an epoch pointer and a valid rank");
   MGP_CHECK_ARG(peer_x == nullptr || (npeers >= 1 && npeers <= 32 && xmap == nullptr), "lap_spmm_wi: peer X needs 1..32 ranks and no xmap");
   g.done = nullptr; g.wait_flags = nullptr; g.publish_flags = nullptr; g.ticket = nullptr; g.red_ptrs = nullptr;
-  g.red_flags = nullptr; g.ship_extra = nullptr; g.ship_ncols = 0; g.last_pass = 0;
+  g.red_flags = nullptr; g.ship_extra = nullptr; g.ship_ncols = 0; g.last_pass = 0; g.ep_coef = nullptr; g.ep_add = 0;
   if (ext) {
     g.done = reinterpret_cast<const T*>(ext->done_flag);
     g.wait_flags = reinterpret_cast<unsigned int* const*>(const_cast<void*>(ext->wait_flags));
@@ -490,6 +498,9 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
     g.red_flags = reinterpret_cast<unsigned int* const*>(const_cast<void*>(ext->red_flags));
     g.ship_extra = reinterpret_cast<const T*>(ext->ship_extra);
     g.ship_ncols = ext->ship_ncols;
+    g.ep_coef = reinterpret_cast<const T*>(ext->ep_coef);
+    g.ep_add = ext->ep_add ? 1 : 0;
+    MGP_CHECK_ARG(!g.ep_add || (g.ep_coef && dot_with && !dot_out), "lap_spmm_wi_ex: ep_add needs ep_coef and the ADD operand in dot_with, and excludes the dot epilogue");
     const bool sync_any = g.wait_flags || g.publish_flags || g.red_ptrs;
     MGP_CHECK_ARG(!sync_any || (peer_x && sync_epoch && rank >= 0 && rank < npeers), "lap_spmm_wi_ex: flags need peer X, an epoch pointer and a valid rank");
     MGP_CHECK_ARG(g.publish_flags == nullptr || g.ticket != nullptr, "lap_spmm_wi_ex: publish_flags needs a ticket counter");
@@ -506,11 +517,11 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   g.stages = (3 * one + rings <= kWiSmemLimit) ? 3 : 2;
   const size_t smem = g.stages * one + rings;
   if (smem > kWiSmemLimit) return MGP_EUNSUPPORTED;
-  g.dot_with = dot_out ? dot_with : nullptr;
+  g.dot_with = (dot_out || g.ep_add) ? dot_with : nullptr;
   g.dot_out = dot_out;
   g.counter = dot_out ? reinterpret_cast<unsigned int*>(dot_ws) : nullptr;
   g.partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
-  g.dot_is_x = (dot_out && dot_with == x) ? 1 : 0;
+  g.dot_is_x = ((dot_out || g.ep_add) && dot_with == x) ? 1 : 0;
   { const char* dbg = getenv("MGP_WI_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
   // producer warps: measured on B200 (cfg-C, C = 16, fp32): 4 -> 163.7 us, 8 -> 144.0, 12 -> 133.4, 16 -> 127.0 (the halo
   // cp.async issue shares the LSU queue with the consumers' shared-memory loads; more producer warps = a larger share)

@@ -146,31 +146,81 @@ class LocalStructure:
         return self._gst.padded_values(a)
 
     def wi_values(self, a):
+        if getattr(self, "_aw_persistent", None) is not None:
+            return self._aw_persistent     # DistPrecision.update_values keeps one buffer alive across bandwidths (CUDA graphs)
         return self._gst.wi_values(a)    # built from the GLOBAL rowptr / wptr: stream positions are global
 
 
 class DistPrecision:
-    """(2nu/kappa^2 + L_sym)^nu on the rows of this rank.  ``values`` = (diag[n], a[nnz]) of the GLOBAL structure."""
+    """(2nu/kappa^2 + L_sym)^nu on the rows of this rank, optionally inside the reference's Scale / Noise wrappers
+    (riemann_gp.py:32-39: Noise(Scale(P)) is the operator of the training loss).  ``values`` = (diag[n], a[nnz]) of the GLOBAL
+    structure.  With ``coef`` (device scalar c = outputscale or its reciprocal) the operator is Q = c P; with ``noise``
+    (device scalar s) it is Q - s Q^2 + s^2 Q^3 = Q (x - s Q (x - s Q x)), i.e. 3 nu chained SpMM launches whose ``x - s Q(.)``
+    combinations ride in the launches' epilogues (mgp_wi_ext.ep_coef / ep_add) -- no elementwise kernel between them.
 
-    def __init__(self, gst, diag, a, shift, nu: int, part: RowPartition, rank: int, group=None):
+    The value arrays live in buffers owned by this object (``update_values`` copies a new bandwidth's values into them), so the
+    solvers' captured CUDA graphs and peer-memory registrations survive a training step."""
+
+    def __init__(self, gst, diag, a, shift, nu: int, part: RowPartition, rank: int, group=None, coef=None, noise=None):
         lo, hi = part.range(rank)
         p0, p1 = int(gst.rowptr[lo]), int(gst.rowptr[hi])
         self.plan = HaloPlan(part, rank, gst.col[p0:p1], group=group)
         self.st = LocalStructure(gst, self.plan)
-        self.diag = diag[lo:hi]
-        self.a = a
-        self.shift = shift
+        self.gst, self.lo, self.hi = gst, lo, hi
         self.nu = nu
         self.n_loc = hi - lo
         self.n_ext = self.n_loc + int(self.plan.halo_ids.numel())
-        # the solvers' captured CUDA graphs bake in the pointer of the value layout: own it here (the structure's cache is a
-        # 4-deep LRU and may drop it while this operator is alive)
+        dt, dev = a.dtype, a.device
         t = gst.tiles
-        self._layout_keep = gst.wi_values(a) if (t is not None and "wptr" in t) else None
+        self.diag = torch.empty(self.n_loc, dtype=dt, device=dev)
+        self.shift = torch.empty(1, dtype=dt, device=dev)
+        self.coef = torch.ones(1, dtype=dt, device=dev) if (coef is not None or noise is not None) else None
+        self.ncoef = torch.zeros(1, dtype=dt, device=dev) if noise is not None else None      # -noise * coef
+        self.has_noise = noise is not None
+        if t is not None and "wptr" in t:
+            self.st._aw_persistent = torch.zeros(t["nnzw"] + 64, dtype=dt, device=dev)
+        self.update_values(diag, a, shift, coef, noise)
+
+    @property
+    def nstage(self):
+        return self.nu * (3 if self.has_noise else 1)
+
+    def update_values(self, diag, a, shift, coef=None, noise=None):
+        """New bandwidth / lengthscale / scales: same memory, new contents (nothing the kernels point at moves)."""
+        with torch.no_grad():
+            self.a = a
+            self.diag.copy_(diag[self.lo:self.hi])
+            self.shift.copy_(shift.detach().reshape(-1)[:1].to(self.shift.dtype))
+            if getattr(self.st, "_aw_persistent", None) is not None:
+                self.st._aw_persistent.copy_(self.gst.wi_values(a))
+            if self.coef is not None:
+                c = torch.ones(1, dtype=self.coef.dtype, device=self.coef.device) if coef is None else \
+                    coef.detach().reshape(-1)[:1].to(self.coef.dtype)
+                self.coef.copy_(c)
+                if self.ncoef is not None:
+                    self.ncoef.copy_(-noise.detach().reshape(-1)[:1].to(self.coef.dtype) * c)
+
+    def stage_epilogues(self):
+        """Per SpMM stage: (ep_coef tensor or None, add_source: bool).  Stage i is the (i % nu)-th Laplacian step of the
+        (i // nu)-th application of Q; the last step of an application carries the wrapper algebra."""
+        out = []
+        for i in range(self.nstage):
+            end_of_q = (i % self.nu) == self.nu - 1
+            q = i // self.nu
+            if not end_of_q or self.coef is None:
+                out.append((None, False))
+            elif self.has_noise and q < 2:
+                out.append((self.ncoef, True))          # x - s c P(.)
+            else:
+                out.append((self.coef, False))          # c P(.)
+        return out
 
     def matvec(self, p, out, tmp, ncols, dot_out=None):
-        """out[:n_loc, :ncols] <- P p  (p, tmp: [n_ext, ld] with halo rows; out: [>= n_loc, ld])."""
+        """out[:n_loc, :ncols] <- P p  (p, tmp: [n_ext, ld] with halo rows; out: [>= n_loc, ld]).  NCCL transport: bare
+        precision operator only."""
         from . import graph
+        if self.coef is not None:
+            raise RuntimeError("DistPrecision.matvec: the NCCL transport covers the bare precision operator; wrappers need PeerCG(mode='cg1')")
         src = p
         for s in range(self.nu):
             last = s == self.nu - 1
@@ -374,7 +424,12 @@ class PeerCG(DistCG):
         if n_tridiag and mode != "cg1":
             raise RuntimeError("PeerCG: the tridiagonal history is recorded by the single-reduction mode only")
         self.p, self.p_ptrs = self.mem.alloc((n_sym, self.ld), dtype)
-        self.tmps = [self.mem.alloc((n_sym, self.ld), dtype) for _ in range(max(op.nu - 1, 0))]
+        nstage = op.nstage if mode == "cg1" else op.nu
+        if mode != "cg1" and op.coef is not None:
+            raise RuntimeError("PeerCG: Scale / Noise wrappers are covered by the single-reduction mode only")
+        # intermediate vectors: a buffer may be rewritten once every peer has finished the stage that read it, which the flag
+        # waits guarantee two stages later -> three rotating buffers serve any chain length
+        self.tmps = [self.mem.alloc((n_sym, self.ld), dtype) for _ in range(min(max(nstage - 1, 0), 3))]
         self.red, self.red_ptrs = self.mem.alloc((2 * self.world * 128,), dtype)
         self.flags, self.flag_ptrs = self.mem.alloc((64,), torch.int32)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -385,7 +440,7 @@ class PeerCG(DistCG):
         self.done_scalar = self.state[scal + solvers.K_DONE:]
         if mode in ("cg1", "fused"):
             self.red2, self.red2_ptrs = self.mem.alloc((2 * 2 * self.world * 128,), dtype)
-            nflag = op.nu + 2
+            nflag = nstage + 2
             self.flags2, base = self.mem.alloc((nflag, 64), torch.int32)
             self.flag_tabs = [(base + 64 * 4 * i).contiguous() for i in range(nflag)]
         if mode == "cg1":
@@ -393,7 +448,7 @@ class PeerCG(DistCG):
             self.r, self.r_ptrs = self.mem.alloc((n_sym, self.ld), dtype)
             self.s = torch.zeros((op.n_loc, self.ld), dtype=dtype, device=dev)
             self.gamma_loc = torch.zeros(ncols, dtype=dtype, device=dev)
-            self.tickets = torch.zeros(8 * max(op.nu, 1), dtype=torch.int32, device=dev)     # one 32-byte slot per SpMM stage
+            self.tickets = torch.zeros(8 * max(nstage, 1), dtype=torch.int32, device=dev)     # one 32-byte slot per SpMM stage
         self.mem.sync()
 
     # -- building blocks -----------------------------------------------------------------------------------------------
@@ -428,20 +483,24 @@ class PeerCG(DistCG):
             src, src_ptrs = dst, dst_ptrs
 
     def _matvec_cg1(self):
-        """w (= self.v) <- P r; the last launch ships (r.w, |r|^2) partials to every rank.  Flag tables: [0] "r complete",
-        [1 .. nu-1] "intermediate vector s complete", [nu] "dot partials shipped"."""
+        """w (= self.v) <- A r for A = P, c P or Noise(c P); the last launch ships (r.w, |r|^2) partials to every rank.  Flag
+        tables: [0] "r complete", [i] "output of stage i - 1 complete", [nstage] "dot partials shipped"."""
         from . import _lib, graph
-        op, c, n_loc, nu = self.op, self.c, self.op.n_loc, self.op.nu
+        op, c, n_loc = self.op, self.c, self.op.n_loc
+        eps_ = op.stage_epilogues()
+        nstage = len(eps_)
         src, src_ptrs = self.r, self.r_ptrs
-        for s in range(nu):
-            last = s == nu - 1
-            dst, dst_ptrs = (self.v, None) if last else self.tmps[s]
+        for s in range(nstage):
+            last = s == nstage - 1
+            dst, dst_ptrs = (self.v, None) if last else self.tmps[s % len(self.tmps)]
+            ep_coef, ep_add = eps_[s]
             ext = _lib.wi_ext(done_flag=self.done_scalar, wait_flags=self.flag_tabs[s],
                               publish_flags=None if last else self.flag_tabs[s + 1], ticket=self.tickets[8 * s:],
-                              red_ptrs=self.red2_ptrs if last else None, red_flags=self.flag_tabs[nu] if last else None,
-                              ship_extra=self.gamma_loc if last else None, ship_ncols=c if last else 0)
+                              red_ptrs=self.red2_ptrs if last else None, red_flags=self.flag_tabs[nstage] if last else None,
+                              ship_extra=self.gamma_loc if last else None, ship_ncols=c if last else 0,
+                              ep_coef=ep_coef, ep_add=ep_add)
             graph.lap_spmm(op.st, op.a, op.diag, src[:n_loc, :c], shift=op.shift, out=dst[:n_loc, :c],
-                           dot_with=self.r[:n_loc, :c] if last else None, dot_out=self.rbuf_pap if last else None,
+                           dot_with=self.r[:n_loc, :c] if (last or ep_add) else None, dot_out=self.rbuf_pap if last else None,
                            peer_x=src_ptrs, peer_ext=(self.rank, self.iter_scalar, ext))
             src, src_ptrs = dst, dst_ptrs
 
@@ -451,7 +510,7 @@ class PeerCG(DistCG):
         sfx = _lib.suffix(self.dt)
         n_loc, c, ld = self.op.n_loc, self.c, self.ld
         if self.mode == "cg1":
-            nu = self.op.nu
+            nu = self.op.nstage
             self._matvec_cg1()
             _lib.call("mgp_cg_peer_cgstep_" + sfx, ptr(self.x), ptr(self.r), ptr(self.p), ptr(self.s), ptr(self.v), c_int64(ld),
                       c_int64(n_loc), c_int32(c), ptr(self.state), ptr(self.hist), c_int32(self.max_hist), ptr(self.ws),
@@ -507,6 +566,141 @@ class PeerCG(DistCG):
         rows = k_done - 1 if info["converged"] else k_done
         rows = max(1, min(rows, self.n_tridiag_iter))
         return solvers._tridiag_from_hist(self.hist.cpu(), rows, self.n_tridiag, self.dt).to(self.dev)
+
+
+class DistBackend:
+    """Routes ``solvers.linear_cg`` of the package's native operators -- PrecisionMaternOperator, bare or inside the reference's
+    Scale / Noise wrappers (riemann_gp.py:32-39) -- to the row-partitioned peer-memory CG of this process group, so that
+    ``manifold_informed_train`` / ``inv_quad_logdet`` / ``solve`` / ``_average_variance`` run UNCHANGED on every rank with their
+    CG + SLQ solves (the dominant cost: utils/train_model.py:55,67-68) sharded over the GPUs:
+
+        from manifold_gp_b200 import distributed, solvers
+        solvers.set_distributed_backend(distributed.DistBackend())      # after init_process_group, same call on every rank
+
+    Every rank passes the same full right-hand side; rows are partitioned in the structure's Morton order; the solution is
+    all-gathered (one collective per solve, outside the iteration) and the CG coefficients / Lanczos tridiagonals are identical
+    on every rank, so the SLQ log-det, the surrogate backward and the optimiser step run redundantly and stay in lock-step.
+    Graph structure and value build are replicated per rank (each rank holds the whole graph: 8 GB at N = 10M, k = 32).
+    Partition-dependent objects (halo plan, local views, peer-mapped vectors, captured CUDA graphs) are cached per graph
+    structure and reused across bandwidths: a training step only copies the new values into the solver's buffers."""
+
+    def __init__(self, group=None, mode="cg1", min_rows=100_000):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.mode = mode
+        self.min_rows = int(min_rows)
+        self._cache = {}
+        self.solves = 0
+
+    @staticmethod
+    def _decompose(op):
+        """(precision operator, coef tensor or None, noise tensor or None) or None when the operator is not covered."""
+        from .operators.noise_wrapper_operator import NoiseWrapperOperator
+        from .operators.precision_matern_operator import PrecisionMaternOperator
+        from .operators.scale_wrapper_operator import ScaleWrapperOperator
+        noise = coef = None
+        cur = op
+        if isinstance(cur, NoiseWrapperOperator):
+            noise, cur = cur.noise, cur.operator
+        if isinstance(cur, ScaleWrapperOperator):
+            sc = cur.scale.detach().reshape(-1)[:1]
+            coef, cur = (sc.reciprocal() if cur.inverse_scale else sc), cur.operator
+        if not isinstance(cur, PrecisionMaternOperator) or not cur._native():
+            return None
+        if cur.laplacian.normalization != "symmetric":
+            return None                       # the D^{+-1/2} factors of the random-walk form are not partitioned yet
+        return cur, coef, noise
+
+    def supports(self, op, rhs) -> bool:
+        if not rhs.is_cuda or rhs.shape[0] < self.min_rows:
+            return False
+        dec = self._decompose(op)
+        if dec is None:
+            return False
+        st = dec[0].laplacian.structure
+        t = st.build_tiles()
+        return t is not None and "wptr" in t and rhs.shape[1] <= 128
+
+    def sharded_self_search(self, knn, k):
+        """kNN of the cloud against itself: this rank searches its block of query rows, the lists are all-gathered
+        (nearest_neighbors.py:35-37 at multi-GPU scale; identical results on every rank)."""
+        x = knn._db
+        n = x.shape[0]
+        part = RowPartition(n, self.world, align=64)
+        lo, hi = part.range(self.rank)
+        t0 = time.perf_counter()
+        d_loc, i_loc = knn.search(x[lo:hi], k)           # a row slice: not the self-search branch again
+        torch.cuda.synchronize()
+        self.last_knn_local_s = time.perf_counter() - t0
+        sizes = [part.range(r)[1] - part.range(r)[0] for r in range(self.world)]
+        d_all = [torch.empty((sz, k), dtype=d_loc.dtype, device=x.device) for sz in sizes]
+        i_all = [torch.empty((sz, k), dtype=i_loc.dtype, device=x.device) for sz in sizes]
+        dist.all_gather(d_all, d_loc.contiguous(), group=self.group)
+        dist.all_gather(i_all, i_loc.contiguous(), group=self.group)
+        return torch.cat(d_all), torch.cat(i_all)
+
+    def cg_chunk(self, op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter):
+        """Same contract as ``solvers._cg_chunk``: (solution [n, C] in the caller's row order, hist (cpu) or None, info)."""
+        from . import solvers
+        prec, coef, noise = self._decompose(op)
+        lap = prec.laplacian
+        gst = lap.structure
+        c_in = rhs.shape[1]
+        # the fused vector kernels want a power-of-two row length: zero columns are free in a 64-byte-row pass and have
+        # residual exactly 0, so tolerance * c / cpad is the published mean-over-columns rule on the original block
+        cpad = 4
+        while cpad < c_in:
+            cpad *= 2
+        if cpad != c_in:
+            wide = torch.zeros((rhs.shape[0], cpad), dtype=rhs.dtype, device=rhs.device)
+            wide[:, :c_in] = rhs
+            sol, hist, info = self.cg_chunk(op, wide, n_tridiag, tolerance * c_in / cpad, eps, stop_updating_after, max_iter, n_tridiag_iter)
+            info["mean_residual"] = info["mean_residual"] * cpad / c_in
+            info["residual_norm"] = info["residual_norm"][:c_in]
+            return sol[:, :c_in], (hist[:, :, :c_in] if hist is not None else None), info
+        n, c = rhs.shape
+        dt = rhs.dtype
+        with torch.no_grad():
+            _, _, diag, a = lap._values()
+            diag, a = diag.detach(), a.detach()
+            shift = prec._shift_const(a.dtype)
+        ent = self._cache.get(id(gst))
+        if ent is None or ent["gst"] is not gst:
+            part = RowPartition(n, self.world, align=gst.TILE_ROWS)
+            ent = {"gst": gst, "part": part, "ops": {}, "solvers": {}}
+            self._cache = {id(gst): ent}                      # one graph at a time: the buffers are per-rank gigabytes
+        okey = (dt, prec.nu, coef is not None, noise is not None)
+        dop = ent["ops"].get(okey)
+        if dop is None:
+            dop = DistPrecision(gst, diag, a, shift, prec.nu, ent["part"], self.rank, self.group, coef=coef, noise=noise)
+            ent["ops"][okey] = dop
+        else:
+            dop.update_values(diag, a, shift, coef, noise)
+        skey = okey + (c, int(n_tridiag), int(n_tridiag_iter))
+        cg = ent["solvers"].get(skey)
+        if cg is None:
+            cg = PeerCG(dop, c, dt, tolerance=tolerance, eps=eps, stop_updating_after=stop_updating_after, max_iter=max_iter,
+                        check_interval=int(solvers.settings.cg_check_interval.value()), group=self.group, mode=self.mode,
+                        n_tridiag=n_tridiag, max_tridiag_iter=n_tridiag_iter if n_tridiag else 20)
+            ent["solvers"][skey] = cg
+        cg.tol, cg.eps, cg.stop, cg.max_iter = float(tolerance), float(eps), float(stop_updating_after), int(max_iter)
+        part = ent["part"]
+        lo, hi = part.range(self.rank)
+        b_loc = gst.to_internal(rhs)[lo:hi].contiguous()
+        x_loc, info = cg.solve(b_loc)
+        sizes = [part.range(r)[1] - part.range(r)[0] for r in range(self.world)]
+        if self.world > 1:
+            parts = [torch.empty((sz, c), dtype=dt, device=rhs.device) for sz in sizes]
+            dist.all_gather(parts, x_loc.contiguous(), group=self.group)
+            sol = torch.cat(parts)
+        else:
+            sol = x_loc
+        sol = gst.to_external(sol)
+        from .solvers import CGInfo, S_RESID
+        cinfo = CGInfo(iterations=info["iterations"], mean_residual=info["mean_residual"], converged=info["converged"],
+                       residual_norm=cg.state[S_RESID * c:(S_RESID + 1) * c].clone(), distributed=self.world)
+        self.solves += 1
+        return sol, (cg.hist.cpu() if n_tridiag else None), cinfo
 
 
 def _collectives_note(cg, transport, nu):

@@ -599,7 +599,31 @@ def _note_kernel(name):
 
 
 def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
-             x_external=False, y_external=False, peer_x=None, peer_sync=None, peer_ext=None, done_flag=None):
+             x_external=False, y_external=False, peer_x=None, peer_sync=None, peer_ext=None, done_flag=None, ep_coef=None,
+             ep_add=None):
+    """``_lap_spmm`` plus the wrappers' epilogue algebra: Y <- ep_add + ep_coef * Y (``ep_coef``: device scalar tensor, ``ep_add``:
+    [n, C] like X; a requested dot product is taken with the scaled Y, and excludes ``ep_add``).  The warp-interleaved kernel
+    applies it inside the launch (mgp_wi_ext.ep_coef / ep_add); for every other kernel it is two elementwise passes here."""
+    if ep_coef is None and ep_add is None:
+        return _lap_spmm(st, a, diag, x, shift, pre, post, out, dot_with, dot_out, x_external, y_external, peer_x, peer_sync,
+                         peer_ext, done_flag)
+    if ep_add is not None and (dot_out is not None or ep_coef is None):
+        raise ValueError("lap_spmm: ep_add needs ep_coef and excludes the dot epilogue")
+    handled = []
+    y = _lap_spmm(st, a, diag, x, shift, pre, post, out, dot_with, dot_out, x_external, y_external, peer_x, peer_sync, peer_ext,
+                  done_flag, _ep=(ep_coef, ep_add, handled))
+    if not handled:
+        cf = ep_coef.to(y.dtype)
+        y.mul_(cf)
+        if ep_add is not None:
+            y.add_(ep_add[:, :y.shape[1]])
+        if dot_out is not None:
+            dot_out.mul_(cf)
+    return y
+
+
+def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, out=None, dot_with=None, dot_out=None,
+              x_external=False, y_external=False, peer_x=None, peer_sync=None, peer_ext=None, done_flag=None, _ep=None):
     """Y = post .* ((diag + shift) .* (pre .* X) - A (pre .* X)).  ``x``: [n, C] CUDA tensor with unit column stride.
 
     ``peer_x``: int64 device tensor of every rank's X base pointer (row-partitioned multi-GPU, see distributed.PeerCG);
@@ -678,9 +702,19 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
         if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi") or peer_x is not None):
             aw = st.wi_values(a)
             hcol = t["hcol_peer"] if peer_x is not None else t["hcol"]
-            if peer_ext is not None or done_flag is not None:
+            ep_here = _ep is not None and peer_ext is None and not (x_external or y_external)
+            if peer_ext is not None or done_flag is not None or ep_here:
                 import ctypes
-                ext = peer_ext[2] if peer_ext is not None else _lib.wi_ext(done_flag=done_flag)
+                if peer_ext is not None:
+                    ext = peer_ext[2]
+                elif ep_here:
+                    cf = _ep[0] if _ep[0].dtype == dt else _ep[0].to(dt)
+                    ext = _lib.wi_ext(done_flag=done_flag, ep_coef=cf, ep_add=_ep[1] is not None)
+                    if _ep[1] is not None:
+                        dot_with = _ep[1]
+                    _ep[2].append(True)
+                else:
+                    ext = _lib.wi_ext(done_flag=done_flag)
                 rc = _lib.call_rc("mgp_lap_spmm_wi_ex_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag),
                                   ptr(t["hptr"]), ptr(hcol), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
                                   c_int32(t["wnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
@@ -703,6 +737,10 @@ def lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, ou
             if rc == 0:
                 _note_kernel("lap_spmm_wi_kernel")
                 return out
+            if _ep is not None and _ep[2]:          # not launched: the epilogue algebra falls to the caller's elementwise passes
+                _ep[2].clear()
+                if _ep[1] is not None:
+                    dot_with = None
             if rc != _lib.MGP_EUNSUPPORTED or peer_x is not None:
                 raise RuntimeError(f"mgp_lap_spmm_wi_{sfx} failed ({rc}): {_lib.last_error()}")
         if SPMM_KERNEL == "wi":

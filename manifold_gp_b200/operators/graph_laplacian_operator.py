@@ -164,14 +164,17 @@ class GraphLaplacianOperator(LinearOperator):
     def _mgp_structure(self):
         return self.structure
 
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp=None, dot_with=None, dot_out=None, ncols=None, done_flag=None):
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp=None, dot_with=None, dot_out=None, ncols=None, done_flag=None,
+                    ep_coef=None, ep_add=None):
         if ncols is not None:
             x, out = x[:, :ncols], out[:, :ncols]
+            if ep_add is not None:
+                ep_add = ep_add[:, :ncols]
         with torch.no_grad():
             _, _, diag, a = self._values()
             pre, post = self._pre_post()
             graph.lap_spmm(self.structure, a.detach(), diag.detach(), x, pre=pre, post=post, out=out,
-                           dot_with=dot_with, dot_out=dot_out, done_flag=done_flag)
+                           dot_with=dot_with, dot_out=dot_out, done_flag=done_flag, ep_coef=ep_coef, ep_add=ep_add)
         return out
 
     def _size(self):

@@ -85,15 +85,19 @@ class PrecisionMaternOperator(LinearOperator):
         return out.squeeze(-1) if squeeze else out
 
     # ---- fused path used by the CUDA CG / Lanczos drivers (no autograd, caller-owned buffers) -------------------------
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None):
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None,
+                    ep_coef=None, ep_add=None):
         """out[:, :ncols] <- P x[:, :ncols] on caller-owned [n, ld] buffers (unit column stride); ``tmp`` is scratch of the
         same shape (used when nu > 1).  If ``dot_out`` is given, dot_out[c] = sum_i dot_with[i,c] * out[i,c] comes out of
         the last launch (``dot_with`` must share x's leading dimension).  ``done_flag``: device scalar of the solver state; the
-        launches are no-ops once it is non-zero (CG chunks replayed past convergence)."""
+        launches are no-ops once it is non-zero (CG chunks replayed past convergence).  ``ep_coef`` / ``ep_add``: the wrappers'
+        algebra on the LAST launch, out <- ep_add + ep_coef * (P x) (``graph.lap_spmm``)."""
         lap = self.laplacian
         st = lap.structure
         if ncols is not None:
             x, out, tmp = x[:, :ncols], out[:, :ncols], (tmp[:, :ncols] if tmp is not None else None)
+            if ep_add is not None:
+                ep_add = ep_add[:, :ncols]
         with torch.no_grad():
             _, _, diag, a = lap._values()
             shift = self._shift_const(a.dtype)
@@ -105,7 +109,8 @@ class PrecisionMaternOperator(LinearOperator):
                 dst = out if ((self.nu - 1 - s) % 2 == 0) else tmp
                 graph.lap_spmm(st, a.detach(), diag.detach(), src, shift=shift, pre=sq if (rw and s == 0) else None,
                                post=sq if (rw and last) else None, out=dst,
-                               dot_with=dot_with if last else None, dot_out=dot_out if last else None, done_flag=done_flag)
+                               dot_with=dot_with if last else None, dot_out=dot_out if last else None, done_flag=done_flag,
+                               ep_coef=ep_coef if last else None, ep_add=ep_add if last else None)
                 src = dst
         return out
 

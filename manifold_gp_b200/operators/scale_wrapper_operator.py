@@ -50,17 +50,25 @@ class ScaleWrapperOperator(LinearOperator):
     def _mgp_cache_key(self, dtype):
         return ("scale", bool(self.inverse_scale), self.scale.data_ptr(), self.scale._version) + tuple(self.operator._mgp_cache_key(dtype))
 
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None):
-        """out[:, :ncols] <- s * (Q x) (or / s) in place on the caller's buffers; the fused dot product is scaled alike."""
-        self.operator._mgp_matvec(x, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols, done_flag=done_flag)
-        s = self.scale.detach().to(out.dtype)
-        view = out if ncols is None else out[:, :ncols]
-        if self.inverse_scale:
-            view.div_(s)
-            if dot_out is not None:
-                dot_out.div_(s)
-        else:
-            view.mul_(s)
-            if dot_out is not None:
-                dot_out.mul_(s)
-        return out
+    def _coef(self, dtype, outer=None):
+        """Device scalar s or 1/s (times an outer wrapper's coefficient), cached per (scale value, outer coefficient)."""
+        key = (self.scale.data_ptr(), self.scale._version, dtype, bool(self.inverse_scale),
+               None if outer is None else (outer.data_ptr(), outer._version))
+        hit = self.__dict__.get("_mgp_coef")
+        if hit is None or hit[0] != key:
+            import torch
+            with torch.no_grad():
+                s = self.scale.detach().to(dtype).reshape(-1)[:1]
+                c = s.reciprocal() if self.inverse_scale else s.clone()
+                if outer is not None:
+                    c = c * outer.to(dtype).reshape(-1)[:1]
+            hit = (key, c.contiguous(), outer)          # keeps ``outer`` alive: its address is part of the key
+            self.__dict__["_mgp_coef"] = hit
+        return hit[1]
+
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None,
+                    ep_coef=None, ep_add=None):
+        """out[:, :ncols] <- ep_add + ep_coef * s * (Q x) (or / s): the scaling rides in the epilogue of the inner operator's
+        last launch (no elementwise pass); the fused dot product is taken with the scaled product."""
+        return self.operator._mgp_matvec(x, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols, done_flag=done_flag,
+                                         ep_coef=self._coef(out.dtype, ep_coef), ep_add=ep_add)

@@ -86,12 +86,19 @@ class PrincipalBlockOperator(LinearOperator):
         k = self._keep_internal(dtype)
         return ("principal", k.data_ptr(), k._version) + tuple(self.base._mgp_cache_key(dtype))
 
-    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None):
+    def _mgp_matvec(self, x: Tensor, out: Tensor, tmp: Tensor, dot_with=None, dot_out=None, ncols=None, done_flag=None,
+                    ep_coef=None, ep_add=None):
         """out <- K Q x for x that is zero on the dropped rows (the CG invariant); the fused dot product of the base launch is
         already the masked one when ``dot_with`` is zero there (it is: CG passes p)."""
         self.base._mgp_matvec(x, out, tmp, dot_with=dot_with, dot_out=dot_out, ncols=ncols, done_flag=done_flag)
         view = out if ncols is None else out[:, :ncols]
         view.mul_(self._keep_internal(out.dtype))
+        if ep_coef is not None:              # (not used by the Schur path itself; kept so the interface composes)
+            view.mul_(ep_coef.to(out.dtype))
+            if dot_out is not None:
+                dot_out.mul_(ep_coef.to(out.dtype))
+        if ep_add is not None:
+            view.add_(ep_add if ncols is None else ep_add[:, :ncols])
         return out
 
 

@@ -40,8 +40,20 @@ class CGInfo(dict):
     pass
 
 
+_DIST_BACKEND = None
+
+
+def set_distributed_backend(backend) -> None:
+    """Route the CG solves of covered operators through a multi-GPU backend (``distributed.DistBackend``); ``None`` restores
+    the single-GPU drivers.  Must be set identically on every rank of the process group."""
+    global _DIST_BACKEND
+    _DIST_BACKEND = backend
+
+
 def _cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter):
     """mBCG on <= 128 columns.  Returns (solution [n,C], hist (cpu) or None, info)."""
+    if _DIST_BACKEND is not None and _DIST_BACKEND.supports(op, rhs):
+        return _DIST_BACKEND.cg_chunk(op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter)
     n, c = rhs.shape
     dt, dev = rhs.dtype, rhs.device
     sfx = _lib.suffix(dt)

@@ -44,6 +44,16 @@ class NearestNeighbors():
         dist = torch.empty((nq, k), dtype=torch.float32, device=q.device)
         idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
         same = q.data_ptr() == self._db.data_ptr() and nq == n
+        # multi-GPU: with a distributed backend registered the self-search of a large cloud is sharded by query
+        # rows (database replicated, no collective in the search) and the lists are all-gathered
+        from .. import solvers as _solvers
+        be = _solvers._DIST_BACKEND
+        if same and be is not None and getattr(be, "world", 1) > 1 and n >= be.min_rows and not getattr(self, "_in_shard", False):
+            self._in_shard = True
+            try:
+                return be.sharded_self_search(self, k)
+            finally:
+                self._in_shard = False
         self.last_search = {"kernel": "cuda_core"}
         if self.tensor_core:
             # k <= 48, n >= 256: TF32 tcgen05 distance tiles + fused top-(k+margin) + exact certified re-rank (knn_tc.cu);

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3] ("cfg-D"): the full hyper-parameter training loop -- precision-form marginal likelihood = mBCG on
+[probes | y] + stochastic-Lanczos-quadrature log-det + backward + Adam, with the output-scale renormalisation by the average
+variance (utils/train_model.py:49-109) -- on a synthetic sphere / Swiss roll in R^3, k = 32, sharded over the GPUs of one box:
+
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 profiles/run_cfgD.py [n] [train calls] [sphere|swiss]
+
+`manifold_informed_train` runs UNCHANGED on every rank; `solvers.set_distributed_backend(DistBackend())` shards what dominates it:
+the kNN self-search (query rows per rank, database replicated) and every CG / SLQ solve (rows partitioned in Morton order,
+single-reduction peer-memory CG, Noise(Scale(P)) applied as 3 nu chained SpMM launches per matvec).  Symmetrise, structure,
+value build, the surrogate backward (one differentiable matvec on [z | s]) and the Adam step are replicated per rank.
+With WORLD_SIZE = 1 (or MGP_CFGD_BACKEND=0) the same script is the single-GPU reference for loss parity."""
+import json, os, sys, time, warnings
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+import manifold_gp_b200 as mgp
+from manifold_gp_b200 import _lib, distributed, solvers
+from manifold_gp_b200._compat import gp as gpc
+from manifold_gp_b200.utils import synthetic, manifold_informed_train
+
+warnings.simplefilter("ignore")
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+dev = torch.device("cuda", local); torch.cuda.set_device(dev)
+if "MASTER_ADDR" not in os.environ:
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = "29543"
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+args = [a for a in sys.argv[1:]]
+n = int(args[0]) if len(args) > 0 else 10_000_000
+calls = int(args[1]) if len(args) > 1 else 3
+shape = args[2] if len(args) > 2 else "sphere"
+NU = int(os.environ.get("TRAIN_NU", "1"))
+NOISE = float(os.environ.get("TRAIN_NOISE", "1.2e-4")) * (1_000_000 / n)       # the Neumann-series noise wrapper needs noise * |Q| < 1
+use_backend = os.environ.get("MGP_CFGD_BACKEND", "1") != "0"
+backend = None
+if use_backend:
+    backend = distributed.DistBackend(min_rows=int(os.environ.get("MGP_CFGD_MIN_ROWS", "100000")))
+    solvers.set_distributed_backend(backend)
+torch.manual_seed(1234)                                    # probes / one-hot picks: identical on every rank
+res = {"workload": f"{shape}_N{n}_k32_nu{NU}_train", "world": world, "backend": "DistBackend(cg1)" if use_backend else "single-GPU drivers",
+       "train_calls": calls}
+x = (synthetic.sphere if shape == "sphere" else synthetic.swiss_roll)(n, seed=0, device=dev)
+g = torch.Generator(device=dev).manual_seed(2)
+y = torch.sin(3.0 * x[:, 0]) * torch.cos(2.0 * x[:, 2]) + 0.05 * torch.randn(n, device=dev, generator=g)
+torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+kernel = mgp.RiemannMaternKernel(nu=NU, x=x, nearest_neighbors=32, laplacian_normalization="symmetric", num_modes=100).to(dev)
+torch.cuda.synchronize(); dist.barrier(); res["graph_build_s"] = round(time.perf_counter() - t0, 3)
+if backend is not None and hasattr(backend, "last_knn_local_s"):
+    res["knn_local_search_s"] = round(backend.last_knn_local_s, 3)
+res["edges_M"] = int(kernel.edge_index.shape[1])
+d2, _ = kernel.knn.search(x[:4096].contiguous(), 32)
+kernel.graphbandwidth = torch.tensor([[float(d2[:, 31].sqrt().median())]], device=dev)
+kernel.lengthscale = torch.tensor([[0.5]], device=dev)
+covar = gpc.ScaleKernel(kernel).to(dev)
+lik = gpc.GaussianLikelihood().to(dev)
+lik.noise = torch.tensor([NOISE], device=dev)
+model = mgp.RiemannGP(x, y, lik, covar).to(dev)
+opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+_lib.reset_launch_count()
+losses, times = [], []
+for it in range(calls + 1):                     # first call includes lazy structure / layout / partition builds and graph captures
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    loss = manifold_informed_train(model, opt, max_iter=0, tolerance=0.0, num_rand_vec=16, max_cholesky=800,
+                                   cg_tolerance=1e-2, cg_max_iter=1000)
+    torch.cuda.synchronize(); dist.barrier()
+    times.append(round(time.perf_counter() - t0, 3)); losses.append(float(loss))
+params = dict(eps=float(kernel.graphbandwidth), lengthscale=float(kernel.lengthscale), noise=float(lik.noise), outputscale=float(covar.outputscale))
+res.update(seconds_per_train_call=times, losses=losses, gpu_launches_rank0=_lib.launch_count(), final_parameters=params,
+           distributed_solves=(backend.solves if backend is not None else 0),
+           peak_memory_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
+           note="one call = outputscale renormalisation (16-RHS CG on the bare precision) x 2 + one loss (mBCG on [10 probes | y], SLQ) "
+                "/ backward / Adam step")
+if rank == 0:
+    print(json.dumps(res))
+dist.barrier(); dist.destroy_process_group()

@@ -88,21 +88,38 @@ def test_out_of_sample_features_and_posterior(dumbbell, normalization):
 
 
 def test_posterior_fp32_within_tolerance(dumbbell):
+    """fp32 is the reference's arithmetic.  Its own eval path is a DENSE fp32 eigh
+    (riemann_kernel.py:124) whose 50 eigenvectors carry ~1e-3 of rounding, so the fp32 posterior cannot agree with the fp64
+    truth to the north-star's 1e-4 -- for the reference itself either.  The test therefore runs the reference's dense path in
+    fp32 beside ours (the oracle restatement evaluated in float32 on the CPU) and requires (a) our fp32 mean AND variance to
+    be as close to the fp64 truth as the reference's own fp32 path is (within 3x of its error, or 1e-4 if that is larger),
+    and (b) a hard ceiling of 1e-2 (mean) / 2e-2 (variance)."""
     model, kernel, x, y = _build(dumbbell, torch.float32)
-    xo, lap, eigval, eigvec = _oracle_side(dumbbell, torch.float64)
     xt = dumbbell["test_x"]
     model.eval()
     model.likelihood.eval()
-    ev, ei = oracle.knn_search(xo.float(), xt.float(), K)
-    zo_tr = oracle.features(lap, eigval, eigvec, NU, KAPPA, x_is_train=True)
-    zo_te = oracle.features(lap, eigval, eigvec, NU, KAPPA, x_is_train=False, edge_value=ev.double(), edge_index=ei,
-                            bump_scale=BUMP_SCALE, bump_decay=BUMP_DECAY)
-    mean_o, cov_o = oracle.low_rank_posterior(zo_tr, zo_te, dumbbell["train_y"].double(), OUTPUTSCALE, NOISE)
+
+    def oracle_posterior(dtype):
+        xo, lap, eigval, eigvec = _oracle_side(dumbbell, dtype)
+        ev, ei = oracle.knn_search(xo.float(), xt.float(), K)
+        zo_tr = oracle.features(lap, eigval, eigvec, NU, KAPPA, x_is_train=True)
+        zo_te = oracle.features(lap, eigval, eigvec, NU, KAPPA, x_is_train=False, edge_value=ev.to(dtype), edge_index=ei,
+                                bump_scale=BUMP_SCALE, bump_decay=BUMP_DECAY)
+        m, c = oracle.low_rank_posterior(zo_tr, zo_te, dumbbell["train_y"].to(dtype), OUTPUTSCALE, NOISE)
+        return m.double(), c.diagonal().double()
+
+    mean_o, var_o = oracle_posterior(torch.float64)
+    mean_r32, var_r32 = oracle_posterior(torch.float32)          # the reference's dense path in its own arithmetic
     with torch.no_grad():
         model.posterior(xt.float().to(DEV))
         mean = model.posterior_mean.cpu().double()
-    # fp32 dense eigh (the reference's own eval path, riemann_kernel.py:124) of a 1546-point graph: eigenvectors carry ~1e-3
-    assert float((mean - mean_o).abs().max() / mean_o.abs().max()) < 1e-2
+        var = model.posterior_covar.to_dense().diagonal().cpu().double()
+    err = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    e_mean, e_var = err(mean, mean_o), err(var, var_o)
+    r_mean, r_var = err(mean_r32, mean_o), err(var_r32, var_o)
+    print(f"fp32 posterior vs fp64 truth: ours mean {e_mean:.2e} var {e_var:.2e}; reference fp32 dense path mean {r_mean:.2e} var {r_var:.2e}")
+    assert e_mean < max(1e-4, 3 * r_mean) and e_mean < 1e-2
+    assert e_var < max(1e-4, 3 * r_var) and e_var < 2e-2
 
 
 def test_training_loss_matches_dense_reference_and_decreases(dumbbell):

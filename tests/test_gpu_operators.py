@@ -101,6 +101,47 @@ def test_spmm_column_counts_vs_oracle(ncols, dtype):
         assert rel_err(lap.matmul(wide[:, 1:1 + ncols]), ref_l) < TOL[dtype]
 
 
+@pytest.mark.parametrize("n,k", [(120_000, 16), (1_000_000, 32)])
+def test_dominant_kernel_vs_oracle_on_a_searched_graph(n, k):
+    """The kernel the headline solve launches (lap_spmm_wi_kernel, C = 16, selected by `auto` only on graphs that carry the
+    Morton hint of NearestNeighbors.graph) DIRECTLY against the oracle's restatement of graph_laplacian_operator.py:108-124 /
+    precision_matern_operator.py:26-37 on the same edge list, in fp32 (1e-5) and fp64 (1e-10), at a mid size and at the full
+    cfg-C size (N = 1M, k = 32); plus the fused dot epilogue and the single-column tile SpMV on the same graph."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph
+    x = oracle.datasets.torus(n, seed=0)
+    idx, val = mgp.NearestNeighbors(x.to(DEV)).graph(k)
+    eps = 0.0274 * (1_000_000 / n) ** 0.5
+    kappa, nu = 0.5, 2
+    olap = oracle.LaplacianOracle(val.double().cpu(), idx.cpu(), n, eps, "symmetric", True)
+    V = torch.randn(n, 16, generator=torch.Generator().manual_seed(7), dtype=torch.float64)
+    ref_l = olap.matmul(V)
+    ref_p = oracle.precision_matmul(olap, nu, kappa, V)
+    for dtype in (torch.float32, torch.float64):
+        lap = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, torch.tensor([[eps]], dtype=dtype, device=DEV), "symmetric", True)
+        prec = mgp.PrecisionMaternOperator(lap, nu, torch.tensor([[kappa]], dtype=dtype, device=DEV))
+        st = lap.structure
+        assert st.perm is not None and st.tiles is not None and "wptr" in st.tiles
+        y = lap.matmul(V.to(dtype).to(DEV))
+        assert graph.LAST_SPMM_KERNEL == "lap_spmm_wi_kernel"
+        assert rel_err(y, ref_l) < TOL[dtype]
+        yp = prec.matmul(V.to(dtype).to(DEV))
+        assert graph.LAST_SPMM_KERNEL == "lap_spmm_wi_kernel"
+        assert rel_err(yp, ref_p) < TOL[dtype]
+        # solver-driver interface (internal order, caller-owned buffers, fused dot product) -- what CG actually calls
+        xi = st.to_internal(V.to(dtype).to(DEV)).contiguous()
+        out, tmp = torch.empty_like(xi), torch.empty_like(xi)
+        dot = torch.zeros(16, dtype=dtype, device=DEV)
+        prec._mgp_matvec(xi, out, tmp, dot_with=xi, dot_out=dot)
+        assert rel_err(st.to_external(out), ref_p) < TOL[dtype]
+        assert rel_err(dot, (V * ref_p).sum(0)) < TOL[dtype] * 10
+        y1 = lap.matmul(V[:, :1].to(dtype).to(DEV))
+        assert graph.LAST_SPMM_KERNEL == "lap_spmv_tile_kernel"
+        assert rel_err(y1, ref_l[:, :1]) < TOL[dtype]
+        del lap, prec, st, y, yp, xi, out, tmp
+        torch.cuda.empty_cache()
+
+
 def test_linearity_and_symmetry_at_scale():
     """Size-independent properties at N = 1M, k = 32 (BASELINE cfg-C): <u, P v> == <P u, v>, P(au+bv) == aPu + bPv."""
     import manifold_gp_b200 as mgp

@@ -96,3 +96,45 @@ def test_peer_cg1_tridiagonals_match_linear_cg(pg1):
     assert t.shape == t_ref.shape
     assert rel_err(t, t_ref) < 1e-8
     assert rel_err(gst.to_external(xs), ref) < 1e-8
+
+
+def test_dist_backend_routes_training_loss_through_the_peer_cg(pg1):
+    """solvers.set_distributed_backend(DistBackend()): inv_quad_logdet of Noise(Scale(Precision)) -- the operator of the training
+    loss (riemann_gp.py:32-39, utils/train_model.py:67-68) -- through the row-partitioned single-reduction CG (3 nu SpMM launches
+    per matvec with the wrapper algebra in their epilogues) against the single-GPU drivers: same iteration count, inverse
+    quadratic form, SLQ log-det (same probes) and the same gradients w.r.t. bandwidth, lengthscale, output scale and noise."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import distributed as D, solvers
+    dtype = torch.float64
+    n, k, nu = 20000, 12, 1
+    x = oracle.datasets.torus(n, seed=4)
+    knn = mgp.NearestNeighbors(x.to(DEV))
+    idx, val = knn.graph(k)
+    y = torch.sin(2.0 * x[:, 0]).to(dtype).to(DEV)
+    probes = torch.randn(n, 6, dtype=dtype, device=DEV, generator=torch.Generator(device=DEV).manual_seed(9))
+
+    def run(backend):
+        solvers.set_distributed_backend(backend)
+        try:
+            eps = torch.tensor([[0.2]], dtype=dtype, device=DEV, requires_grad=True)
+            kap = torch.tensor([[0.9]], dtype=dtype, device=DEV, requires_grad=True)
+            osc = torch.tensor(1.7, dtype=dtype, device=DEV, requires_grad=True)
+            noi = torch.tensor(2e-3, dtype=dtype, device=DEV, requires_grad=True)
+            lap = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, eps, "symmetric", True)
+            prec = mgp.PrecisionMaternOperator(lap, nu, kap)
+            op = mgp.NoiseWrapperOperator(mgp.ScaleWrapperOperator(prec, osc, inverse_scale=True), noi)
+            with mgp.settings.max_cholesky_size(0), mgp.settings.cg_tolerance(1e-4), mgp.settings.max_cg_iterations(2000):
+                iq, ld, info = solvers.inv_quad_logdet(op, inv_quad_rhs=y.unsqueeze(-1), logdet=True, probes=probes, return_info=True)
+            (iq + ld).backward()
+            return float(iq), float(ld), info["iterations"], [float(t.grad.reshape(-1)[0]) for t in (eps, kap, osc, noi)]
+        finally:
+            solvers.set_distributed_backend(None)
+
+    want = run(None)
+    be = D.DistBackend(min_rows=1000)
+    got = run(be)
+    assert be.solves >= 1
+    assert got[2] == want[2]
+    assert abs(got[0] - want[0]) <= 1e-7 * abs(want[0]) and abs(got[1] - want[1]) <= 1e-7 * abs(want[1])
+    for a, b in zip(got[3], want[3]):
+        assert abs(a - b) <= 1e-5 * max(abs(b), 1e-12), (got, want)
