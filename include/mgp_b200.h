@@ -216,42 +216,6 @@ int mgp_lap_spmv_tile_f64(const int32_t* wptr, const uint16_t* wcol, const doubl
                           const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift, const double* post,
                           const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
                           const double* dot_with, double* dot_out, void* dot_ws, void* stream);
-/* The same one-block-per-tile shape for 64-byte rows (ncols a multiple of 16 fp32 / 8 fp64): X rows staged with cp.async by the
- * whole block, streams read straight from global memory, overlap from the blocks resident per SM (no producer warps).
- * Same operation, reference lines, dot epilogue and alignment rules as mgp_lap_spmm_wi (no peer-memory mode). */
-int mgp_lap_spmm_tile64_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
-                            const int32_t* hcol, int32_t tile_rows, int32_t hmax, const float* shift, const float* post,
-                            const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n,
-                            int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws, void* stream);
-int mgp_lap_spmm_tile64_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag, const int32_t* hptr,
-                            const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift, const double* post,
-                            const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
-                            int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws, void* stream);
-/* EXPERIMENTAL, not dispatched by default (parity-tested on B200, not yet timed): quad-row SpMM (lap_spmm_quad.cu).  Walks the UNION columns of row quads so that one
- * shared-memory X-row load serves four matrix rows.  Streams from manifold_gp_b200/graph.py::quad_streams: qwptr[16 ntiles + 1]
- * (entry offsets per warp, multiples of 8), qidx[P] tile-local columns, qval[4 P] value slots (16-byte aligned), qrows[4 * 32 ntiles]
- * rows of every quad (-1 = none).  Same operation, reference lines, dot epilogue and alignment rules as mgp_lap_spmm_wi. */
-int mgp_lap_spmm_quad_f32(const int32_t* qwptr, const uint16_t* qidx, const float* qval, const int32_t* qrows, const float* diag,
-                          const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t hmax, const float* shift,
-                          const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,
-                          int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws, void* stream);
-int mgp_lap_spmm_quad_f64(const int32_t* qwptr, const uint16_t* qidx, const double* qval, const int32_t* qrows, const double* diag,
-                          const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift,
-                          const double* post, const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y,
-                          int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws, void* stream);
-/* EXPERIMENTAL, not dispatched by default, NOT yet run on a GPU: the quad-row walk inside the pipelined producer of
- * mgp_lap_spmm_wi (lap_spmm_quadpipe.cu).  qwptr padded like wptr (512 ceil(ntiles/32) + 4 ints), qnzmax = largest number of
- * stream entries of a tile (multiple of 8); everything else as mgp_lap_spmm_quad / mgp_lap_spmm_wi (no peer-memory mode). */
-int mgp_lap_spmm_qp_f32(const int32_t* qwptr, const uint16_t* qidx, const float* qval, const int32_t* qrows, const float* diag,
-                        const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t qnzmax, int32_t hmax,
-                        const float* shift, const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx,
-                        float* y, int64_t ldy, int64_t n, int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws,
-                        void* stream);
-int mgp_lap_spmm_qp_f64(const int32_t* qwptr, const uint16_t* qidx, const double* qval, const int32_t* qrows, const double* diag,
-                        const int32_t* hptr, const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t qnzmax, int32_t hmax,
-                        const double* shift, const double* post, const int32_t* xmap, const int32_t* ymap, const double* x,
-                        int64_t ldx, double* y, int64_t ldy, int64_t n, int32_t ncols, const double* dot_with, double* dot_out,
-                        void* dot_ws, void* stream);
 int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const float* a, int64_t n, float* aw, void* stream);
 int mgp_lap_wi_values_f64(const int32_t* rowptr, const int32_t* wptr, const double* a, int64_t n, double* aw, void* stream);
 int mgp_lap_spmm_wi_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,

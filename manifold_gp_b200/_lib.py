@@ -56,12 +56,6 @@ _SIG = {
     "mgp_lap_spmm_pipe_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_spmv_tile_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, P, P, P, P]),
     "mgp_lap_spmv_tile_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, P, P, P, P]),
-    "mgp_lap_spmm_tile64_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
-    "mgp_lap_spmm_tile64_f64": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
-    "mgp_lap_spmm_quad_f32": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
-    "mgp_lap_spmm_quad_f64": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
-    "mgp_lap_spmm_qp_f32": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
-    "mgp_lap_spmm_qp_f64": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P]),
     "mgp_lap_wi_values_f32": (c_int32, [P, P, P, c_int64, P, P]),
     "mgp_lap_wi_values_f64": (c_int32, [P, P, P, c_int64, P, P]),
     "mgp_lap_spmm_wi_f32": (c_int32, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, c_int64, P, c_int64, c_int64, c_int32, P, P, P, P, c_int32, c_int32, P, P, P]),

@@ -116,157 +116,6 @@ lap_spmv_tile_kernel(const int* __restrict__ wptr, const unsigned short* __restr
   }
 }
 
-// ---- the same shape for 64-byte rows (16 fp32 / 8 fp64 columns per pass): one block per tile, no producer warps ------------
-// The tile's X rows are staged with 16-byte cp.async by all 256 threads, the (index, value) streams are read straight from
-// global memory (coalesced, 4 steps in flight per warp); overlap comes from the ~5 blocks resident per SM.  Row walk and
-// lane <-> chunk rotation are those of lap_spmm_wi_kernel (same stream layout, same bank behaviour).
-template <typename T>
-__global__ void __launch_bounds__(kSvThreads)
-lap_spmm_tile64_kernel(const int* __restrict__ wptr, const unsigned short* __restrict__ wcol, const T* __restrict__ aw,
-                       const T* __restrict__ diag, const int* __restrict__ hptr, const int* __restrict__ hcol,
-                       const T* __restrict__ shift_p, const T* __restrict__ post, const int* __restrict__ xmap,
-                       const int* __restrict__ ymap, const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int64_t ldy,
-                       int64_t n, int c0, const T* __restrict__ dot_with, T* __restrict__ dot_out, T* __restrict__ partials,
-                       unsigned int* __restrict__ counter, int dot_is_x) {
-  constexpr int VEC = 16 / sizeof(T);
-  constexpr int CW = 4 * VEC;
-  constexpr int ROW_BYTES = 64;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* const xs = smem_raw;
-  const int t = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t row0 = (int64_t)t * kSvRows;
-  const int nrows = (int)min((int64_t)kSvRows, n - row0);
-  const int h0 = hptr[t], nh = hptr[t + 1] - h0;
-  {
-    const int ch = tid & 3;
-    const unsigned char* xb = reinterpret_cast<const unsigned char*>(x + c0) + ch * 16;
-    const int64_t ldxb = ldx * (int64_t)sizeof(T);
-    for (int rr = tid >> 2; rr < nrows + nh; rr += kSvThreads / 4) {
-      int64_t src = rr < nrows ? row0 + rr : (int64_t)__ldg(hcol + h0 + rr - nrows);
-      if (xmap) src = __ldg(xmap + src);
-      const int dst = rr < nrows ? rr : kSvRows + (rr - nrows);
-      cp_async16(xs + (size_t)dst * ROW_BYTES + ch * 16, xb + src * ldxb);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  }
-  __syncthreads();
-  const T shift = shift_p ? *shift_p : T(0);
-  const int slot = lane >> 2, l = lane & 3;
-  const int cbase = c0 + l * VEC;
-  const uint32_t o0 = (uint32_t)(((0 + l) & 3) * 16), o1 = (uint32_t)(((1 + l) & 3) * 16);
-  const uint32_t o2 = (uint32_t)(((2 + l) & 3) * 16), o3 = (uint32_t)(((3 + l) & 3) * 16);
-  T dsum[VEC];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) dsum[v] = T(0);
-  for (int wb = warp; wb < 16; wb += kSvThreads / 32) {
-    const int base = wptr[16 * t + wb];
-    const int steps = (wptr[16 * t + wb + 1] - base) >> 5;
-    const unsigned short* cp = wcol + base + lane;
-    const T* vp = aw + base + lane;
-    T acc[4][VEC];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[c][v] = T(0);
-    auto fma_row = [&](uint32_t j, T wv) {
-      const unsigned char* xr = xs + j * ROW_BYTES;
-      const Vec<T, VEC> x0 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o0);
-      const Vec<T, VEC> x1 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o1);
-      const Vec<T, VEC> x2 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o2);
-      const Vec<T, VEC> x3 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o3);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        acc[0][v] = fma(wv, x0.v[v], acc[0][v]);
-        acc[1][v] = fma(wv, x1.v[v], acc[1][v]);
-        acc[2][v] = fma(wv, x2.v[v], acc[2][v]);
-        acc[3][v] = fma(wv, x3.v[v], acc[3][v]);
-      }
-    };
-    int s = 0;
-    for (; s + 4 <= steps; s += 4) {
-      const uint32_t j0 = __ldcs(cp), j1 = __ldcs(cp + 32), j2 = __ldcs(cp + 64), j3 = __ldcs(cp + 96);
-      const T a0 = __ldcs(vp), a1 = __ldcs(vp + 32), a2 = __ldcs(vp + 64), a3 = __ldcs(vp + 96);
-      fma_row(j0, a0); fma_row(j1, a1); fma_row(j2, a2); fma_row(j3, a3);
-      cp += 128; vp += 128;
-    }
-    for (; s < steps; ++s) {
-      fma_row(__ldcs(cp), __ldcs(vp));
-      cp += 32; vp += 32;
-    }
-    // lane l ends up with chunk l complete: its own acc[0] plus acc[4 - d] of the lane d places further (mod 4) in the slot
-    T res[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) res[v] = acc[0][v];
-#pragma unroll
-    for (int d = 1; d < 4; ++d) {
-      const int src = (lane & ~3) | ((l + d) & 3);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) res[v] += __shfl_sync(0xffffffffu, acc[4 - d][v], src);
-    }
-    const int r = wb * 8 + slot;
-    if (r < nrows) {
-      const int64_t row = row0 + r;
-      const Vec<T, VEC> xi = *reinterpret_cast<const Vec<T, VEC>*>(xs + (size_t)r * ROW_BYTES + l * 16);
-      const T d = __ldg(diag + row) + shift;
-      const T po = post ? __ldg(post + row) : T(1);
-      Vec<T, VEC> out;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) out.v[v] = po * (d * xi.v[v] - res[v]);
-      const int64_t yrow = ymap ? (int64_t)__ldg(ymap + row) : row;
-      st_vec<T, VEC>(y + yrow * ldy + cbase, out);
-      if (dot_out) {
-        Vec<T, VEC> dw = xi;
-        if (!dot_is_x) {
-          const int64_t drow = xmap ? (int64_t)__ldg(xmap + row) : row;
-          dw = ldg_vec<T, VEC>(dot_with + drow * ldx + cbase);
-        }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) dsum[v] = fma(dw.v[v], out.v[v], dsum[v]);
-      }
-    }
-  }
-  if (dot_out) {
-    __syncthreads();
-    spmm_dot_epilogue<T, VEC, 4, CW, kSvThreads>(dsum, CW, c0, partials, counter, dot_out);
-  }
-}
-
-template <typename T>
-static int lap_spmm_tile64(const int* wptr, const unsigned short* wcol, const T* aw, const T* diag, const int* hptr,
-                           const int* hcol, int tile_rows, int hmax, const T* shift, const T* post, const int* xmap,
-                           const int* ymap, const T* x, int64_t ldx, T* y, int64_t ldy, int64_t n, int ncols, const T* dot_with,
-                           T* dot_out, void* dot_ws, cudaStream_t st) {
-  constexpr int VEC = 16 / sizeof(T);
-  constexpr int CW = 4 * VEC;
-  MGP_CHECK_ARG(wptr && wcol && aw && diag && hptr && hcol && x && y, "lap_spmm_tile64: null pointer");
-  MGP_CHECK_ARG(n > 0 && ncols > 0 && ldx >= ncols && ldy >= ncols && hmax >= 0, "lap_spmm_tile64: bad shape");
-  MGP_CHECK_ARG(x != y, "lap_spmm_tile64: X and Y must not alias");
-  MGP_CHECK_ARG((dot_out == nullptr) || (dot_with && dot_ws), "lap_spmm_tile64: dot epilogue needs dot_with and dot_ws");
-  const bool ok = tile_rows == kSvRows && (ncols % CW == 0) && (ldx % VEC == 0) && (ldy % VEC == 0) && (((uintptr_t)x) % 16 == 0) &&
-                  (((uintptr_t)y) % 16 == 0) && (dot_with == nullptr || ((uintptr_t)dot_with) % 16 == 0);
-  if (!ok) return MGP_EUNSUPPORTED;
-  const size_t smem = (size_t)(kSvRows + hmax + 4) * 64;
-  if (smem > 200 * 1024) return MGP_EUNSUPPORTED;
-  auto kern = lap_spmm_tile64_kernel<T>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    MGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  const int64_t ntiles = ceil_div(n, (int64_t)kSvRows);
-  if (dot_out && (size_t)ntiles * CW * sizeof(T) > kDotWsPartialBytes) return MGP_EUNSUPPORTED;   // per-tile partials must fit dot_ws
-  unsigned int* counter = dot_out ? reinterpret_cast<unsigned int*>(dot_ws) : nullptr;
-  T* partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
-  for (int c0 = 0; c0 < ncols; c0 += CW) {
-    kern<<<(unsigned)ntiles, kSvThreads, smem, st>>>(wptr, wcol, aw, diag, hptr, hcol, shift, post, xmap, ymap, x, ldx, y, ldy, n, c0,
-                                                    dot_out ? dot_with : nullptr, dot_out, partials, counter,
-                                                    (dot_out && dot_with == x) ? 1 : 0);
-    MGP_LAUNCH_CHECK();
-  }
-  return MGP_OK;
-}
-
 template <typename T>
 static int lap_spmv_tile(const int* wptr, const unsigned short* wcol, const T* aw, const T* diag, const int* hptr, const int* hcol,
                          int tile_rows, int hmax, const T* shift, const T* post, const int* xmap, const int* ymap, const T* x,
@@ -306,21 +155,6 @@ int mgp_lap_spmv_tile_f64(const int32_t* wptr, const uint16_t* wcol, const doubl
                           const double* dot_with, double* dot_out, void* dot_ws, void* stream) {
   return mgp::lap_spmv_tile<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, hmax, shift, post, xmap, ymap, x, ldx, y, ldy, n,
                                    dot_with, dot_out, dot_ws, (cudaStream_t)stream);
-}
-
-int mgp_lap_spmm_tile64_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
-                            const int32_t* hcol, int32_t tile_rows, int32_t hmax, const float* shift, const float* post,
-                            const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n,
-                            int32_t ncols, const float* dot_with, float* dot_out, void* dot_ws, void* stream) {
-  return mgp::lap_spmm_tile64<float>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, hmax, shift, post, xmap, ymap, x, ldx, y, ldy, n,
-                                     ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
-}
-int mgp_lap_spmm_tile64_f64(const int32_t* wptr, const uint16_t* wcol, const double* aw, const double* diag, const int32_t* hptr,
-                            const int32_t* hcol, int32_t tile_rows, int32_t hmax, const double* shift, const double* post,
-                            const int32_t* xmap, const int32_t* ymap, const double* x, int64_t ldx, double* y, int64_t ldy, int64_t n,
-                            int32_t ncols, const double* dot_with, double* dot_out, void* dot_ws, void* stream) {
-  return mgp::lap_spmm_tile64<double>(wptr, wcol, aw, diag, hptr, hcol, tile_rows, hmax, shift, post, xmap, ymap, x, ldx, y, ldy, n,
-                                      ncols, dot_with, dot_out, dot_ws, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -60,99 +60,6 @@ def attach_permutation(idx: torch.Tensor, perm: torch.Tensor) -> None:
         pass
 
 
-# ---- quad-row union lists (groundwork for the next SpMM generation) ------------------------------
-def quad_union_lists(rowptr: torch.Tensor, col: torch.Tensor, n: int, R: int = 128, row_pos: torch.Tensor = None):
-    """Group the rows of every ``R``-row tile into quads and merge the column lists of each quad.
-
-    Morton-adjacent rows of a kNN graph share most of their neighbours (measured: the union of a quad's column sets is 0.44
-    of the sum of their sizes, ``profiles/pair_stats.py``), so a kernel that walks UNION columns loads an X row once for four
-    matrix rows.  This is the layout-independent half of that format (pure index plumbing, any device; not used by the
-    current kernels):
-
-      qrows [Q, 4]  int64   rows of each quad (-1 = padding in the last tile), Q = ntiles * R / 4
-      qptr  [Q + 1] int64   offsets into the union lists
-      qcol  [U]     int64   union columns of each quad, ascending
-      qsrc  [U, 4]  int64   CSR entry that holds A[qrows[q, s], qcol[u]], or -1 if that row does not have the column
-                            (per-bandwidth values are then ``qval = where(qsrc >= 0, a[qsrc], 0)``)
-
-    ``row_pos`` [n]: position of each row inside its tile used to form the quads (rows at positions 4j .. 4j+3 share a
-    quad); default = the row's own order.  Pass a spatially coherent order (e.g. the Morton position before the in-tile
-    degree sort) to maximise the sharing."""
-    dev = rowptr.device
-    rp = rowptr.to(torch.int64)
-    nnz = int(rp[-1])
-    ntiles = (n + R - 1) // R
-    rows = torch.arange(n, device=dev, dtype=torch.int64)
-    if row_pos is None:
-        pos = rows % R
-    else:
-        # rank of the row inside its tile under the given order
-        tile = rows // R
-        order = torch.argsort(tile * (int(row_pos.max()) + 1) + row_pos.to(torch.int64), stable=True)
-        pos = torch.empty(n, dtype=torch.int64, device=dev)
-        pos[order] = rows - (rows // R) * R                     # consecutive ranks inside each tile (tiles are contiguous)
-    quad_of_row = (rows // R) * (R // 4) + pos // 4
-    slot_of_row = pos % 4
-    Q = ntiles * (R // 4)
-    qrows = torch.full((Q, 4), -1, dtype=torch.int64, device=dev)
-    qrows[quad_of_row, slot_of_row] = rows
-    erow = torch.repeat_interleave(rows, rp[1:] - rp[:-1])
-    ecol = col.to(torch.int64)[:nnz]
-    key = quad_of_row[erow] * n + ecol
-    ukey, inv = torch.unique(key, sorted=True, return_inverse=True)
-    U = int(ukey.numel())
-    qcol = ukey % n
-    counts = torch.bincount(ukey // n, minlength=Q)
-    qptr = torch.zeros(Q + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(counts, 0, out=qptr[1:])
-    qsrc = torch.full((U, 4), -1, dtype=torch.int64, device=dev)
-    qsrc[inv, slot_of_row[erow]] = torch.arange(nnz, device=dev, dtype=torch.int64)
-    return {"qrows": qrows, "qptr": qptr, "qcol": qcol, "qsrc": qsrc, "union_per_nonzero": U / max(nnz, 1)}
-
-
-def quad_streams(q: dict, lcol_of_entry: torch.Tensor, n: int, R: int = 128, warps: int = 16):
-    """Lane-consumption-order streams of the quad-row SpMM from ``quad_union_lists`` output.
-
-    Kernel shape this layout is for: ``warps`` consumer warps per tile, each owning R / 4 / warps quads (2 at R = 128, 16
-    warps); a quad is served by 16 / (quads per warp) ... concretely, at 2 quads per warp, by 16 lanes = 4 lane groups x 4
-    lanes: lane group g of the warp (g = lane >> 2, 0..7) works for quad 2w + (g >> 2) and takes every 4th union column of
-    it (sub-list g & 3); the 4 lanes of a group own the four 16-byte chunks of the 64-byte X row / output row.  Per step a
-    group needs ONE tile-local column index and ONE 4-wide value slot (the values of the quad's 4 rows for that column):
-
-      position(w, t, g) = qwptr[tile * warps + w] + 8 t + g          (steps t = 0 .. steps_w - 1, padded per warp)
-      qidx [P]     int32 (stored as uint16 by the kernel)  tile-local column of the union column, or 0 for padding
-      qent [P, 4]  int64  CSR entry of (row slot, that column) or -1  ->  values = where(qent >= 0, a[qent], 0)
-      qwptr [ntiles * warps + 1]  int64
-
-    ``lcol_of_entry`` [nnz]: the tile-local column (own rows 0 .. R-1, halo R ..) of every CSR entry, as the tile structure
-    already stores it.  Pure index plumbing (any device)."""
-    dev = q["qptr"].device
-    Q = q["qptr"].numel() - 1
-    qpw = (R // 4) // warps                       # quads per warp
-    assert qpw * warps * 4 == R and 8 % qpw == 0
-    gpq = 8 // qpw                                # lane groups (sub-lists) per quad
-    ulen = q["qptr"][1:] - q["qptr"][:-1]         # union columns per quad
-    steps_q = (ulen + gpq - 1) // gpq             # steps a quad needs
-    nw = Q // qpw
-    steps_w = steps_q.view(nw, qpw).max(dim=1).values
-    qwptr = torch.zeros(nw + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(steps_w * 8, 0, out=qwptr[1:])
-    P = int(qwptr[-1])
-    qidx = torch.zeros(P, dtype=torch.int32, device=dev)
-    qent = torch.full((P, 4), -1, dtype=torch.int64, device=dev)
-    # every union column u of quad k sits at sub-list (u_local % gpq), step (u_local // gpq)
-    U = q["qcol"].numel()
-    quad_of_u = torch.repeat_interleave(torch.arange(Q, device=dev, dtype=torch.int64), ulen)
-    u_local = torch.arange(U, device=dev, dtype=torch.int64) - q["qptr"][quad_of_u]
-    w_of_u = quad_of_u // qpw
-    g_of_u = (quad_of_u % qpw) * gpq + u_local % gpq
-    pos = qwptr[w_of_u] + 8 * (u_local // gpq) + g_of_u
-    qent[pos] = q["qsrc"]
-    first = q["qsrc"].clamp_min(-1).max(dim=1).values           # any valid entry of the union column carries its local column id
-    qidx[pos] = lcol_of_entry.to(torch.int64)[first].to(torch.int32)
-    return {"qwptr": qwptr, "qidx": qidx, "qent": qent, "entries": P, "padding": 1.0 - U / max(P, 1)}
-
-
 # ---- graph persistence (SURVEY.md 8(f-3)) ----------------------------------------------------------------------------------
 # The kNN graph is the most expensive setup step (O(N^2 d)) and is hyper-parameter independent, but the reference rebuilds
 # it in every run (riemann_kernel.py:40-42 builds it in __init__, nothing is written to disk).  One file holds what a
@@ -329,7 +236,7 @@ class GraphStructure:
             key = (tile_id << 20) | ((1 << 20) - 1 - deg[perm].clamp_max((1 << 20) - 1))
             order = torch.argsort(key, stable=True)
             perm = perm[order]
-            self.morton_pos = order                     # position of each final row in the spatial order (quad forming)
+            self.morton_pos = order                     # position of each final row in the spatial order
             self.perm = perm.contiguous()
             self.inv = torch.empty_like(self.perm)
             self.inv[self.perm] = torch.arange(self.perm.numel(), device=idx.device)
@@ -442,60 +349,6 @@ class GraphStructure:
             log.append(out)
         return out
 
-    # -- experimental quad-row streams (lap_spmm_quad.cu; SPMM_KERNEL = "quad" only) -------------------------------------
-    def quad_tiles(self):
-        q = self.__dict__.get("_quad_tiles")
-        if q is None:
-            t = self.build_tiles()
-            if t is None or "lcol" not in t or t["rows"] != 128:
-                return None
-            ul = quad_union_lists(self.rowptr, self.col, self.n, t["rows"], row_pos=self.morton_pos)
-            qs = quad_streams(ul, t["lcol"][:self.nnz], self.n, t["rows"], 16)
-            if int(qs["qwptr"][-1]) >= 2 ** 31:
-                return None
-            q = {"qwptr": qs["qwptr"].to(torch.int32).contiguous(), "qidx": qs["qidx"].to(torch.int16).contiguous(),
-                 "qent": qs["qent"], "qrows": ul["qrows"].to(torch.int32).contiguous(), "entries": qs["entries"],
-                 "union_per_nonzero": ul["union_per_nonzero"], "padding": qs["padding"]}
-            try:
-                # extras of the pipelined kernel (quadpipe, not yet validated): it bulk-copies metadata in chunks of 32 tiles
-                # (516 ints), so qwptr is padded like wi_streams pads wptr, and the streams get a zero tail
-                ntiles = (self.n + t["rows"] - 1) // t["rows"]
-                qwpad = torch.full((512 * ((ntiles + 31) // 32) + 4,), int(qs["qwptr"][-1]), dtype=torch.int32,
-                                   device=q["qwptr"].device)
-                qwpad[:q["qwptr"].numel()] = q["qwptr"]
-                tile_tot = qs["qwptr"][16::16] - qs["qwptr"][:-1:16]
-                q["qwptr_pad"] = qwpad.contiguous()
-                q["qnzmax"] = int(tile_tot.max()) if ntiles else 0
-                q["qidx_pad"] = torch.cat([q["qidx"], torch.zeros(64, dtype=torch.int16, device=q["qidx"].device)]).contiguous()
-            except Exception:                      # the validated quad path must not depend on these
-                pass
-            self._quad_tiles = q
-        return q
-
-    def quad_values(self, a: torch.Tensor) -> torch.Tensor:
-        """4-wide value slots of the quad streams for one value array (cached like the other layouts)."""
-        cache = self.__dict__.setdefault("_quad_value_cache", [])
-        for ref, ver, out in cache:
-            if ref.data_ptr() == a.data_ptr() and ver == a._version and ref.dtype == a.dtype:
-                return out
-        q = self.quad_tiles()
-        ent = q["qent"]
-        out = torch.where(ent >= 0, a.detach()[ent.clamp_min(0)], torch.zeros((), dtype=a.dtype, device=a.device)).contiguous()
-        cache.append((a.detach(), a._version, out))
-        del cache[:-2]
-        return out
-
-    def quad_values_padded(self, a: torch.Tensor) -> torch.Tensor:
-        """``quad_values`` flattened with a zero tail (the pipelined kernel's bulk copies never run off the end)."""
-        cache = self.__dict__.setdefault("_quad_value_pad_cache", [])
-        for ref, ver, out in cache:
-            if ref.data_ptr() == a.data_ptr() and ver == a._version and ref.dtype == a.dtype:
-                return out
-        out = torch.cat([self.quad_values(a).reshape(-1), torch.zeros(256, dtype=a.dtype, device=a.device)]).contiguous()
-        cache.append((a.detach(), a._version, out))
-        del cache[:-2]
-        return out
-
     def padded_values(self, a: torch.Tensor) -> torch.Tensor:
         return self._value_layout(a, "pad")
 
@@ -588,9 +441,8 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 
 
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
-TILE64_MODES = ("tile64",)   # add "auto" to make the one-block-per-tile kernel the default for 64-byte-row passes
 LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call launched (bench.py reports it)
-SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv" | "tile64" | "quad" | "quadpipe" (experimental)  (tests force each; "auto": wi, else pipe, else tiled, else csr)
+SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv"  (tests force each; "auto": wi, else pipe, else tiled, else csr; one column: spmv)
 
 
 def _note_kernel(name):
@@ -649,8 +501,8 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
     # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
     # kernel (X served from L1/L2) is faster
-    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad", "quadpipe"))
-    if SPMM_KERNEL in ("tiled", "pipe", "wi", "tile64", "quad", "quadpipe") and not use_tiled:
+    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi"))
+    if SPMM_KERNEL in ("tiled", "pipe", "wi") and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
         t = st.tiles
@@ -658,47 +510,6 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
         if peer_x is not None and not (pre is None and "wptr" in t):
             raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
-        if SPMM_KERNEL == "quadpipe":
-            q = st.quad_tiles() if (pre is None and peer_x is None) else None
-            if q is None or "qwptr_pad" not in q:
-                raise RuntimeError("lap_spmm: quadpipe kernel requested but this call / structure does not qualify")
-            rc = _lib.call_rc("mgp_lap_spmm_qp_" + sfx, ptr(q["qwptr_pad"]), ptr(q["qidx_pad"]), ptr(st.quad_values_padded(a)), ptr(q["qrows"]),
-                              ptr(diag), ptr(t["hptr"]), ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
-                              c_int32(q["qnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
-                              ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
-                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with),
-                              ptr(dot_out), ptr(ws), stream())
-            if rc != 0:
-                raise RuntimeError(f"mgp_lap_spmm_qp_{sfx} failed ({rc}): {_lib.last_error()}")
-            _note_kernel("lap_spmm_qp_kernel")
-            return out
-        if SPMM_KERNEL == "quad":
-            q = st.quad_tiles() if (pre is None and peer_x is None) else None
-            if q is None:
-                raise RuntimeError("lap_spmm: quad kernel requested but this call / structure does not qualify")
-            rc = _lib.call_rc("mgp_lap_spmm_quad_" + sfx, ptr(q["qwptr"]), ptr(q["qidx"]), ptr(st.quad_values(a)), ptr(q["qrows"]),
-                              ptr(diag), ptr(t["hptr"]), ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["hmax"]), ptr(shift_t),
-                              ptr(post), ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
-                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with),
-                              ptr(dot_out), ptr(ws), stream())
-            if rc != 0:
-                raise RuntimeError(f"mgp_lap_spmm_quad_{sfx} failed ({rc}): {_lib.last_error()}")
-            _note_kernel("lap_spmm_quad_kernel")
-            return out
-        if pre is None and "wptr" in t and SPMM_KERNEL in TILE64_MODES and peer_x is None:
-            aw = st.wi_values(a)
-            rc = _lib.call_rc("mgp_lap_spmm_tile64_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag), ptr(t["hptr"]),
-                              ptr(t["hcol"]), c_int32(t["rows"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
-                              ptr(st.perm32 if x_external else None), ptr(st.perm32 if y_external else None), ptr(x),
-                              c_int64(x.stride(0)), ptr(out), c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with),
-                              ptr(dot_out), ptr(ws), stream())
-            if rc == 0:
-                _note_kernel("lap_spmm_tile64_kernel")
-                return out
-            if rc != _lib.MGP_EUNSUPPORTED:
-                raise RuntimeError(f"mgp_lap_spmm_tile64_{sfx} failed ({rc}): {_lib.last_error()}")
-            if SPMM_KERNEL == "tile64":
-                raise RuntimeError("lap_spmm: tile64 kernel requested but this call does not qualify")
         if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi") or peer_x is not None):
             aw = st.wi_values(a)
             hcol = t["hcol_peer"] if peer_x is not None else t["hcol"]

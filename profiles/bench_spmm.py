@@ -49,10 +49,8 @@ for c in (1, 4, 8, 16):
     P = torch.randn(n, c, device=dev); V = torch.empty_like(P)
     dot = torch.zeros(c, device=dev)
     alg = nnz * 8 + n * (2 * c * 4 + 4)
-    for kern in ("csr", "tiled", "pipe", "wi", "tile64", "quad", "quadpipe"):
-        if (kern == "pipe" and c % 4) or (kern in ("wi", "tile64", "quad", "quadpipe") and c % 16) or (ONLY and kern not in ONLY):
-            continue
-        if kern in ("quad", "quadpipe") and not (ONLY and kern in ONLY):      # experimental: only on request
+    for kern in ("csr", "tiled", "pipe", "wi"):
+        if (kern == "pipe" and c % 4) or (kern == "wi" and c % 16) or (ONLY and kern not in ONLY):
             continue
         graph.SPMM_KERNEL = kern
         t = timeit(lambda: graph.lap_spmm(st, a, diag, P, shift=shift, out=V))

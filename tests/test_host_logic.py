@@ -105,102 +105,6 @@ def test_knn_graph_file_round_trip(tmp_path):
         graph.load_knn_graph(path, "cpu", x=x[:-1], k=k)
 
 
-def test_quad_union_lists_reproduce_the_matvec():
-    """graph.quad_union_lists (groundwork for the quad-row SpMM): walking union columns with 4-wide value slots reproduces
-    A x exactly, every CSR entry appears exactly once, and a spatially coherent row order shares more columns."""
-    import oracle
-    from manifold_gp_b200 import graph
-    n, k, R = 3000, 12, 128
-    x = oracle.datasets.torus(n, seed=3)
-    idx, val = oracle.knn_graph(x, k)
-    # symmetric CSR over both directions of every edge, rows in a spatially coherent (Morton) order
-    perm = graph.morton_permutation(x)
-    inv = torch.empty_like(perm); inv[perm] = torch.arange(n)
-    r = torch.cat([inv[idx[0]], inv[idx[1]]]); c = torch.cat([inv[idx[1]], inv[idx[0]]]); v = torch.cat([val, val]).double()
-    order = torch.argsort(r * n + c)
-    r, c, v = r[order], c[order], v[order]
-    rowptr = torch.zeros(n + 1, dtype=torch.int64); rowptr[1:] = torch.cumsum(torch.bincount(r, minlength=n), 0)
-    q = graph.quad_union_lists(rowptr, c, n, R)
-    assert int((q["qsrc"] >= 0).sum()) == r.numel()                         # every entry placed exactly once
-    assert torch.equal(torch.sort(q["qsrc"][q["qsrc"] >= 0]).values, torch.arange(r.numel()))
-    qval = torch.where(q["qsrc"] >= 0, v[q["qsrc"].clamp_min(0)], torch.zeros((), dtype=torch.float64))
-    xv = torch.randn(n, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
-    ref = torch.zeros(n, 3, dtype=torch.float64).index_add_(0, r, v.unsqueeze(1) * xv[c])
-    quad_of_u = torch.repeat_interleave(torch.arange(q["qptr"].numel() - 1), q["qptr"][1:] - q["qptr"][:-1])
-    y = torch.zeros(n, 3, dtype=torch.float64)
-    for s in range(4):
-        rows_s = q["qrows"][quad_of_u, s]
-        ok = rows_s >= 0
-        y.index_add_(0, rows_s[ok], qval[ok, s].unsqueeze(1) * xv[q["qcol"][ok]])
-    assert torch.allclose(y, ref, rtol=1e-12, atol=1e-12)
-    assert q["union_per_nonzero"] < 0.6                                      # Morton-adjacent quads share columns
-    # a scrambled in-tile order shares less; passing the coherent order back through row_pos restores the sharing
-    g = torch.Generator().manual_seed(1)
-    scr = torch.cat([t0 + torch.randperm(min(R, n - t0), generator=g) for t0 in range(0, n, R)])   # new -> old, tiles kept
-    sinv = torch.empty_like(scr); sinv[scr] = torch.arange(n)
-    r2, c2 = sinv[r], sinv[c]
-    o2 = torch.argsort(r2 * n + c2)
-    r2, c2 = r2[o2], c2[o2]
-    rp2 = torch.zeros(n + 1, dtype=torch.int64); rp2[1:] = torch.cumsum(torch.bincount(r2, minlength=n), 0)
-    q_bad = graph.quad_union_lists(rp2, c2, n, R)
-    q_fix = graph.quad_union_lists(rp2, c2, n, R, row_pos=scr % R)
-    assert q_bad["union_per_nonzero"] > q["union_per_nonzero"] + 0.05
-    assert abs(q_fix["union_per_nonzero"] - q["union_per_nonzero"]) < 1e-9
-
-
-def test_quad_streams_lane_walk_reproduces_the_matvec():
-    """graph.quad_streams: emulate the planned kernel's lane walk (16 warps per 128-row tile, 8 lane groups per warp, one
-    tile-local index + one 4-wide value slot per group and step) in torch and compare with the CSR product."""
-    import oracle
-    from manifold_gp_b200 import graph
-    n, k, R, W = 2000, 10, 128, 16
-    x = oracle.datasets.torus(n, seed=7)
-    idx, val = oracle.knn_graph(x, k)
-    perm = graph.morton_permutation(x)
-    inv = torch.empty_like(perm); inv[perm] = torch.arange(n)
-    r = torch.cat([inv[idx[0]], inv[idx[1]]]); c = torch.cat([inv[idx[1]], inv[idx[0]]]); v = torch.cat([val, val]).double()
-    order = torch.argsort(r * n + c)
-    r, c, v = r[order], c[order], v[order]
-    rowptr = torch.zeros(n + 1, dtype=torch.int64); rowptr[1:] = torch.cumsum(torch.bincount(r, minlength=n), 0)
-    ntiles = (n + R - 1) // R
-    # tile-local columns: own rows 0..R-1, halo rows R.. in ascending global order (what the tile structure stores)
-    tile_of_e = r // R
-    own = (c // R) == tile_of_e
-    lcol = torch.where(own, c % R, torch.zeros_like(c))
-    halo_lists = []
-    for t in range(ntiles):
-        m = (tile_of_e == t) & ~own
-        hl = torch.unique(c[m])
-        halo_lists.append(hl)
-        lcol[m] = R + torch.searchsorted(hl, c[m])
-    q = graph.quad_union_lists(rowptr, c, n, R)
-    s = graph.quad_streams(q, lcol, n, R, W)
-    assert s["padding"] < 0.35
-    qval = torch.where(s["qent"] >= 0, v[s["qent"].clamp_min(0)], torch.zeros((), dtype=torch.float64))
-    C = 16
-    X = torch.randn(n, C, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
-    ref = torch.zeros(n, C, dtype=torch.float64).index_add_(0, r, v.unsqueeze(1) * X[c])
-    Y = torch.zeros(n, C, dtype=torch.float64)
-    qpw, gpq = (R // 4) // W, 8 // ((R // 4) // W)
-    for t in range(ntiles):
-        xs = torch.cat([X[t * R:min(n, (t + 1) * R)], torch.zeros(max(0, (t + 1) * R - n), C, dtype=torch.float64), X[halo_lists[t]]])
-        for w in range(W):
-            base, end = int(s["qwptr"][t * W + w]), int(s["qwptr"][t * W + w + 1])
-            steps = (end - base) // 8
-            acc = torch.zeros(8, 4, C, dtype=torch.float64)                      # [lane group][row slot][columns]
-            for st in range(steps):
-                for g in range(8):
-                    pos = base + 8 * st + g
-                    acc[g] += qval[pos].unsqueeze(1) * xs[int(s["qidx"][pos])].unsqueeze(0)
-            for kq in range(qpw):                                               # reduce the sub-lists of each quad
-                tot = acc[kq * gpq:(kq + 1) * gpq].sum(0)
-                rows_q = q["qrows"][(t * W + w) * qpw + kq]
-                for slot in range(4):
-                    if int(rows_q[slot]) >= 0:
-                        Y[int(rows_q[slot])] = tot[slot]
-    assert torch.allclose(Y, ref, rtol=1e-12, atol=1e-12)
-
-
 _FAKE_LINEAR_OPERATOR = '''
 import torch
 
