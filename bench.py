@@ -349,10 +349,26 @@ def run_ours(args):
         "knn_tensor": knn_tensor,
         "clocks": clk.summary(),
     }
+    if not args.no_cfgb:
+        out["cfgB"] = cfgb_bench()
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(idx.cpu(), val.cpu(), n, eps)
     print(json.dumps(out))
     return out
+
+
+def cfgb_bench():
+    """BASELINE.json configs[1] end to end in a child process (profiles/run_cfgB.py: 70k x 784 cloud, k = 10 -> tcgen05 kNN graph
+    -> smallest-500 eigenpairs -> spectral features / out-of-sample extension -> semi-supervised posterior -> one 16-RHS
+    precision CG solve), stage timings and self-checks as that script reports them."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "run_cfgB.py")], capture_output=True, text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        return json.loads(line[-1])
+    except Exception as e:      # reported, never hidden
+        return {"error": repr(e)[:300]}
 
 
 def knn_tensor_bench(dev, n=70000, d=784, k=10):
@@ -499,6 +515,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=CFG["n"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfgb", action="store_true", help="skip the cfg-B end-to-end child run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

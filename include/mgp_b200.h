@@ -236,6 +236,10 @@ int mgp_lap_spmm_wi_f64(const int32_t* wptr, const uint16_t* wcol, const double*
  *   done_flag      device scalar (T): the launch is a no-op when it is non-zero (every CG kernel is, once converged);
  *   wait_flags     producers wait -- lazily, at the first halo row that lives on another rank -- until
  *                  wait_flags[rank][src] >= epoch for every src; nothing is published at kernel start;
+ *   publish_at_start  with wait_flags: block 0 ALSO publishes wait_flags[dst][rank] = epoch at kernel start ("everything enqueued
+ *                  before this launch is complete on my side", the semantics of mgp_lap_spmm_wi's sync_flags) -- the system-scope
+ *                  fence of the publish then overlaps the launch's own work instead of ending the producing kernel (measured at
+ *                  125k rows per rank: 4 us per launch);
  *   publish_flags  after ALL rows of Y are written (last block to finish, last column pass): publish_flags[dst][rank] = epoch
  *                  ("my Y is complete") -- the consumer of Y on another rank waits on it with wait_flags;
  *   ticket         device uint32 counter for that completion ticket (zeroed once; resets itself);
@@ -259,6 +263,8 @@ typedef struct mgp_wi_ext {
   int32_t ship_ncols;
   int32_t ep_add;
   const void* ep_coef;
+  int32_t publish_at_start;
+  int32_t reserved;
 } mgp_wi_ext;
 int mgp_lap_spmm_wi_ex_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
                            const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
@@ -390,13 +396,15 @@ int mgp_cg_peer_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, 
  * (iteration + 2) in rflag for the peers' next SpMM.  Same iterates, masks and stopping rules as linear_cg; convergence is noticed
  * one matvec later (the tested residual norm is the one entering the iteration) and no update is applied then.  s must be
  * zeroed, rflag published as 1 (mgp_peer_publish) and gamma_loc filled with the local |r_0|^2 before the first iteration.
+ * delta_loc != NULL: block 0 of THIS kernel ships (delta_loc, gamma_loc) to the peers first (the SpMM launch then needs no
+ * red_ptrs); rflag_ptrs == NULL: "r complete" is published by the next SpMM launch at its start (mgp_wi_ext.publish_at_start).
  * red_ptrs[r] -> T[2][2][world][128]; flags zeroed + barrier before each solve.  ld as mgp_cg_peer_rupdate. */
 int mgp_cg_peer_cgstep_f32(float* x, float* r, float* p, float* s, const float* w, int64_t ld, int64_t n, int32_t ncols, float* state,
-                           float* hist, int32_t max_hist, void* ws, float* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
-                           int32_t rank, int32_t world, void* stream);
+                           float* hist, int32_t max_hist, void* ws, float* gamma_loc, const float* delta_loc, void* red_ptrs, void* dflag_ptrs,
+                           void* rflag_ptrs, int32_t rank, int32_t world, void* stream);
 int mgp_cg_peer_cgstep_f64(double* x, double* r, double* p, double* s, const double* w, int64_t ld, int64_t n, int32_t ncols, double* state,
-                           double* hist, int32_t max_hist, void* ws, double* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
-                           int32_t rank, int32_t world, void* stream);
+                           double* hist, int32_t max_hist, void* ws, double* gamma_loc, const double* delta_loc, void* red_ptrs, void* dflag_ptrs,
+                           void* rflag_ptrs, int32_t rank, int32_t world, void* stream);
 /* flags[dst][rank] = value on every rank, after everything enqueued before on this stream (no waiting). */
 int mgp_peer_publish(void* flag_ptrs, uint32_t value, int32_t rank, int32_t world, void* stream);
 int mgp_peer_barrier(void* flag_ptrs, void* epoch_ctr, int32_t rank, int32_t world, void* stream);

@@ -1024,8 +1024,8 @@ template <typename T>
 __global__ void __launch_bounds__(kCgBlock)
 cg_peer_cgstep_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T* __restrict__ s, const T* __restrict__ wv_,
                       int ld, int64_t n, int ncols, T* __restrict__ state, T* __restrict__ hist, int max_hist, void* ws,
-                      T* __restrict__ gamma_loc, T* const* __restrict__ red_ptrs, unsigned int* const* __restrict__ dflag_ptrs,
-                      unsigned int* const* __restrict__ rflag_ptrs, int rank, int world) {
+                      T* __restrict__ gamma_loc, const T* __restrict__ delta_loc, T* const* __restrict__ red_ptrs,
+                      unsigned int* const* __restrict__ dflag_ptrs, unsigned int* const* __restrict__ rflag_ptrs, int rank, int world) {
   using V = typename V16<T>::type;
   constexpr int N = V16<T>::N;
   T* k = state + S_NARR * ncols;
@@ -1038,6 +1038,31 @@ cg_peer_cgstep_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T
   const int it = (int)k[K_ITER];
   const unsigned int epoch = (unsigned int)it + 1u;
   const int buf = (int)(epoch & 1u);
+  // The vector data of this thread's first element does not depend on the scalars: its five loads are in flight while the
+  // partials cross NVLink and the flags are polled.
+  const int64_t total = n * (int64_t)ld / N;
+  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
+  V* x4 = reinterpret_cast<V*>(x);
+  V* r4 = reinterpret_cast<V*>(r);
+  V* p4 = reinterpret_cast<V*>(p);
+  V* s4 = reinterpret_cast<V*>(s);
+  const V* w4 = reinterpret_cast<const V*>(wv_);
+  int64_t e = (int64_t)blockIdx.x * kCgBlock + tid;
+  V pq, sq, rq, wq, xq;
+  if (e < total) { pq = p4[e]; sq = s4[e]; rq = r4[e]; wq = w4[e]; xq = x4[e]; }
+  if (delta_loc && blockIdx.x == 0) {
+    // first half of the all-reduce done here (round-1 placement): ship this rank's (r.w, |r|^2) partials to every peer.  The
+    // system-scope fence sees only this block's few stores; shipping from the END of the SpMM launch instead
+    // (mgp_wi_ext.red_ptrs) put a fence behind ~10^5 outstanding stores on the critical path (+4 us per iteration at 125k rows).
+    for (int i = tid; i < world * ncols; i += kCgBlock) {
+      const int dst = i / ncols, c = i - dst * ncols;
+      peer_red_slot<T>(red_ptrs[dst], 0, buf, world, rank)[c] = delta_loc[c];
+      peer_red_slot<T>(red_ptrs[dst], 1, buf, world, rank)[c] = gamma_loc[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) st_release_sys(dflag_ptrs[tid] + rank, epoch);
+  }
   wait_flags(dflag_ptrs[rank], world, epoch);
   const T eps = k[K_EPS], stop = k[K_STOP];
   T local = T(0);
@@ -1090,17 +1115,12 @@ cg_peer_cgstep_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T
   T a[N], b[N], acc[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) { a[u] = al[c0 + u]; b[u] = be[c0 + u]; acc[u] = T(0); }
-  const int64_t total = n * (int64_t)ld / N;
-  const int64_t stride = (int64_t)gridDim.x * kCgBlock;
-  V* x4 = reinterpret_cast<V*>(x);
-  V* r4 = reinterpret_cast<V*>(r);
-  V* p4 = reinterpret_cast<V*>(p);
-  V* s4 = reinterpret_cast<V*>(s);
-  const V* w4 = reinterpret_cast<const V*>(wv_);
-#pragma unroll 2
-  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + tid; e < total; e += stride) {
+  while (e < total) {
+    const int64_t en = e + stride;
+    V pn, sn, rn4, wn, xn;
+    if (en < total) { pn = p4[en]; sn = s4[en]; rn4 = r4[en]; wn = w4[en]; xn = x4[en]; }      // next element in flight
     T pv[N], sv[N], rv[N], wv[N], xv[N];
-    v16_unpack<T>(p4[e], pv); v16_unpack<T>(s4[e], sv); v16_unpack<T>(r4[e], rv); v16_unpack<T>(w4[e], wv); v16_unpack<T>(x4[e], xv);
+    v16_unpack<T>(pq, pv); v16_unpack<T>(sq, sv); v16_unpack<T>(rq, rv); v16_unpack<T>(wq, wv); v16_unpack<T>(xq, xv);
 #pragma unroll
     for (int u = 0; u < N; ++u) {
       pv[u] = fma(b[u], pv[u], rv[u]);
@@ -1110,6 +1130,8 @@ cg_peer_cgstep_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T
       acc[u] = fma(rv[u], rv[u], acc[u]);
     }
     p4[e] = v16_pack<T>(pv); s4[e] = v16_pack<T>(sv); x4[e] = v16_pack<T>(xv); r4[e] = v16_pack<T>(rv);
+    pq = pn; sq = sn; rq = rn4; wq = wn; xq = xn;
+    e = en;
   }
   vec_block_partials<T, N>(acc, ld, ncols, w.partials + (int64_t)blockIdx.x * ncols);
   if (last_block_ticket(w.counter)) {
@@ -1130,9 +1152,11 @@ cg_peer_cgstep_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T
     }
     __syncthreads();
     if (tid == 0) { k[K_MEAN] = s_mean; k[K_ITER] = T(it + 1); }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < world) st_release_sys(rflag_ptrs[tid] + rank, epoch + 1u);     // r_{k+1} complete on this rank
+    if (rflag_ptrs) {                  // optional: publish "r_{k+1} complete" from here (else the next SpMM does, at its start)
+      __threadfence_system();
+      __syncthreads();
+      if (tid < world) st_release_sys(rflag_ptrs[tid] + rank, epoch + 1u);
+    }
   }
 }
 
@@ -1306,26 +1330,26 @@ int mgp_cg_peer_pxupdate_f64(double* x, double* p, const double* r, int64_t ld, 
   return MGP_OK;
 }
 int mgp_cg_peer_cgstep_f32(float* x, float* r, float* p, float* s, const float* w, int64_t ld, int64_t n, int32_t ncols, float* state,
-                           float* hist, int32_t max_hist, void* ws, float* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
-                           int32_t rank, int32_t world, void* stream) {
-  MGP_CHECK_ARG(x && r && p && s && w && state && ws && gamma_loc && red_ptrs && dflag_ptrs && rflag_ptrs && n > 0 && ncols > 0 &&
+                           float* hist, int32_t max_hist, void* ws, float* gamma_loc, const float* delta_loc, void* red_ptrs, void* dflag_ptrs,
+                           void* rflag_ptrs, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(x && r && p && s && w && state && ws && gamma_loc && red_ptrs && dflag_ptrs && n > 0 && ncols > 0 &&
                     world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_cgstep: bad arguments");
   if (!cg_vec_ok<float>(ld, x, r, p, s) || (((uintptr_t)w) % 16) != 0) return MGP_EUNSUPPORTED;
   int64_t g = ceil_div(n * ld / V16<float>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
   cg_peer_cgstep_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, r, p, s, w, (int)ld, n, ncols, state, hist, max_hist, ws,
-      gamma_loc, (float* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
+      gamma_loc, delta_loc, (float* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }
 int mgp_cg_peer_cgstep_f64(double* x, double* r, double* p, double* s, const double* w, int64_t ld, int64_t n, int32_t ncols, double* state,
-                           double* hist, int32_t max_hist, void* ws, double* gamma_loc, void* red_ptrs, void* dflag_ptrs, void* rflag_ptrs,
-                           int32_t rank, int32_t world, void* stream) {
-  MGP_CHECK_ARG(x && r && p && s && w && state && ws && gamma_loc && red_ptrs && dflag_ptrs && rflag_ptrs && n > 0 && ncols > 0 &&
+                           double* hist, int32_t max_hist, void* ws, double* gamma_loc, const double* delta_loc, void* red_ptrs, void* dflag_ptrs,
+                           void* rflag_ptrs, int32_t rank, int32_t world, void* stream) {
+  MGP_CHECK_ARG(x && r && p && s && w && state && ws && gamma_loc && red_ptrs && dflag_ptrs && n > 0 && ncols > 0 &&
                     world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_cgstep: bad arguments");
   if (!cg_vec_ok<double>(ld, x, r, p, s) || (((uintptr_t)w) % 16) != 0) return MGP_EUNSUPPORTED;
   int64_t g = ceil_div(n * ld / V16<double>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
   cg_peer_cgstep_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, r, p, s, w, (int)ld, n, ncols, state, hist, max_hist, ws,
-      gamma_loc, (double* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
+      gamma_loc, delta_loc, (double* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

@@ -507,6 +507,10 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
     MGP_CHECK_ARG(g.red_ptrs == nullptr || (g.red_flags && dot_out && g.ship_ncols > 0 && g.ship_ncols <= 128 && g.ship_ncols <= ncols),
                   "lap_spmm_wi_ex: shipping the dot partials needs red_flags, dot_out and 0 < ship_ncols <= min(128, ncols)");
     MGP_CHECK_ARG(sync_flags == nullptr || g.wait_flags == nullptr, "lap_spmm_wi_ex: sync_flags and wait_flags are exclusive");
+    if (ext->publish_at_start && g.wait_flags) {      // the round-1 barrier form: block 0 publishes at kernel start, lazy wait
+      g.sync_flags = g.wait_flags;
+      g.wait_flags = nullptr;
+    }
   }
   g.ntiles = (int)ceil_div(n, (int64_t)R);
   g.lmax = (lmax + 3) & ~3;

@@ -449,6 +449,7 @@ class PeerCG(DistCG):
             self.s = torch.zeros((op.n_loc, self.ld), dtype=dtype, device=dev)
             self.gamma_loc = torch.zeros(ncols, dtype=dtype, device=dev)
             self.tickets = torch.zeros(8 * max(nstage, 1), dtype=torch.int32, device=dev)     # one 32-byte slot per SpMM stage
+            self.publish_at_end = os.environ.get("MGP_PEER_PUBLISH", "start") == "end"
         self.mem.sync()
 
     # -- building blocks -----------------------------------------------------------------------------------------------
@@ -494,11 +495,15 @@ class PeerCG(DistCG):
             last = s == nstage - 1
             dst, dst_ptrs = (self.v, None) if last else self.tmps[s % len(self.tmps)]
             ep_coef, ep_add = eps_[s]
-            ext = _lib.wi_ext(done_flag=self.done_scalar, wait_flags=self.flag_tabs[s],
-                              publish_flags=None if last else self.flag_tabs[s + 1], ticket=self.tickets[8 * s:],
-                              red_ptrs=self.red2_ptrs if last else None, red_flags=self.flag_tabs[nstage] if last else None,
-                              ship_extra=self.gamma_loc if last else None, ship_ncols=c if last else 0,
-                              ep_coef=ep_coef, ep_add=ep_add)
+            if self.publish_at_end:      # A/B form: flags / partials leave from the END of the producing launch
+                ext = _lib.wi_ext(done_flag=self.done_scalar, wait_flags=self.flag_tabs[s],
+                                  publish_flags=None if last else self.flag_tabs[s + 1], ticket=self.tickets[8 * s:],
+                                  red_ptrs=self.red2_ptrs if last else None, red_flags=self.flag_tabs[nstage] if last else None,
+                                  ship_extra=self.gamma_loc if last else None, ship_ncols=c if last else 0,
+                                  ep_coef=ep_coef, ep_add=ep_add)
+            else:                        # default: "source complete" published by block 0 of the CONSUMING launch at its start
+                ext = _lib.wi_ext(done_flag=self.done_scalar, wait_flags=self.flag_tabs[s], publish_at_start=True,
+                                  ep_coef=ep_coef, ep_add=ep_add)
             graph.lap_spmm(op.st, op.a, op.diag, src[:n_loc, :c], shift=op.shift, out=dst[:n_loc, :c],
                            dot_with=self.r[:n_loc, :c] if (last or ep_add) else None, dot_out=self.rbuf_pap if last else None,
                            peer_x=src_ptrs, peer_ext=(self.rank, self.iter_scalar, ext))
@@ -514,7 +519,8 @@ class PeerCG(DistCG):
             self._matvec_cg1()
             _lib.call("mgp_cg_peer_cgstep_" + sfx, ptr(self.x), ptr(self.r), ptr(self.p), ptr(self.s), ptr(self.v), c_int64(ld),
                       c_int64(n_loc), c_int32(c), ptr(self.state), ptr(self.hist), c_int32(self.max_hist), ptr(self.ws),
-                      ptr(self.gamma_loc), ptr(self.red2_ptrs), ptr(self.flag_tabs[nu]), ptr(self.flag_tabs[0]),
+                      ptr(self.gamma_loc), ptr(None if self.publish_at_end else self.rbuf_pap), ptr(self.red2_ptrs),
+                      ptr(self.flag_tabs[nu]), ptr(self.flag_tabs[0] if self.publish_at_end else None),
                       c_int32(self.rank), c_int32(self.world), stream())
             return
         self._matvec()
@@ -546,7 +552,8 @@ class PeerCG(DistCG):
         import ctypes
         self.gamma_loc.copy_(self.rbuf)                          # cg_dist_init left this rank's |r_0|^2 column sums there
         self.s.zero_()
-        _lib.call("mgp_peer_publish", ptr(self.flag_tabs[0]), ctypes.c_uint32(1), c_int32(self.rank), c_int32(self.world), stream())
+        if self.publish_at_end:
+            _lib.call("mgp_peer_publish", ptr(self.flag_tabs[0]), ctypes.c_uint32(1), c_int32(self.rank), c_int32(self.world), stream())
 
     def solve(self, b_loc: torch.Tensor):
         if self.mode in ("cg1", "fused"):
