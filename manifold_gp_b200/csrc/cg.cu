@@ -112,10 +112,14 @@ __device__ __forceinline__ T block_sum_t0(T v) {
 // per-thread accumulators of the vectorised kernels (thread t holds columns (t*N) % ld .. +N-1) -> one partial per column of
 // the block: lanes with equal columns are combined by a shuffle tree, the 8 warps through shared memory (fixed order)
 template <typename T, int N>
-__device__ __forceinline__ void vec_block_partials(const T (&acc)[N], int ld, int ncols, T* dst /* partials of this block */) {
+__device__ __forceinline__ void vec_block_partials(const T (&acc)[N], int ld, int ncols, T* dst /* partials of this block */,
+                                                   int col0 = -1 /* first column held by this thread; default (tid * N) % ld */) {
   __shared__ T wpart[kCgBlock / 32][kCgMaxCols];
+  __shared__ int wblock[kCgBlock / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int groups = ld / N;                       // threads per row of the vector; a power of two
+  const int span = 32 * N;                         // columns a warp covers when groups >= 32 (one aligned block of the row)
+  if (col0 < 0) col0 = (tid * N) % ld;             // threads whose indices are congruent mod `groups` hold the same columns
   T a[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) {
@@ -123,19 +127,19 @@ __device__ __forceinline__ void vec_block_partials(const T (&acc)[N], int ld, in
     for (int o = groups; o < 32; o <<= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
   }
   if (groups >= 32) {
-    // a warp covers 32 * N consecutive columns starting at ((warp * 32) % groups) * N: warps with equal start are combined below
+    if (lane == 0) wblock[warp] = col0 / span;
 #pragma unroll
-    for (int u = 0; u < N; ++u) wpart[warp][(tid * N) % ld + u] = a[u];
+    for (int u = 0; u < N; ++u) wpart[warp][col0 + u] = a[u];
   } else if (lane < groups) {
 #pragma unroll
-    for (int u = 0; u < N; ++u) wpart[warp][lane * N + u] = a[u];
+    for (int u = 0; u < N; ++u) wpart[warp][col0 + u] = a[u];
   }
   __syncthreads();
   if (tid < ncols) {
     T s = T(0);
     if (groups >= 32) {
-      const int wpr = groups / 32;                 // warps per row of the vector
-      for (int w = (tid / (32 * N)) % wpr; w < kCgBlock / 32; w += wpr) s += wpart[w][tid];
+      for (int w = 0; w < kCgBlock / 32; ++w)
+        if (wblock[w] == tid / span) s += wpart[w][tid];
     } else {
 #pragma unroll
       for (int w = 0; w < kCgBlock / 32; ++w) s += wpart[w][tid];
@@ -624,7 +628,8 @@ cg_rupdate_vec_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_
   const T eps = k[K_EPS];
   for (int c = tid; c < ld; c += kCgBlock) al[c] = c < ncols ? cg_alpha_of<T>(state, ncols, c, eps) : T(0);
   __syncthreads();
-  const int c0 = (tid * N) % ld;          // this thread's columns: constant because (blockDim * N) % ld == 0
+  // reversed walk (below): element total-1-q of thread q = tid (mod ld/N) has the MIRRORED columns
+  const int c0 = (ld - ((tid + 1) * N) % ld) % ld;
   T a[N], acc[N];
 #pragma unroll
   for (int u = 0; u < N; ++u) { a[u] = al[c0 + u]; acc[u] = T(0); }
@@ -632,8 +637,13 @@ cg_rupdate_vec_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_
   const int64_t stride = (int64_t)gridDim.x * kCgBlock;
   V* r4 = reinterpret_cast<V*>(r);
   const V* v4 = reinterpret_cast<const V*>(v);
+  // Walks the vectors from the END: the matvec that produced v wrote its rows in ascending tile order, so the tail of v is
+  // what is still in L2; the p / x pass that follows walks ascending and meets the rows of r this pass wrote last.
+  // (total * N) % ld == 0 and (kCgBlock * N) % ld == 0, so element total-1-q has the columns of a thread whose index is the
+  // mirror image: the per-thread column map is re-derived for the reversed index.
 #pragma unroll 4
-  for (int64_t e = (int64_t)blockIdx.x * kCgBlock + tid; e < total; e += stride) {
+  for (int64_t q = (int64_t)blockIdx.x * kCgBlock + tid; q < total; q += stride) {
+    const int64_t e = total - 1 - q;
     T vv[N], rv[N];
     v16_unpack<T>(__ldcs(v4 + e), vv); v16_unpack<T>(r4[e], rv);
 #pragma unroll
@@ -643,7 +653,7 @@ cg_rupdate_vec_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_
     }
     r4[e] = v16_pack<T>(rv);
   }
-  vec_block_partials<T, N>(acc, ld, ncols, w.partials + (int64_t)blockIdx.x * ncols);
+  vec_block_partials<T, N>(acc, ld, ncols, w.partials + (int64_t)blockIdx.x * ncols, c0);
   if (last_block_ticket(w.counter)) {
     __shared__ T tot[kCgMaxCols];
     last_block_reduce<T>(w.partials, ncols, tot);

@@ -96,6 +96,23 @@ __host__ __device__ inline size_t wi_stage_bytes(int lmax, int nzcap) {
 }
 __host__ __device__ inline size_t wi_ring_bytes(int hmax) { return 2 * (size_t)kWiMetaBytes + (size_t)kWiIdSlots * hmax * 4; }
 
+// packed fp32 pairs (sm_100: fma.rn.f32x2 -> FFMA2)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(double, double) { return 0ull; }     // never called (fp64 keeps scalar FMAs)
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t, double&, double&) {}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 template <int PW>
 __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory"); }
 
@@ -335,26 +352,58 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         for (int v = 0; v < VEC; ++v) acc[c][v] = T(0);
       uint32_t j = cp[0];
       T wv = vp[0];
-#pragma unroll 2
-      for (int t = 0; t < steps; ++t) {
-        const uint32_t jn = cp[32];                  // next step in flight (the last one reads into the next block: unused)
-        const T wn = vp[32];
-        cp += 32;
-        vp += 32;
-        const unsigned char* xr = xs + j * ROW_BYTES;
-        const Vec<T, VEC> x0 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o0);
-        const Vec<T, VEC> x1 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o1);
-        const Vec<T, VEC> x2 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o2);
-        const Vec<T, VEC> x3 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o3);
+      if constexpr (sizeof(T) == 4) {
+        // fp32: packed FMAs (fma.rn.f32x2, SASS FFMA2) -- two IEEE fused multiply-adds per issue slot, bit-identical results.
+        // The walk is issue-bound as much as shared-memory bound (ncu source page): 16 FFMA -> 8 FFMA2 per nonzero.
+        uint64_t a2[4][2];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          acc[0][v] = fma(wv, x0.v[v], acc[0][v]);
-          acc[1][v] = fma(wv, x1.v[v], acc[1][v]);
-          acc[2][v] = fma(wv, x2.v[v], acc[2][v]);
-          acc[3][v] = fma(wv, x3.v[v], acc[3][v]);
+        for (int c = 0; c < 4; ++c) { a2[c][0] = 0ull; a2[c][1] = 0ull; }
+#pragma unroll 2
+        for (int t = 0; t < steps; ++t) {
+          const uint32_t jn = cp[32];                // next step in flight (the last one reads into the next block: unused)
+          const T wn = vp[32];
+          cp += 32;
+          vp += 32;
+          const unsigned char* xr = xs + j * ROW_BYTES;
+          const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(xr + o0);
+          const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(xr + o1);
+          const ulonglong2 x2 = *reinterpret_cast<const ulonglong2*>(xr + o2);
+          const ulonglong2 x3 = *reinterpret_cast<const ulonglong2*>(xr + o3);
+          const uint64_t w2 = pack_f32x2(wv, wv);
+          a2[0][0] = ffma2(w2, x0.x, a2[0][0]); a2[0][1] = ffma2(w2, x0.y, a2[0][1]);
+          a2[1][0] = ffma2(w2, x1.x, a2[1][0]); a2[1][1] = ffma2(w2, x1.y, a2[1][1]);
+          a2[2][0] = ffma2(w2, x2.x, a2[2][0]); a2[2][1] = ffma2(w2, x2.y, a2[2][1]);
+          a2[3][0] = ffma2(w2, x3.x, a2[3][0]); a2[3][1] = ffma2(w2, x3.y, a2[3][1]);
+          j = jn;
+          wv = wn;
         }
-        j = jn;
-        wv = wn;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          unpack_f32x2(a2[c][0], acc[c][0], acc[c][1]);
+          unpack_f32x2(a2[c][1], acc[c][2], acc[c][3]);
+        }
+      } else {
+#pragma unroll 2
+        for (int t = 0; t < steps; ++t) {
+          const uint32_t jn = cp[32];                // next step in flight (the last one reads into the next block: unused)
+          const T wn = vp[32];
+          cp += 32;
+          vp += 32;
+          const unsigned char* xr = xs + j * ROW_BYTES;
+          const Vec<T, VEC> x0 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o0);
+          const Vec<T, VEC> x1 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o1);
+          const Vec<T, VEC> x2 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o2);
+          const Vec<T, VEC> x3 = *reinterpret_cast<const Vec<T, VEC>*>(xr + o3);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            acc[0][v] = fma(wv, x0.v[v], acc[0][v]);
+            acc[1][v] = fma(wv, x1.v[v], acc[1][v]);
+            acc[2][v] = fma(wv, x2.v[v], acc[2][v]);
+            acc[3][v] = fma(wv, x3.v[v], acc[3][v]);
+          }
+          j = jn;
+          wv = wn;
+        }
       }
       // acc[c] of lane l holds chunk (c + l) mod 4 of the slot's partial sums; lane l ends up with chunk l complete:
       // its own acc[0] plus acc[4 - d] of the lane d places further (mod 4) in the slot, d = 1..3

@@ -67,7 +67,7 @@ __device__ __forceinline__ bool spmm_dot_epilogue(T (&dsum)[VEC], int cw, int c0
     for (int w = 0; w < BLOCK / 32; ++w) s += sm_dot[w][tid];
     partials[(int64_t)blockIdx.x * cw + tid] = s;
   }
-  const bool is_last_block = last_block_ticket(counter);
+  const bool is_last_block = last_block_ticket_writers(counter, tid < cw);
   if (is_last_block) {
     const int c = tid % cw;
     const int lanes_per_col = BLOCK / cw;  // cw <= 32

@@ -716,11 +716,14 @@ def _collectives_note(cg, transport, nu):
     mode = getattr(cg, "mode", "unfused")
     halo = "read from the owners' vectors over NVLink inside the SpMM"
     if mode == "cg1":
+        at_end = bool(getattr(cg, "publish_at_end", False))
         return {"launches": nu + 1, "sync_points": nu + 1,
-                "all_reduce": "1 (Chronopoulos-Gear single-reduction CG): (r.w, |r|^2) partials shipped by the last block of the last "
-                              "SpMM launch, added in rank order at the start of the one vector kernel",
-                "barrier": f"{nu} 'vector complete' flags, published by the last block of the PRODUCING kernel, waited for at the "
-                           "consumer's first remote halo row", "halo": halo}
+                "all_reduce": "1 (Chronopoulos-Gear single-reduction CG): (r.w, |r|^2) partials shipped by "
+                              + ("the last block of the last SpMM launch" if at_end else "block 0 of the one vector kernel at its start")
+                              + ", added in rank order by every block of that kernel",
+                "barrier": f"{nu} 'source vector complete' flags, published "
+                           + ("by the last block of the PRODUCING kernel" if at_end else "by block 0 of the CONSUMING SpMM launch at its start")
+                           + ", waited for at the consumer's first remote halo row", "halo": halo}
     if mode == "fused":
         return {"launches": nu + 2, "sync_points": nu + 2,
                 "barrier": "inside the SpMM launches (flags over NVLink, published at kernel start, waited on at the first remote halo row)",
