@@ -85,7 +85,8 @@ struct WiArgs {
   int last_pass;                       // 1 on the launch of the last column pass
   const T* ep_coef;                    // optional epilogue: Y <- coef * Y (+ ADD) with coef = *ep_coef; the dot epilogue sees the scaled Y
   int ep_add;                          // 1: ADD = dot_with (rows like X; no dot product on such a launch) -- y = add + coef * (A' x)
-  int debug;     // timing experiments only (MGP_WI_DEBUG bit mask): 1 = consumers skip the row walk, 2 = producers skip the halo rows
+  int debug;     // timing experiments only (MGP_WI_DEBUG bit mask): 1 = consumers skip the row walk, 2 = producers skip the halo rows,
+                 // 4 = one elected producer warp polls the barriers and releases the others through a named barrier (slower)
                  // (same-process A/B on B200, cfg-C: 150 us full, 104 without halo copies, 90 without the walk, 62 with neither)
 };
 
@@ -111,6 +112,13 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
+}
+
+__device__ __forceinline__ void ffma2_acc(uint64_t& c, uint64_t a, uint64_t b) {       // c += a * b (pairwise, in place)
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void lds_v2b64(uint32_t addr, uint64_t& lo, uint64_t& hi) {   // 16-byte shared load as two f32 pairs
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
 }
 
 template <int PW>
@@ -183,6 +191,14 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
 #pragma unroll
   for (int v = 0; v < VEC; ++v) dsum[v] = T(0);
 
+  // Register re-partition between the warp-specialised halves (PW == 16: 1024 threads = 64 registers each at launch): the
+  // producers issue copies and need few registers, the consumers' walk is register-starved at 64 (ncu source page, round 2: the
+  // unrolled step re-materialised the stage base and shuffled accumulator pairs with 8 IMAD.MOV per 2 steps).  setmaxnreg is
+  // warpgroup-granular; producers = warpgroups 0..3, consumers = warpgroups 4..7; 16 x 32 x (40 + 88) = 65536 registers.
+  if constexpr (PW == 16 && sizeof(T) == 4) {
+    if (warp < kWiProducerWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+  }
   if (warp < kWiProducerWarps) {
     // =================================================== producer ===================================================
     const int pw = warp, sub = lane >> 2, ch = lane & 3;          // producer warp / row of a pass / 16-byte chunk
@@ -228,6 +244,17 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
       unsigned short* const cs = reinterpret_cast<unsigned short*>(vs + g.nzcap);
       int* const rp = reinterpret_cast<int*>(cs + g.nzcap);
       const int c = t >> 5;
+      // Experiment (MGP_WI_DEBUG bit 4): ONE producer warp polls for this tile's three conditions and releases the others
+      // through the named barrier.  Measured in one process on B200 (cfg-C, C = 16): 124.9 us against 121.1 us with every
+      // producer warp polling for itself -- the extra barrier per tile costs more than the polling it saves.  Off by default.
+      if (g.debug & 4) {
+        if (pw == 0) {
+          wait_meta(c);
+          mbar_wait(&ids_bar[i % kWiIdSlots], (uint32_t)((i / kWiIdSlots) & 1));
+          mbar_wait(&empty_bar[s], ph ^ 1);
+        }
+        producers_sync<PW>();
+      }
       wait_meta(c);                                                // passes at once except on the first tile of a chunk
       const int* wp = meta_w(c) + 16 * (t & 31);
       const int* hp = meta_h(c) + (t & 31);
@@ -358,22 +385,27 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         uint64_t a2[4][2];
 #pragma unroll
         for (int c = 0; c < 4; ++c) { a2[c][0] = 0ull; a2[c][1] = 0ull; }
+        // 32-bit shared-window addresses, one base per chunk of this lane's rotation: a step is 1 shift + 4 adds of address
+        // arithmetic (the generic-pointer form re-derived the stage base inside the loop)
+        const uint32_t xb = smem_u32(xs);
+        const uint32_t b0 = xb + o0, b1 = xb + o1, b2 = xb + o2, b3 = xb + o3;
 #pragma unroll 2
         for (int t = 0; t < steps; ++t) {
           const uint32_t jn = cp[32];                // next step in flight (the last one reads into the next block: unused)
           const T wn = vp[32];
           cp += 32;
           vp += 32;
-          const unsigned char* xr = xs + j * ROW_BYTES;
-          const ulonglong2 x0 = *reinterpret_cast<const ulonglong2*>(xr + o0);
-          const ulonglong2 x1 = *reinterpret_cast<const ulonglong2*>(xr + o1);
-          const ulonglong2 x2 = *reinterpret_cast<const ulonglong2*>(xr + o2);
-          const ulonglong2 x3 = *reinterpret_cast<const ulonglong2*>(xr + o3);
+          const uint32_t off = j << 6;               // j * ROW_BYTES
+          uint64_t x00, x01, x10, x11, x20, x21, x30, x31;
+          lds_v2b64(b0 + off, x00, x01);
+          lds_v2b64(b1 + off, x10, x11);
+          lds_v2b64(b2 + off, x20, x21);
+          lds_v2b64(b3 + off, x30, x31);
           const uint64_t w2 = pack_f32x2(wv, wv);
-          a2[0][0] = ffma2(w2, x0.x, a2[0][0]); a2[0][1] = ffma2(w2, x0.y, a2[0][1]);
-          a2[1][0] = ffma2(w2, x1.x, a2[1][0]); a2[1][1] = ffma2(w2, x1.y, a2[1][1]);
-          a2[2][0] = ffma2(w2, x2.x, a2[2][0]); a2[2][1] = ffma2(w2, x2.y, a2[2][1]);
-          a2[3][0] = ffma2(w2, x3.x, a2[3][0]); a2[3][1] = ffma2(w2, x3.y, a2[3][1]);
+          ffma2_acc(a2[0][0], w2, x00); ffma2_acc(a2[0][1], w2, x01);
+          ffma2_acc(a2[1][0], w2, x10); ffma2_acc(a2[1][1], w2, x11);
+          ffma2_acc(a2[2][0], w2, x20); ffma2_acc(a2[2][1], w2, x21);
+          ffma2_acc(a2[3][0], w2, x30); ffma2_acc(a2[3][1], w2, x31);
           j = jn;
           wv = wn;
         }

@@ -19,32 +19,28 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 // Bounded wait: a logic error traps (the launch fails with an error) instead of hanging the GPU.
-// Round 2: the r01 loop (try_wait + spin counter + compare + branch, no suspend hint) was the single hottest instruction
-// block of the C = 16 SpMM -- ncu source page of lap_spmm_wi_kernel<float,16>: 4.15 M + 1.92 M iterations x 6 instructions =
-// 28 % of all issued warp instructions were producers / consumers polling a barrier, on a kernel whose issue slots are 68 %
-// busy.  Now: one plain try_wait on the fast path; on the slow path try_wait with a suspend-time hint (the warp sleeps in
-// hardware until the phase completes or the hint expires) and a wall-clock guard read only there.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
+// Round 2, from the ncu source page of lap_spmm_wi_kernel<float,16> (per-SASS-line executed counts): the r01 loop (try_wait + spin
+// counter + compare + branch) ran 4.15 M + 1.92 M iterations per launch -- 28 % of all issued warp instructions were 16 producer
+// and 16 consumer warps polling barriers, on a kernel whose issue slots are 68 % busy.  A suspend-time hint on try_wait did not
+// change that (the hardware still returns within tens of ns; measured 2.06 M iterations).  Now: one plain try_wait on the fast
+// path; on the slow path the warp SLEEPS (nanosleep, no issue slots) between polls, and only one producer warp polls at all
+// (lap_spmm_wi.cu releases the others through a named barrier, which blocks in hardware).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
   asm volatile(
       "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
       : "=r"(done)
-      : "r"(addr), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
-  if (done) return;
-  uint64_t t0 = 0;
-  for (;;) {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.b32 %0, 1, 0, p; }"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(200000u)      // suspend-time hint in ns
-        : "memory");
-    if (done) return;
-    uint64_t now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 20000000000ull) __trap();   // 20 s
+  return done != 0;
+}
+template <unsigned SLEEP_NS = 96>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_test(bar, parity)) return;
+  for (uint32_t spins = 0;; ++spins) {
+    __nanosleep(SLEEP_NS);
+    if (mbar_test(bar, parity)) return;
+    if (spins > (1u << 26)) __trap();               // >= 6 s of sleeping alone
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

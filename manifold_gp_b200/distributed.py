@@ -575,6 +575,83 @@ class PeerCG(DistCG):
         return solvers._tridiag_from_hist(self.hist.cpu(), rows, self.n_tridiag, self.dt).to(self.dev)
 
 
+def dist_lanczos_tridiag(dop: "DistPrecision", max_iter: int, init_vec_loc: torch.Tensor, tol: float = 1e-5, group=None):
+    """Row-partitioned Lanczos with full re-orthogonalisation (``solvers.lanczos_tridiag`` over several GPUs; the reference's
+    ``GraphLaplacianOperator.diagonalization`` path, graph_laplacian_operator.py:132-135, SURVEY.md 8e "CG / Lanczos").
+
+    ``dop``: a ``DistPrecision`` (with ``nu = 1`` and ``shift = 0`` it is the Laplacian itself).  Every rank holds its rows of
+    the Lanczos vectors; per step: halo exchange + local fused SpMV, local ``Q^T r`` partial dots (``mgp_lanczos_dots``),
+    ONE all-reduce of ``[j]`` floats, local ``r -= Q c`` + norm partial (``mgp_lanczos_axpy``), one all-reduce of the norm;
+    check passes as in the single-GPU driver.  Returns (q_loc [steps, n_loc], t [steps, steps]) -- ``t`` identical on every
+    rank, so ``eigh(t)`` and the Ritz vectors ``q_loc^T V`` need no further communication."""
+    from . import _lib
+    from ._lib import c_int32, c_int64, ptr, stream
+    n_loc, n_ext = dop.n_loc, dop.n_ext
+    dt, dev = init_vec_loc.dtype, init_vec_loc.device
+    sfx = _lib.suffix(dt)
+    n_glob = dop.plan.part.n
+    num_iter = min(int(max_iter), n_glob)
+    q = torch.zeros((num_iter + 1, n_loc), dtype=dt, device=dev)
+    src = torch.zeros((n_ext, 1), dtype=dt, device=dev)              # [own rows | halo rows] of the current Lanczos vector
+    tmp = torch.zeros((n_ext, 1), dtype=dt, device=dev)
+    r = init_vec_loc.reshape(n_loc).to(dt).clone()
+    c = torch.zeros(num_iter + 1, dtype=dt, device=dev)
+    nrm2 = torch.zeros(1, dtype=dt, device=dev)
+    beta = torch.zeros(1, dtype=dt, device=dev)
+    ws = torch.zeros(_lib.query("mgp_lanczos_ws_bytes", c_int64(n_loc), c_int32(num_iter + 1)), dtype=torch.uint8, device=dev)
+    alphas = torch.zeros(num_iter, dtype=dt, device=dev)
+    betas = torch.zeros(num_iter, dtype=dt, device=dev)
+    world = dist.get_world_size(group)
+
+    def allreduce(t):
+        if world > 1:
+            dist.all_reduce(t, group=group)
+
+    def dots(j):
+        _lib.call("mgp_lanczos_dots_" + sfx, ptr(q), c_int64(n_loc), c_int32(j), ptr(r), c_int64(n_loc), ptr(c), ptr(ws), stream())
+        allreduce(c[:max(j, 1)])
+
+    def axpy(j):
+        _lib.call("mgp_lanczos_axpy_" + sfx, ptr(q), c_int64(n_loc), c_int32(j), ptr(r), c_int64(n_loc), ptr(c), ptr(nrm2), ptr(ws), stream())
+        allreduce(nrm2)
+
+    def normalize(dst, beta_out):
+        _lib.call("mgp_lanczos_normalize_" + sfx, ptr(r), c_int64(n_loc), ptr(nrm2), ptr(dst), ptr(beta_out), stream())
+
+    c.zero_()
+    axpy(0)                                                            # j = 0: norm only
+    normalize(q[0], None)
+    steps = 0
+    for k in range(num_iter):
+        src[:n_loc, 0].copy_(q[k])
+        dop.matvec(src, r.unsqueeze(-1), tmp, 1)                       # r <- A q_k on this rank's rows (halo exchange inside)
+        j = k + 1
+        dots(j)
+        axpy(j)                                                        # removes alpha_k q_k, beta_{k-1} q_{k-1} and every other component
+        alphas[k:k + 1].copy_(c[k:k + 1])
+        steps = k + 1
+        if k + 1 >= num_iter:
+            break
+        ok = False
+        nr2 = 0.0
+        for _ in range(10):
+            dots(j)
+            worst, nr2 = torch.stack((c[:j].abs().max(), nrm2[0])).tolist()
+            if nr2 <= 0.0 or worst / (nr2 ** 0.5) <= tol:
+                ok = True
+                break
+            axpy(j)
+        normalize(q[k + 1], beta)
+        betas[k:k + 1].copy_(beta)
+        if nr2 ** 0.5 <= 1e-6 or not ok:
+            break
+    t = torch.diag(alphas[:steps])
+    if steps > 1:
+        off = betas[:steps - 1]
+        t = t + torch.diag(off, 1) + torch.diag(off, -1)
+    return q[:steps], t
+
+
 class DistBackend:
     """Routes ``solvers.linear_cg`` of the package's native operators -- PrecisionMaternOperator, bare or inside the reference's
     Scale / Noise wrappers (riemann_gp.py:32-39) -- to the row-partitioned peer-memory CG of this process group, so that
@@ -645,6 +722,32 @@ class DistBackend:
         dist.all_gather(d_all, d_loc.contiguous(), group=self.group)
         dist.all_gather(i_all, i_loc.contiguous(), group=self.group)
         return torch.cat(d_all), torch.cat(i_all)
+
+    def lanczos_eigenpairs(self, lap, max_iter, init_vec=None, tol=1e-5):
+        """``solvers.diagonalization(method="lanczos")`` of a symmetric-normalised GraphLaplacianOperator over the process group:
+        (evals ascending [j], evecs [n, j] in the caller's row order, identical on every rank)."""
+        from . import solvers
+        gst = lap.structure
+        n = lap.shape[0]
+        with torch.no_grad():
+            _, _, diag, a = lap._values()
+            diag, a = diag.detach(), a.detach()
+        part = RowPartition(n, self.world, align=gst.TILE_ROWS)
+        dop = DistPrecision(gst, diag, a, torch.zeros(1, dtype=a.dtype, device=a.device), 1, part, self.rank, self.group)
+        lo, hi = part.range(self.rank)
+        if init_vec is None:
+            init_vec = torch.randn(n, dtype=a.dtype, device=a.device)
+            if self.world > 1:
+                dist.broadcast(init_vec, 0, group=self.group)
+        q_loc, t = dist_lanczos_tridiag(dop, max_iter, gst.to_internal(init_vec.reshape(n, 1))[lo:hi, 0], tol, self.group)
+        evals, v = solvers.lanczos_tridiag_to_diag(t)
+        ev_loc = q_loc.T @ v
+        if self.world > 1:
+            sizes = [part.range(r)[1] - part.range(r)[0] for r in range(self.world)]
+            parts = [torch.empty((sz, ev_loc.shape[1]), dtype=ev_loc.dtype, device=ev_loc.device) for sz in sizes]
+            dist.all_gather(parts, ev_loc.contiguous(), group=self.group)
+            ev_loc = torch.cat(parts)
+        return evals, gst.to_external(ev_loc), t
 
     def cg_chunk(self, op, rhs, n_tridiag, tolerance, eps, stop_updating_after, max_iter, n_tridiag_iter):
         """Same contract as ``solvers._cg_chunk``: (solution [n, C] in the caller's row order, hist (cpu) or None, info)."""

@@ -521,6 +521,12 @@ def diagonalization(op, method=None):
             evals, evecs = torch.linalg.eigh(op.to_dense())
         return evals, DenseEigenvectors(evecs)
     if method == "lanczos":
+        be = _DIST_BACKEND
+        if be is not None and getattr(be, "world", 1) > 1 and n >= be.min_rows and hasattr(op, "structure") and \
+                getattr(op, "normalization", None) == "symmetric" and not getattr(op, "transposed", False):
+            with torch.no_grad():          # row-partitioned Lanczos over the process group (distributed.dist_lanczos_tridiag)
+                evals, evecs, _ = be.lanczos_eigenpairs(op, settings.max_root_decomposition_size.value())
+            return evals, DenseEigenvectors(evecs)
         with torch.no_grad():
             q, t = lanczos_tridiag(op, settings.max_root_decomposition_size.value())
             evals, v = lanczos_tridiag_to_diag(t)

@@ -138,3 +138,27 @@ def test_dist_backend_routes_training_loss_through_the_peer_cg(pg1):
     assert abs(got[0] - want[0]) <= 1e-7 * abs(want[0]) and abs(got[1] - want[1]) <= 1e-7 * abs(want[1])
     for a, b in zip(got[3], want[3]):
         assert abs(a - b) <= 1e-5 * max(abs(b), 1e-12), (got, want)
+
+
+def test_distributed_lanczos_matches_the_single_gpu_driver(pg1):
+    """distributed.dist_lanczos_tridiag (row-partitioned vectors, all-reduced re-orthogonalisation dots) on a process group of size 1
+    against solvers.lanczos_tridiag with the same start vector: same tridiagonal, same Ritz values / vectors."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import distributed as D, solvers
+    dtype = torch.float64
+    n, k = 12000, 10
+    x = oracle.datasets.torus(n, seed=5)
+    idx, val = mgp.NearestNeighbors(x.to(DEV)).graph(k)
+    lap = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, torch.tensor([[0.2]], dtype=dtype, device=DEV), "symmetric", True)
+    v0 = torch.randn(n, dtype=dtype, device=DEV, generator=torch.Generator(device=DEV).manual_seed(11))
+    q_ref, t_ref = solvers.lanczos_tridiag(lap, 40, init_vec=v0)
+    be = D.DistBackend(min_rows=1000)
+    evals, evecs, t = be.lanczos_eigenpairs(lap, 40, init_vec=v0)
+    assert t.shape == t_ref.shape
+    assert rel_err(t, t_ref) < 1e-8
+    ev_ref, v_ref = solvers.lanczos_tridiag_to_diag(t_ref)
+    assert rel_err(evals, ev_ref) < 1e-8
+    # Ritz vectors: the same q^T V as the single-GPU driver's (eigenvector signs of eigh(T) may differ between the two T's)
+    ref_vecs = q_ref.T @ v_ref
+    assert evecs.shape == ref_vecs.shape
+    assert rel_err(evecs.abs(), ref_vecs.abs()) < 1e-6
