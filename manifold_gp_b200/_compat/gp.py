@@ -36,16 +36,18 @@ class Interval(nn.Module):
         super().__init__()
         self.register_buffer("lower_bound", torch.as_tensor(float(lower_bound)))
         self.register_buffer("upper_bound", torch.as_tensor(float(upper_bound)))
+        # decided once on the host: reading the (device) buffer on every parameter access would synchronise the training loop
+        self._unbounded_above = math.isinf(float(upper_bound))
 
     def transform(self, raw):
         lo, hi = self.lower_bound.to(raw), self.upper_bound.to(raw)
-        if math.isinf(float(hi)):
+        if self._unbounded_above:
             return torch.nn.functional.softplus(raw) + lo
         return lo + (hi - lo) * torch.sigmoid(raw)
 
     def inverse_transform(self, value):
         lo, hi = self.lower_bound.to(value), self.upper_bound.to(value)
-        if math.isinf(float(hi)):
+        if self._unbounded_above:
             return _inv_softplus(value - lo)
         t = (value - lo) / (hi - lo)
         return torch.log(t) - torch.log1p(-t)

@@ -30,7 +30,8 @@ n = int(args[0]) if len(args) > 0 else 10_000_000
 calls = int(args[1]) if len(args) > 1 else 3
 shape = args[2] if len(args) > 2 else "sphere"
 NU = int(os.environ.get("TRAIN_NU", "1"))
-NOISE = float(os.environ.get("TRAIN_NOISE", "1.2e-4")) * (1_000_000 / n)       # the Neumann-series noise wrapper needs noise * |Q| < 1
+NOISE = float(os.environ.get("TRAIN_NOISE", "2.5e-5")) * (1_000_000 / n)       # the Neumann-series noise wrapper needs noise * |Q| < 1
+                                                                                  # (|Q| ~ 2 / eps^2 ~ 1.5e4 * n / 1e6 on the unit sphere at k = 32)
 use_backend = os.environ.get("MGP_CFGD_BACKEND", "1") != "0"
 backend = None
 if use_backend:
