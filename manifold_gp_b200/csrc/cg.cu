@@ -617,6 +617,8 @@ cg_rupdate_vec_kernel(T* __restrict__ r, const T* __restrict__ v, int ld, int64_
                       T* __restrict__ hist, int max_hist, void* ws, T* __restrict__ rbuf) {
   using V = typename V16<T>::type;
   constexpr int N = V16<T>::N;
+  pdl_wait();
+  pdl_launch_dependents();
   T* k = state + S_NARR * ncols;
   if (k[K_DONE] != T(0)) {
     if (blockIdx.x == 0 && threadIdx.x == 0) k[K_XPEND] = T(0);
@@ -668,6 +670,8 @@ cg_pxupdate_vec_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict
                        const T* __restrict__ state) {
   using V = typename V16<T>::type;
   constexpr int N = V16<T>::N;
+  pdl_wait();
+  pdl_launch_dependents();
   if (state[S_NARR * ncols + K_XPEND] == T(0)) return;
   const int c0 = (threadIdx.x * N) % ld;
   T a[N], b[N];
@@ -765,7 +769,7 @@ static int cg_rupdate(T* r, const T* v, int64_t ld, int64_t n, int ncols, T* sta
     const int64_t cap = (int64_t)kNumSMs * 8;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    cg_rupdate_vec_kernel<T><<<(unsigned)g, kCgBlock, 0, st>>>(r, v, (int)ld, n, ncols, state, hist, max_hist, ws, rbuf);
+    MGP_CUDA(launch_pdl(cg_rupdate_vec_kernel<T>, dim3((unsigned)g), dim3(kCgBlock), 0, st, r, v, (int)ld, n, ncols, state, hist, max_hist, ws, rbuf));
     MGP_LAUNCH_CHECK();
     return MGP_OK;
   }
@@ -783,7 +787,7 @@ static int cg_pxupdate(T* x, T* p, const T* r, int64_t ld, int64_t n, int ncols,
     int64_t gv = ceil_div(total / V16<T>::N, (int64_t)kCgBlock * 4);
     if (gv > kNumSMs * 8) gv = kNumSMs * 8;
     if (gv < 1) gv = 1;
-    cg_pxupdate_vec_kernel<T><<<(unsigned)gv, kCgBlock, 0, st>>>(x, p, r, (int)ld, n, ncols, state);
+    MGP_CUDA(launch_pdl(cg_pxupdate_vec_kernel<T>, dim3((unsigned)gv), dim3(kCgBlock), 0, st, x, p, r, (int)ld, n, ncols, state));
     MGP_LAUNCH_CHECK();
     return MGP_OK;
   }
@@ -1038,6 +1042,8 @@ cg_peer_cgstep_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T
                       unsigned int* const* __restrict__ dflag_ptrs, unsigned int* const* __restrict__ rflag_ptrs, int rank, int world) {
   using V = typename V16<T>::type;
   constexpr int N = V16<T>::N;
+  pdl_wait();
+  pdl_launch_dependents();
   T* k = state + S_NARR * ncols;
   if (k[K_DONE] != T(0)) return;
   CgWs<T> w = cg_ws<T>(ws);
@@ -1340,8 +1346,9 @@ int mgp_cg_peer_cgstep_f32(float* x, float* r, float* p, float* s, const float* 
                     world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_cgstep: bad arguments");
   if (!cg_vec_ok<float>(ld, x, r, p, s) || (((uintptr_t)w) % 16) != 0) return MGP_EUNSUPPORTED;
   int64_t g = ceil_div(n * ld / V16<float>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
-  cg_peer_cgstep_kernel<float><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, r, p, s, w, (int)ld, n, ncols, state, hist, max_hist, ws,
-      gamma_loc, delta_loc, (float* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
+  MGP_CUDA(launch_pdl(cg_peer_cgstep_kernel<float>, dim3((unsigned)g), dim3(kCgBlock), 0, (cudaStream_t)stream, x, r, p, s, w, (int)ld, n, ncols,
+                      state, hist, max_hist, ws, gamma_loc, delta_loc, (float* const*)red_ptrs, (unsigned int* const*)dflag_ptrs,
+                      (unsigned int* const*)rflag_ptrs, rank, world));
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }
@@ -1352,8 +1359,9 @@ int mgp_cg_peer_cgstep_f64(double* x, double* r, double* p, double* s, const dou
                     world >= 1 && world <= 32 && rank >= 0 && rank < world, "cg_peer_cgstep: bad arguments");
   if (!cg_vec_ok<double>(ld, x, r, p, s) || (((uintptr_t)w) % 16) != 0) return MGP_EUNSUPPORTED;
   int64_t g = ceil_div(n * ld / V16<double>::N, (int64_t)kCgBlock * 4); if (g > kNumSMs * 8) g = kNumSMs * 8; if (g < 1) g = 1;
-  cg_peer_cgstep_kernel<double><<<(unsigned)g, kCgBlock, 0, (cudaStream_t)stream>>>(x, r, p, s, w, (int)ld, n, ncols, state, hist, max_hist, ws,
-      gamma_loc, delta_loc, (double* const*)red_ptrs, (unsigned int* const*)dflag_ptrs, (unsigned int* const*)rflag_ptrs, rank, world);
+  MGP_CUDA(launch_pdl(cg_peer_cgstep_kernel<double>, dim3((unsigned)g), dim3(kCgBlock), 0, (cudaStream_t)stream, x, r, p, s, w, (int)ld, n, ncols,
+                      state, hist, max_hist, ws, gamma_loc, delta_loc, (double* const*)red_ptrs, (unsigned int* const*)dflag_ptrs,
+                      (unsigned int* const*)rflag_ptrs, rank, world));
   MGP_LAUNCH_CHECK();
   return MGP_OK;
 }

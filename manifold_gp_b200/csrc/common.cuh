@@ -43,6 +43,31 @@ void count_launch(int n = 1);
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The solver loops are chains of 3-4 dependent launches of 20-130 us each; launched with the programmatic-stream-serialization
+// attribute a kernel's CTAs are scheduled while its predecessor drains, and block in `griddepcontrol.wait` (first statement of the
+// kernel) until the predecessor has completed and flushed -- the launch latency between dependent kernels disappears from the
+// critical path.  MGP_PDL=0 restores plain launches.  A kernel launched this way MUST call pdl_wait() before touching anything
+// a predecessor wrote; pdl_launch_dependents() lets ITS successor's CTAs become resident early (they block in their own wait).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers ------------------------------------------------------------------------------------------

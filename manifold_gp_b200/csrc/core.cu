@@ -1,6 +1,7 @@
 // Error reporting, version string, launch accounting.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -18,6 +19,14 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MGP_PDL");
+    return e != nullptr && e[0] == '1';       // opt-in until measured (MGP_PDL=1)
+  }();
+  return on;
+}
 
 }  // namespace mgp
 

@@ -159,6 +159,8 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
   unsigned char* const ring = smem_raw + (size_t)nstages * stage_bytes;
   int* const ids_ring = reinterpret_cast<int*>(ring + 2 * kWiMetaBytes);
 
+  pdl_wait();                                      // PDL: everything below may read what the predecessor launch wrote
+  pdl_launch_dependents();                         // the successor's CTAs may become resident (they block in their own wait)
   if (g.done && *g.done != T(0)) return;          // uniform: CG converged, nothing to compute, publish or wait for
   if (g.peer_x && tid < g.npeers) peer_tab[tid] = g.peer_x[tid];
   if (tid == 0) {
@@ -628,7 +630,7 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   for (int c0 = 0; c0 < ncols; c0 += CW) {
     g.c0 = c0;
     g.last_pass = (c0 + CW >= ncols) ? 1 : 0;
-    kern<<<(unsigned)blocks, kWiThreads, smem, st>>>(g);
+    MGP_CUDA(launch_pdl(kern, dim3((unsigned)blocks), dim3(kWiThreads), smem, st, g));
     MGP_LAUNCH_CHECK();
   }
   return MGP_OK;
