@@ -63,6 +63,10 @@ int mgp_knn_search_f32(const float* db, int64_t n, const float* q, int64_t nq, i
  * stats (device uint32[4]): [0] queries that needed the exhaustive re-search, [1] float bits of the largest
  * |approximate - exact| candidate distance seen, [2] queries processed.  `same` is a sizing hint only (the query-role copy
  * of the points differs from the database-role copy in the norm column and is always prepared).  Returns MGP_EUNSUPPORTED (nothing launched; ws_bytes query returns 0) outside that range. */
+/* Minimum size K' of the exact re-rank window of the tensor-core search (0 = default k + 16 rounded to 32; 32; 64).  Process-wide;
+ * affects mgp_knn_search_tc_ws_bytes and mgp_knn_search_tc_f32 alike.  NearestNeighbors.search raises it to 64 when a pilot of
+ * 1024 queries shows the certificate failing (clouds whose neighbour distances sit below the 3xTF32 error band). */
+int mgp_knn_tc_config(int32_t min_kp);
 size_t mgp_knn_search_tc_ws_bytes(int64_t n, int64_t nq, int32_t d, int32_t k, int32_t same);
 int mgp_knn_search_tc_f32(const float* db, int64_t n, const float* q, int64_t nq, int32_t d, int32_t k,
                           float* dist2, int64_t* idx, void* ws, size_t ws_bytes, uint32_t* stats, void* stream);

@@ -32,6 +32,7 @@ _SIG = {
     "mgp_add_launch_count": (None, [c_int64]),
     "mgp_knn_search_ws_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
     "mgp_knn_search_f32": (c_int32, [P, c_int64, P, c_int64, c_int32, c_int32, P, P, P, c_size_t, P]),
+    "mgp_knn_tc_config": (c_int32, [c_int32]),
     "mgp_knn_search_tc_ws_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "mgp_knn_search_tc_f32": (c_int32, [P, c_int64, P, c_int64, c_int32, c_int32, P, P, P, c_size_t, P, P]),
     "mgp_graph_symmetrize_ws_bytes": (c_size_t, [c_int64, c_int32]),

@@ -701,6 +701,13 @@ static int tc_variant() {
   return (v >= 0 && v <= 3) ? v : kTcDefaultVariant;
 }
 
+// Minimum K' (candidates kept per query for the exact re-rank), set by mgp_knn_tc_config.  The certificate needs the K'-th
+// approximate distance to clear the k-th exact one by the 3xTF32 error band E ~ 2^-20 (4 |q|^2 + 2 tau); on clouds whose
+// neighbour distances are far below that band (RMNIST-shape generator at N = 1M: d_k^2 ~ 2e-5 against E ~ 2.5e-4) K' = 32 fails
+// for every query and the search degenerates to the exhaustive CUDA-core re-search (163 s at 1M x 784, cfg-E sweep); K' = 64
+// keeps enough of the band for the certificate to pass.
+static int g_tc_min_kp = 0;
+
 static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->variant = tc_variant();
   if (!getenv("MGP_KNN_TC_VARIANT") && d + 1 <= 16) p->variant = 2;      // small d: 16-wide k-blocks (64-byte rows)
@@ -714,6 +721,7 @@ static bool tc_plan(int64_t n, int64_t nq, int d, int k, bool same, TcPlan* p) {
   p->ntiles = (int)ceil_div(n, kTcBN);
   p->nqtiles = (int)ceil_div(nq, kTcBM);
   p->kp = ((k + 16 + 31) / 32) * 32;            // 32 or 64
+  if (g_tc_min_kp > p->kp) p->kp = g_tc_min_kp;  // mgp_knn_tc_config: wider exact re-rank window for very dense clouds
   p->cap = p->kp + 64;
   // Database splits: enough (query tile, split) work items for >= 6 waves over the SMs, no more.  Measured on B200
   // (70k x 784, k = 10): 2 splits 52.6 ms, 4 splits 58.5, 8 splits 66.2 -- every item restarts the selection warm-up, and
@@ -776,6 +784,12 @@ static void launch_rerank(const TcPlan& p, const float* db, const float* q, int6
 using namespace mgp;
 
 extern "C" {
+
+int mgp_knn_tc_config(int32_t min_kp) {
+  MGP_CHECK_ARG(min_kp == 0 || min_kp == 32 || min_kp == 64, "knn_tc_config: min_kp must be 0, 32 or 64");
+  g_tc_min_kp = min_kp;
+  return MGP_OK;
+}
 
 size_t mgp_knn_search_tc_ws_bytes(int64_t n, int64_t nq, int32_t d, int32_t k, int32_t same) {
   TcPlan p;

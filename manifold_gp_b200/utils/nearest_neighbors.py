@@ -58,14 +58,19 @@ class NearestNeighbors():
         if self.tensor_core:
             # k <= 48, n >= 256: TF32 tcgen05 distance tiles + fused top-(k+margin) + exact certified re-rank (knn_tc.cu);
             # bit-identical results to the CUDA-core kernel below.
+            wide = self._wide_window(q, k) if (nq >= 65536 and not getattr(self, "_in_pilot", False)) else False
+            _lib.call("mgp_knn_tc_config", c_int32(64 if wide else 0))
             nb = _lib.query("mgp_knn_search_tc_ws_bytes", c_int64(n), c_int64(nq), c_int32(d), c_int32(k), c_int32(int(same)))
+            if nb <= 0:
+                _lib.call("mgp_knn_tc_config", c_int32(0))
             if nb > 0:
                 ws = _lib.workspace(nb, q.device)
                 stats = torch.zeros(4, dtype=torch.int32, device=q.device)
                 rc = _lib.call_rc("mgp_knn_search_tc_f32", ptr(self._db), c_int64(n), ptr(self._db if same else q), c_int64(nq),
                                   c_int32(d), c_int32(k), ptr(dist), ptr(idx), ptr(ws), c_size_t(ws.numel()), ptr(stats), stream())
+                _lib.call("mgp_knn_tc_config", c_int32(0))
                 if rc == 0:
-                    self.last_search = {"kernel": "tcgen05", "stats": stats}   # device tensor: reading it synchronises
+                    self.last_search = {"kernel": "tcgen05", "stats": stats, "wide_window": bool(wide)}   # stats: device tensor
                     return dist.to(self.x.dtype), idx
                 if rc != _lib.MGP_EUNSUPPORTED:
                     raise RuntimeError(f"mgp_knn_search_tc_f32 failed ({rc}): {_lib.last_error()}")
@@ -74,6 +79,26 @@ class NearestNeighbors():
         _lib.call("mgp_knn_search_f32", ptr(self._db), c_int64(n), ptr(q), c_int64(nq), c_int32(d), c_int32(k),
                   ptr(dist), ptr(idx), ptr(ws), c_size_t(ws.numel()), stream())
         return dist.to(self.x.dtype), idx
+
+    def _wide_window(self, q, k) -> bool:
+        """Pilot for large searches: 1024 evenly spaced queries through the tensor-core search with the default re-rank window.
+        If more than 2 % of them fail the exactness certificate (and would be re-searched exhaustively on the CUDA cores), the
+        full search keeps a 64-candidate window instead.  Results are exact either way; this only chooses the faster route.
+        Costs one small search (~10 ms at N = 1M, d = 3) and one 16-byte device read."""
+        nq = q.shape[0]
+        if k > 16:                   # k + 16 already rounds to a 64-candidate window
+            return False
+        sel = q[:: max(1, nq // 1024)][:1024].contiguous()
+        self._in_pilot = True
+        try:
+            self.search(sel, k)
+            info = self.last_search
+        finally:
+            self._in_pilot = False
+        if info.get("kernel") != "tcgen05":
+            return False
+        failed = int(info["stats"][0])
+        return failed > 0.02 * sel.shape[0]
 
     def graph(self, k, symmetric=True, self_loop=False, nprobe=1):
         """(idx[2,M] int64 upper-triangular sorted, val[M] mean squared distance) -- :39-55."""

@@ -73,3 +73,32 @@ def test_tc_iid_gaussian_falls_back_but_stays_exact():
     g = torch.Generator().manual_seed(11)
     x = torch.randn(4000, 128, generator=g)
     _check(x, x, 8, max_research=1.0)
+
+
+def test_dense_cloud_takes_the_wide_rerank_window_and_stays_exact():
+    """A cloud whose neighbour distances sit below the 3xTF32 error band (70k points on 2 one-parameter curves in R^64): with the
+    default 32-candidate re-rank window most queries fail the exactness certificate and fall to the exhaustive CUDA-core
+    re-search (cfg-E sweep, round 2: 163 s at 1M x 784).  NearestNeighbors.search pilots 1024 queries and switches to the
+    64-candidate window -- which only helps when the band is a few dozen candidates wide (1M x 64, k = 8: 14.8 -> 4.5 s; not
+    at d = 784) -- and in every case the results stay bit-identical to the CUDA-core search, which is what this test pins."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200.utils import synthetic
+    x = synthetic.rmnist_shape(70000, 64, prototypes=2, device="cuda")
+    k = 10
+    knn = mgp.NearestNeighbors(x)
+    d_tc, i_tc = knn.search(x, k)
+    info = knn.last_search
+    assert info["kernel"] == "tcgen05"
+    assert info["wide_window"] is True
+    research_wide = int(info["stats"][0])
+    # the default window on the same cloud, for the record: many more uncertified queries
+    knn._in_pilot = True                       # suppress the pilot: default window
+    try:
+        knn.search(x, k)
+        research_default = int(knn.last_search["stats"][0])
+    finally:
+        knn._in_pilot = False
+    assert research_wide <= research_default      # (on THIS cloud both are ~all queries: the window cannot cover the error band)
+    knn.tensor_core = False
+    d_cc, i_cc = knn.search(x, k)
+    assert torch.equal(i_tc, i_cc) and torch.equal(d_tc, d_cc)
