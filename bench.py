@@ -46,6 +46,9 @@ def ncu_traffic(kernel_substr):
     no entry for the kernel that actually ran -- never a stale constant."""
     try:
         tab = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        # graph.LAST_SPMM_KERNEL -> the instantiation ncu lists (template arguments: value type, producer warps, paired walk)
+        kernel_substr = {"lap_spmm_wi_kernel<pair>": "lap_spmm_wi_kernel<float, 16, 1>",
+                         "lap_spmm_wi_kernel": "lap_spmm_wi_kernel<float, 16, 0>"}.get(kernel_substr, kernel_substr)
         for name, row in tab.items():
             if kernel_substr in name:
                 return int(row["dram_bytes"]), row.get("source")
@@ -333,7 +336,7 @@ def run_ours(args):
         "e2e": {"value": round(total_iters / (e2e_ms * 1e-3), 1), "unit": UNIT, "solve_ms": round(e2e_ms, 3),
                 "h2d_bytes_per_step": Bh.numel() * 4, "d2h_bytes_per_step": Xh.numel() * 4},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"{spmm16_kernel}<float> (C=16 SpMM step of the Matern precision operator)",
+        "roofline": {"bound": "hbm", "kernel": f"{spmm16_kernel} fp32 (C=16 SpMM step of the Matern precision operator)",
                      "achieved": round(ach16, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach16 / hbm_peak, 4),
                      "frac_of_nominal_8000": round(ach16 / 8000.0, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": b16, "us_per_launch": round(spmm16_us, 2),

@@ -269,7 +269,13 @@ typedef struct mgp_wi_ext {
   const void* ep_coef;
   int32_t publish_at_start;
   int32_t reserved;
+  const uint8_t* pair_rows;   /* non-NULL (fp32 only): wptr / wcol / aw are the PAIRED-ROW streams of graph.pair_streams -- a slot of 8 lanes
+                                 walks the union list of two spatially adjacent rows, aw holds two values per entry (mgp_lap_pair_values),
+                                 pair_rows[128 tile + 2 pair + half] is the tile-local row that position outputs */
 } mgp_wi_ext;
+/* out[i] = src[i] >= 0 ? a[src[i]] : 0 -- the value stream of the paired layout (two sources per stream entry), once per bandwidth. */
+int mgp_lap_pair_values_f32(const int32_t* src, const float* a, int64_t count, float* out, void* stream);
+int mgp_lap_pair_values_f64(const int32_t* src, const double* a, int64_t count, double* out, void* stream);
 int mgp_lap_spmm_wi_ex_f32(const int32_t* wptr, const uint16_t* wcol, const float* aw, const float* diag, const int32_t* hptr,
                            const int32_t* hcol, int32_t tile_rows, int32_t lmax, int32_t wnzmax, int32_t hmax, const float* shift,
                            const float* post, const int32_t* xmap, const int32_t* ymap, const float* x, int64_t ldx, float* y,

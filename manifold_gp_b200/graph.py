@@ -192,6 +192,133 @@ def wi_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 128)
     return dict(wptr=wpad, wcol=wcol, nnzw=nnzw, wnzmax=int(tile_tot.max()))
 
 
+def pair_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, spatial_pos: torch.Tensor = None, R: int = 128):
+    """Paired-row entry streams of the v6 SpMM walk (csrc/lap_spmm_wi.cu, PAIR = true).  Two spatially adjacent rows of a tile
+    share most of their columns (kNN graph in Morton order: the union of a pair's lists is ~0.66 of their sum), so a slot of
+    8 lanes walks the UNION list of a row pair: one 64-byte X-row load from shared memory feeds both rows (32 FMAs instead
+    of 16 per load -- the walk is bound by shared-memory wavefronts).  Layout, per tile of R = 128 rows:
+
+    * the 64 pairs are Morton-adjacent rows (``spatial_pos``: position of every row in the spatial order; None = rows 2p, 2p+1),
+      ordered by union length (descending) so the 4 pairs of a warp block run in lock-step; ``qrow[128 tile + 2 pi + h]`` is the
+      tile-local row that half h of pair pi outputs (uint8);
+    * warp block b = 16 tile + (pi >> 2), slot = pi & 3; stream position qptr[b] + 32 t + 8 slot + l holds the union entry that
+      lane l of the slot consumes in step t: its tile-local column in ``qcol`` and TWO source positions into the CSR value
+      array in ``qsrc[2 pos], qsrc[2 pos + 1]`` = (value of the lane's OWN output row, value of the other row), -1 = zero.
+      Lanes 0-3 of a slot output row A (h = 0), lanes 4-7 row B, so the first exchange of the final reduction needs no select;
+    * bank conflicts: lane l reads 16-byte chunk (c + l) & 3 in load c, lanes l and l + 4 of a slot read the same chunk of
+      different X rows -- conflict-free when the two columns have opposite parity, so lanes 0-3 are filled with even
+      columns and lanes 4-7 with odd ones (the surplus of one parity spills into the other side's free positions);
+    * padding entries (value sources -1) carry a valid own-row index of the parity their lane expects.
+
+    Pure index plumbing (any device); duplicates of a column inside one row (a diagonal COO entry is listed twice) are kept
+    as separate union entries."""
+    assert R == 128
+    dev = rowptr.device
+    ntiles = (n + R - 1) // R
+    nblk = ntiles * 16
+    NT = ntiles * R
+    rp = rowptr.to(torch.int64)
+    nnz = int(rp[-1])
+    rowlen = rp[1:] - rp[:-1]
+    ar = lambda m: torch.arange(m, device=dev, dtype=torch.int64)
+    # spatial position of every (real or virtual) row inside its tile -> first-cut pair id and half
+    q0 = ar(NT) % R
+    if spatial_pos is not None:
+        q0[:n] = spatial_pos.to(torch.int64) % R
+        if NT > n:                                                   # virtual rows take the positions the real rows left free
+            used = torch.zeros(R, dtype=torch.bool, device=dev)
+            used[q0[(ntiles - 1) * R:n]] = True
+            q0[n:] = (~used).nonzero().reshape(-1)
+    gp_row = (ar(NT) // R) * (R // 2) + (q0 >> 1)                    # global pair id of every row (before the length sort)
+    half_row = q0 & 1
+    rows = torch.repeat_interleave(ar(n), rowlen)
+    lc = lcol16.to(torch.int64) & 0xFFFF
+    # occurrence rank of a column inside its row (0 except for repeated entries)
+    k1 = rows * 65536 + lc
+    o1 = torch.argsort(k1, stable=True)
+    k1s = k1[o1]
+    first = torch.ones(nnz, dtype=torch.bool, device=dev)
+    first[1:] = k1s[1:] != k1s[:-1]
+    start = torch.cummax(torch.where(first, ar(nnz), torch.zeros((), dtype=torch.int64, device=dev)), 0).values
+    occ = torch.empty(nnz, dtype=torch.int64, device=dev)
+    occ[o1] = ar(nnz) - start
+    assert nnz == 0 or int(occ.max()) < 8
+    del k1, k1s, first, start
+    # union entries: group by (pair, column, occurrence); at most one entry of each half per group
+    k2 = ((gp_row[rows] * 65536 + lc) * 8 + occ) * 2 + half_row[rows]
+    o2 = torch.argsort(k2)
+    k2s = k2[o2]
+    newg = torch.ones(nnz, dtype=torch.bool, device=dev)
+    newg[1:] = (k2s[1:] >> 1) != (k2s[:-1] >> 1)
+    uid = torch.cumsum(newg.to(torch.int64), 0) - 1                  # union id of every sorted entry
+    nu = int(uid[-1]) + 1 if nnz else 0
+    h_s = k2s & 1
+    src = torch.full((nu, 2), -1, dtype=torch.int64, device=dev)      # CSR positions of the (A, B) values
+    src[uid, h_s] = o2
+    u_gp = torch.empty(nu, dtype=torch.int64, device=dev)
+    u_lc = torch.empty(nu, dtype=torch.int64, device=dev)
+    u_gp[uid] = k2s >> 20
+    u_lc[uid] = (k2s >> 4) & 0xFFFF
+    del k2, k2s, newg, uid, h_s, o1, o2, occ
+    npairs = ntiles * (R // 2)
+    ucount = torch.bincount(u_gp, minlength=npairs)
+    # pairs of a tile by union length, descending -> pair index pi inside the tile
+    pk = (ar(npairs) // (R // 2)) * (1 << 20) + ((1 << 20) - 1 - ucount)
+    porder = torch.argsort(pk, stable=True)
+    pi_of = torch.empty(npairs, dtype=torch.int64, device=dev)
+    pi_of[porder] = ar(npairs) % (R // 2)
+    tile_of_pair = ar(npairs) // (R // 2)
+    blk_of_pair = tile_of_pair * 16 + (pi_of >> 2)
+    steps = torch.zeros(nblk, dtype=torch.int64, device=dev)
+    steps.scatter_reduce_(0, blk_of_pair, (ucount + 7) >> 3, reduce="amax")
+    qptr = torch.zeros(nblk + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(steps * 32, 0, out=qptr[1:])
+    nnzq = int(qptr[-1])
+    if nnzq >= 2 ** 30 - 64:
+        return None
+    # row table
+    qrow = torch.zeros(NT, dtype=torch.uint8, device=dev)
+    qrow[(ar(NT) // R) * R + 2 * pi_of[gp_row] + half_row] = (ar(NT) % R).to(torch.uint8)
+    # lane assignment: rank of every union entry inside its (pair, parity) class
+    par = u_lc & 1
+    k3 = u_gp * 2 + par
+    o3 = torch.argsort(k3, stable=True)
+    cnt3 = torch.bincount(k3, minlength=2 * npairs)
+    st3 = torch.cumsum(cnt3, 0) - cnt3
+    rk = torch.empty(nu, dtype=torch.int64, device=dev)
+    rk[o3] = ar(nu) - st3[k3[o3]]
+    cap = 4 * steps[blk_of_pair[u_gp]]                               # positions per lane class of the slot
+    spill = rk >= cap
+    cls = torch.where(spill, 1 - par, par)
+    r = torch.where(spill, cnt3[u_gp * 2 + (1 - par)] + (rk - cap), rk)
+    pos = qptr[blk_of_pair[u_gp]] + (r >> 2) * 32 + (pi_of[u_gp] & 3) * 8 + cls * 4 + (r & 3)
+    # padding index per position: an own row of the slot's pair with the parity of the lane class
+    p = ar(nnzq)
+    blk = torch.repeat_interleave(ar(nblk), steps * 32)
+    lane = (p - qptr[blk]) & 31
+    tile_p = blk >> 4
+    qa = tile_p * R + ((blk & 15) * 4 + (lane >> 3)) * 2              # table index of the slot's row A
+    ra = qrow[qa].to(torch.int64)
+    want = (lane >> 2) & 1
+    cand = (ra & ~1) | want
+    nrows_t = torch.clamp(n - tile_p * R, max=R)
+    cand = torch.where(cand < nrows_t, cand, torch.where(ra < nrows_t, ra, torch.zeros_like(ra)))
+    qcol = torch.zeros(nnzq + 64, dtype=torch.int16, device=dev)
+    qcol[:nnzq] = cand.to(torch.int32).to(torch.int16)
+    del p, blk, lane, tile_p, qa, ra, want, cand
+    qcol[pos] = u_lc.to(torch.int32).to(torch.int16)
+    qsrc = torch.full((nnzq + 64, 2), -1, dtype=torch.int32, device=dev)
+    mine = torch.where(cls == 0, src[:, 0], src[:, 1])
+    other = torch.where(cls == 0, src[:, 1], src[:, 0])
+    qsrc[pos, 0] = mine.to(torch.int32)
+    qsrc[pos, 1] = other.to(torch.int32)
+    tile_tot = qptr[16::16] - qptr[:-1:16]
+    qpad = torch.full((512 * ((ntiles + 31) // 32) + 4,), nnzq, dtype=torch.int32, device=dev)
+    qpad[:nblk + 1] = qptr.to(torch.int32)
+    return dict(qptr=qpad, qcol=qcol, qsrc=qsrc.reshape(-1).contiguous(), qrow=qrow, nnzq=nnzq, qnzmax=int(tile_tot.max()),
+                q_unions=nu)
+
+
 def wi_halo_lists(halo_ptr: torch.Tensor, halo_col: torch.Tensor, ntiles: int):
     """Halo id lists for the v5 kernel: every tile's list padded to a multiple of 4 ids (16-byte bulk copies) by repeating
     its last id (a valid row; 0 for empty lists is never read), offsets array padded to whole 32-tile chunks + 4."""
@@ -338,6 +465,9 @@ class GraphStructure:
             out = torch.empty(t["nnzp"] + 8, dtype=a.dtype, device=a.device)
             out[t["nnzp"]:].zero_()
             _lib.call("mgp_lap_pad_values_" + sfx, ptr(self.rowptr), ptr(t["prowptr"]), ptr(a), c_int64(self.n), ptr(out), stream())
+        elif kind == "pair":
+            out = torch.empty(t["qsrc"].numel(), dtype=a.dtype, device=a.device)
+            _lib.call("mgp_lap_pair_values_" + sfx, ptr(t["qsrc"]), ptr(a), c_int64(out.numel()), ptr(out), stream())
         else:
             out = torch.empty(t["nnzw"] + 64, dtype=a.dtype, device=a.device)
             out[t["nnzw"]:].zero_()
@@ -354,6 +484,22 @@ class GraphStructure:
 
     def wi_values(self, a: torch.Tensor) -> torch.Tensor:
         return self._value_layout(a, "wi")
+
+    def pair_tiles(self):
+        """The paired-row streams (``pair_streams``) of this structure, built on first use (fp32 SpMM with whole 64-byte
+        rows of right-hand sides); None when the tile structure does not exist."""
+        t = self.build_tiles()
+        if t is None or "wptr" not in t:
+            return None
+        if "qptr" not in t and not self.__dict__.get("_pair_tried"):
+            self._pair_tried = True
+            q = pair_streams(self.rowptr, t["lcol"][:self.nnz], self.n, self.morton_pos, self.TILE_ROWS)
+            if q is not None:
+                t.update(q)
+        return t if "qptr" in t else None
+
+    def pair_values(self, a: torch.Tensor) -> torch.Tensor:
+        return self._value_layout(a, "pair")
 
     def tiled_ok(self, dtype, cw: int) -> bool:
         """Does the widest pass for ``cw`` columns of ``dtype`` fit the shared-memory budget of the tiled kernel?"""
@@ -442,7 +588,13 @@ def lap_values(st: GraphStructure, d2csr: torch.Tensor, eps, self_loops: bool):
 
 # ---- SpMM ---------------------------------------------------------------------------------------------------------
 LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call launched (bench.py reports it)
-SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "spmv"  (tests force each; "auto": wi, else pipe, else tiled, else csr; one column: spmv)
+SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "wp" | "spmv"  (tests force each; "auto": wp (fp32, whole 64-byte rows), else wi, else pipe, else tiled, else csr; one column: spmv)
+
+
+PAIR_WALK = True       # "auto" may take the paired-row walk of the warp-interleaved kernel (MGP_PAIR_WALK=0 turns it off)
+import os as _os
+if _os.environ.get("MGP_PAIR_WALK", "1") == "0":
+    PAIR_WALK = False
 
 
 def _note_kernel(name):
@@ -501,8 +653,8 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
     # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
     # kernel (X served from L1/L2) is faster
-    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi"))
-    if SPMM_KERNEL in ("tiled", "pipe", "wi") and not use_tiled:
+    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "wp"))
+    if SPMM_KERNEL in ("tiled", "pipe", "wi", "wp") and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
         t = st.tiles
@@ -510,25 +662,32 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
         if peer_x is not None and not (pre is None and "wptr" in t):
             raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
-        if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi") or peer_x is not None):
-            aw = st.wi_values(a)
+        if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi", "wp") or peer_x is not None):
+            # paired-row walk (v6): fp32, whole 64-byte rows of right-hand sides, single GPU
+            pair = (SPMM_KERNEL in ("auto", "wp") and PAIR_WALK and dt == torch.float32 and c % 16 == 0 and peer_x is None
+                    and peer_ext is None and hasattr(st, "pair_tiles") and st.pair_tiles() is not None)
+            if SPMM_KERNEL == "wp" and not pair:
+                raise RuntimeError("lap_spmm: paired-row kernel requested but this call does not qualify (fp32, multiples of 16 "
+                                   "columns, no peer memory)")
+            aw = st.pair_values(a) if pair else st.wi_values(a)
+            sptr, scol, snzmax = (t["qptr"], t["qcol"], t["qnzmax"]) if pair else (t["wptr"], t["wcol"], t["wnzmax"])
             hcol = t["hcol_peer"] if peer_x is not None else t["hcol"]
             ep_here = _ep is not None and peer_ext is None and not (x_external or y_external)
-            if peer_ext is not None or done_flag is not None or ep_here:
+            if peer_ext is not None or done_flag is not None or ep_here or pair:
                 import ctypes
                 if peer_ext is not None:
                     ext = peer_ext[2]
                 elif ep_here:
                     cf = _ep[0] if _ep[0].dtype == dt else _ep[0].to(dt)
-                    ext = _lib.wi_ext(done_flag=done_flag, ep_coef=cf, ep_add=_ep[1] is not None)
+                    ext = _lib.wi_ext(done_flag=done_flag, ep_coef=cf, ep_add=_ep[1] is not None, pair_rows=t["qrow"] if pair else None)
                     if _ep[1] is not None:
                         dot_with = _ep[1]
                     _ep[2].append(True)
                 else:
-                    ext = _lib.wi_ext(done_flag=done_flag)
-                rc = _lib.call_rc("mgp_lap_spmm_wi_ex_" + sfx, ptr(t["wptr"]), ptr(t["wcol"]), ptr(aw), ptr(diag),
+                    ext = _lib.wi_ext(done_flag=done_flag, pair_rows=t["qrow"] if pair else None)
+                rc = _lib.call_rc("mgp_lap_spmm_wi_ex_" + sfx, ptr(sptr), ptr(scol), ptr(aw), ptr(diag),
                                   ptr(t["hptr"]), ptr(hcol), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
-                                  c_int32(t["wnzmax"]), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
+                                  c_int32(snzmax), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
                                   ptr(st.perm32 if x_external else None),
                                   ptr(st.perm32 if y_external else None), ptr(x), c_int64(x.stride(0)), ptr(out),
                                   c_int64(out.stride(0)), c_int64(st.n), c_int32(c), ptr(dot_with), ptr(dot_out), ptr(ws),
@@ -546,7 +705,7 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
                                   c_int32(0 if peer_sync is None else int(peer_sync[0])), ptr(None if peer_sync is None else peer_sync[1]),
                                   ptr(None if peer_sync is None else peer_sync[2]), stream())
             if rc == 0:
-                _note_kernel("lap_spmm_wi_kernel")
+                _note_kernel("lap_spmm_wi_kernel<pair>" if pair else "lap_spmm_wi_kernel")
                 return out
             if _ep is not None and _ep[2]:          # not launched: the epilogue algebra falls to the caller's elementwise passes
                 _ep[2].clear()
@@ -554,7 +713,7 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
                     dot_with = None
             if rc != _lib.MGP_EUNSUPPORTED or peer_x is not None:
                 raise RuntimeError(f"mgp_lap_spmm_wi_{sfx} failed ({rc}): {_lib.last_error()}")
-        if SPMM_KERNEL == "wi":
+        if SPMM_KERNEL in ("wi", "wp"):
             raise RuntimeError("lap_spmm: warp-interleaved kernel requested but this call does not qualify (pre scaling, "
                                "column count not a multiple of one 64-byte row, alignment or shared memory)")
         if pre is None and "prowptr" in t and SPMM_KERNEL in ("auto", "pipe"):

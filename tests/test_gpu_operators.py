@@ -103,7 +103,7 @@ def test_spmm_column_counts_vs_oracle(ncols, dtype):
 
 @pytest.mark.parametrize("n,k", [(120_000, 16), (1_000_000, 32)])
 def test_dominant_kernel_vs_oracle_on_a_searched_graph(n, k):
-    """The kernel the headline solve launches (lap_spmm_wi_kernel, C = 16, selected by `auto` only on graphs that carry the
+    """The kernel the headline solve launches (lap_spmm_wi_kernel, paired-row walk, C = 16, selected by `auto` only on graphs that carry the
     Morton hint of NearestNeighbors.graph) DIRECTLY against the oracle's restatement of graph_laplacian_operator.py:108-124 /
     precision_matern_operator.py:26-37 on the same edge list, in fp32 (1e-5) and fp64 (1e-10), at a mid size and at the full
     cfg-C size (N = 1M, k = 32); plus the fused dot epilogue and the single-column tile SpMV on the same graph."""
@@ -122,12 +122,23 @@ def test_dominant_kernel_vs_oracle_on_a_searched_graph(n, k):
         prec = mgp.PrecisionMaternOperator(lap, nu, torch.tensor([[kappa]], dtype=dtype, device=DEV))
         st = lap.structure
         assert st.perm is not None and st.tiles is not None and "wptr" in st.tiles
+        # fp32: `auto` takes the paired-row walk of the kernel (the one the headline solve launches); the single-row walk of the
+        # same kernel (all there is in fp64) is forced beside it
+        expect = "lap_spmm_wi_kernel<pair>" if dtype == torch.float32 else "lap_spmm_wi_kernel"
         y = lap.matmul(V.to(dtype).to(DEV))
-        assert graph.LAST_SPMM_KERNEL == "lap_spmm_wi_kernel"
+        assert graph.LAST_SPMM_KERNEL == expect
         assert rel_err(y, ref_l) < TOL[dtype]
         yp = prec.matmul(V.to(dtype).to(DEV))
-        assert graph.LAST_SPMM_KERNEL == "lap_spmm_wi_kernel"
+        assert graph.LAST_SPMM_KERNEL == expect
         assert rel_err(yp, ref_p) < TOL[dtype]
+        if dtype == torch.float32:
+            graph.SPMM_KERNEL = "wi"
+            try:
+                yp1 = prec.matmul(V.to(dtype).to(DEV))
+                assert graph.LAST_SPMM_KERNEL == "lap_spmm_wi_kernel"
+            finally:
+                graph.SPMM_KERNEL = "auto"
+            assert rel_err(yp1, ref_p) < TOL[dtype]
         # solver-driver interface (internal order, caller-owned buffers, fused dot product) -- what CG actually calls
         xi = st.to_internal(V.to(dtype).to(DEV)).contiguous()
         out, tmp = torch.empty_like(xi), torch.empty_like(xi)

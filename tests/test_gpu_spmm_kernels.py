@@ -81,7 +81,8 @@ def test_tiled_and_csr_kernels_agree_with_dense(problem, dtype):
             if not use_pre and c % (16 if dtype == torch.float32 else 8) == 0:
                 # v5 warp-interleaved kernel (64-byte rows of X, entry streams in lane-consumption order) and the
                 # one-block-per-tile kernel on the same streams
-                for kern64 in ("wi",):
+                # ... and (fp32) the paired-row walk of the same kernel (union lists of spatially adjacent row pairs)
+                for kern64 in ("wi",) + (("wp",) if dtype == torch.float32 else ()):
                     graph.SPMM_KERNEL = kern64
                     try:
                         dot = torch.zeros(c, dtype=dtype, device=DEV)
@@ -95,6 +96,7 @@ def test_tiled_and_csr_kernels_agree_with_dense(problem, dtype):
                     finally:
                         graph.SPMM_KERNEL = "auto"
                     assert rel_err(Y, ref) < tol, (kern64, c, use_post)
+                    assert graph.LAST_SPMM_KERNEL == ("lap_spmm_wi_kernel<pair>" if kern64 == "wp" else "lap_spmm_wi_kernel")
                     assert torch.equal(Y, Y2)
                     assert rel_err(dot, (X.double() * ref).sum(0)) < tol * 10, (kern64, c)
                     assert (dot3.double() - (Z.double() * ref).sum(0)).abs().max() < tol * 10 * (Z.double().norm() * ref.norm()) / c ** 0.5
@@ -102,7 +104,8 @@ def test_tiled_and_csr_kernels_agree_with_dense(problem, dtype):
         Xe = X
         ref_ext = st.to_external((D @ st.to_internal(Xe).double()) - A @ st.to_internal(Xe).double())
         for kern in ("csr", "tiled") + (("pipe",) if c % (4 if dtype == torch.float32 else 2) == 0 else ()) + \
-                (("wi",) if c % (16 if dtype == torch.float32 else 8) == 0 else ()):
+                (("wi",) if c % (16 if dtype == torch.float32 else 8) == 0 else ()) + \
+                (("wp",) if dtype == torch.float32 and c % 16 == 0 else ()):
             graph.SPMM_KERNEL = kern
             try:
                 Y = graph.lap_spmm(st, a, diag, Xe, x_external=True, y_external=True)
@@ -198,3 +201,45 @@ def test_single_column_tile_spmv_matches_dense(problem, dtype):
     out = lap._matmul(v)
     assert graph.LAST_SPMM_KERNEL == "lap_spmv_tile_kernel"
     assert rel_err(out, (lap.to_dense().double() @ v.double())) < tol
+
+
+def test_paired_walk_on_ragged_graphs_and_epilogues(problem):
+    """The paired-row walk (fp32) on graphs whose last tile is partial and whose rows have very different lengths (k = 5 and
+    k = 40), against the single-row walk of the same kernel and a float64 CSR reference; wrapper epilogue (y = add + coef * Ax),
+    the CG done flag, and many more tiles than thread blocks (byte-ring wrap-around)."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph, _lib
+    x, _, _ = problem
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    for n, k in ((20000, 40), (19999, 5), (130, 6), (100, 3)):
+        xs = x[:n].contiguous()
+        idx, val = mgp.NearestNeighbors(xs).graph(k)
+        lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[0.12]], device=DEV), "symmetric")
+        st = lap.structure
+        _, deg, diag, a = lap._values()
+        assert st.pair_tiles() is not None
+        for c in (16, 48):
+            X = torch.randn(n, c, device=DEV, generator=gen)
+            Z = torch.randn(n, c, device=DEV, generator=gen)
+            rows = torch.repeat_interleave(torch.arange(n, device=DEV), (st.rowptr[1:] - st.rowptr[:-1]).long())
+            ref = diag.double().unsqueeze(1) * X.double()
+            ref.index_add_(0, rows, -a.double().unsqueeze(1) * X.double()[st.col.long()])
+            res = {}
+            for kern in ("wi", "wp"):
+                graph.SPMM_KERNEL = kern
+                try:
+                    dot = torch.zeros(c, device=DEV)
+                    Y = graph.lap_spmm(st, a, diag, X, dot_with=Z, dot_out=dot)
+                    coef = torch.tensor([0.37], device=DEV)
+                    Ye = graph.lap_spmm(st, a, diag, X, ep_coef=coef, ep_add=Z)
+                    done = torch.ones(1, device=DEV)
+                    keep = torch.full((n, c), 7.0, device=DEV)
+                    graph.lap_spmm(st, a, diag, X, out=keep, done_flag=done)
+                finally:
+                    graph.SPMM_KERNEL = "auto"
+                assert rel_err(Y, ref) < 1e-5, (kern, n, k, c)
+                assert rel_err(Ye, Z.double() + 0.37 * ref) < 1e-5, (kern, n, k, c)
+                assert bool((keep == 7.0).all())
+                assert (dot.double() - (Z.double() * ref).sum(0)).abs().max() < 1e-4 * (Z.double().norm() * ref.norm()) / c ** 0.5
+                res[kern] = Y
+            assert rel_err(res["wp"], res["wi"]) < 2e-6

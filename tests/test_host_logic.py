@@ -192,3 +192,74 @@ def test_cuda_solvers_stay_in_front_of_a_real_linear_operator_base(tmp_path):
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(tmp_path), root, os.environ.get("PYTHONPATH", "")]))
     r = subprocess.run([sys.executable, "-c", _REAL_BASE_SCRIPT], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "REAL_BASE_OK" in r.stdout, r.stdout + r.stderr
+
+
+def _emulate_pair_walk(t, a, xs_tiles, n, R=128):
+    """The lane walk of the paired-row kernel on the CPU: per warp block, step and lane one union entry feeds the lane's OWN
+    row and the OTHER row of its pair; lanes 0-3 of a slot output row A, lanes 4-7 row B."""
+    qptr, qcol, qsrc, qrow = t["qptr"].long(), t["qcol"].long() & 0xFFFF, t["qsrc"].long().view(-1, 2), t["qrow"].long()
+    ntiles = (n + R - 1) // R
+    nnzq = t["nnzq"]
+    pos = torch.arange(nnzq)
+    blk = torch.searchsorted(qptr[:16 * ntiles + 1], pos, right=True) - 1
+    lane = (pos - qptr[blk]) & 31
+    tile = blk >> 4
+    a0 = torch.cat([a, torch.zeros(1, dtype=a.dtype)])
+    vm, vo = a0[qsrc[:nnzq, 0]], a0[qsrc[:nnzq, 1]]            # index -1 -> the appended zero
+    xr = xs_tiles[tile, qcol[:nnzq]]                             # [nnzq, C]
+    pi = (blk & 15) * 4 + (lane >> 3)
+    h = (lane >> 2) & 1
+    row_mine = tile * R + qrow[tile * R + 2 * pi + h]
+    row_other = tile * R + qrow[tile * R + 2 * pi + (1 - h)]
+    y = torch.zeros(ntiles * R, xs_tiles.shape[2], dtype=a.dtype)
+    y.index_add_(0, row_mine, vm.unsqueeze(1) * xr)
+    y.index_add_(0, row_other, vo.unsqueeze(1) * xr)
+    return y[:n], dict(lane=lane, blk=blk, col=qcol[:nnzq], real=(qsrc[:nnzq] >= 0).any(1))
+
+
+def test_pair_streams_reproduce_the_matvec_and_keep_lane_parity():
+    from manifold_gp_b200.graph import pair_streams
+    g = torch.Generator().manual_seed(3)
+    R = 128
+    for n, maxlen, with_pos in ((300, 9, True), (128, 40, False), (1000, 5, True), (5, 7, True), (257, 50, True), (640, 30, False)):
+        ntiles = (n + R - 1) // R
+        rowlen = torch.randint(0, maxlen, (n,), generator=g)
+        rowptr = torch.zeros(n + 1, dtype=torch.int32)
+        rowptr[1:] = torch.cumsum(rowlen, 0)
+        nnz = int(rowptr[-1])
+        # columns drawn from a narrow window so that neighbouring rows really share columns; a few duplicates inside a row
+        rows = torch.repeat_interleave(torch.arange(n), rowlen)
+        lcol = torch.cat([(r % R) // 2 + torch.randperm(64, generator=g)[:int(rowlen[r])] for r in range(n)] + [torch.zeros(0, dtype=torch.long)])
+        if nnz > 4:
+            lcol[1] = lcol[0]                            # a repeated column inside a row (the reference lists diagonal entries twice)
+        lcol = lcol.to(torch.int16)
+        a = torch.randn(nnz, generator=g, dtype=torch.float64)
+        pos = None
+        if with_pos:                                   # a spatial order that differs from the row order inside every tile
+            pos = torch.cat([tl * R + torch.randperm(min(R, n - tl * R), generator=g) for tl in range(ntiles)])
+        t = pair_streams(rowptr, lcol, n, pos, R)
+        assert t["qnzmax"] % 32 == 0 and t["qptr"].numel() == 512 * ((ntiles + 31) // 32) + 4
+        xs = torch.randn(ntiles, 256, 4, generator=g, dtype=torch.float64)
+        y, info = _emulate_pair_walk(t, a, xs, n)
+        ref = torch.zeros(n, 4, dtype=torch.float64)
+        ref.index_add_(0, rows, a.unsqueeze(1) * xs[rows // R, lcol.long()])
+        assert torch.allclose(y, ref, atol=1e-12)
+        # every CSR entry is used exactly once
+        used = t["qsrc"].long()
+        used = used[used >= 0]
+        assert used.numel() == nnz and torch.equal(torch.sort(used).values, torch.arange(nnz))
+        # the row table is a permutation of every tile's rows
+        assert torch.equal(torch.sort(t["qrow"].long().view(ntiles, R), 1).values, torch.arange(R).expand(ntiles, R))
+        # padding columns are valid own rows; lanes 0-3 of a slot hold even columns, lanes 4-7 odd ones, up to the spill
+        lane, col, real = info["lane"], info["col"], info["real"]
+        nrows_t = torch.clamp(n - (info["blk"] >> 4) * R, max=R)
+        assert bool((col[~real] < nrows_t[~real]).all())
+        expect = (lane >> 2) & 1
+        mism = ((col & 1) != expect) & real
+        assert float(mism.sum()) <= 0.5 * float(real.sum())
+    # Morton-adjacent rows with identical lists: the union is half the entries
+    n = 256
+    rowptr = torch.arange(0, 8 * (n + 1), 8, dtype=torch.int32)
+    lcol = (torch.arange(n).repeat_interleave(8) // 2 * 2 + torch.arange(8).repeat(n) * 16).remainder(300).to(torch.int16)
+    t = pair_streams(rowptr, lcol, n, None, R)
+    assert t["q_unions"] == 8 * n // 2
