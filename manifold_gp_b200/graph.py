@@ -192,13 +192,63 @@ def wi_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 128)
     return dict(wptr=wpad, wcol=wcol, nnzw=nnzw, wnzmax=int(tile_tot.max()))
 
 
+def pair_matching(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 128, chunk_tiles: int = 2048):
+    """Which rows of a tile share a slot of the paired-row walk: a greedy maximum-weight matching of every tile's rows, weight =
+    number of columns two rows have in common (the X-row loads the pair saves).  Per tile the 128 x 128 weight matrix is one
+    small product of the tile's 0/1 pattern with its transpose; the matching is the locally-dominant-edge form of the greedy
+    algorithm (every round each free row points at its heaviest free partner, mutual choices are matched; ties are broken by
+    a strict order on the pairs, so the heaviest remaining edge is always mutual and <= 64 rounds finish a tile).  On the
+    cfg-C torus: 0.594 union entries per nonzero against 0.661 for Morton-adjacent rows (measured on a 60k proxy).
+    Returns ``pos`` [ntiles * R] int64: position of every (real or virtual) row in its tile's pair order -- rows at positions
+    2p, 2p + 1 are a pair.  Setup only (torch ops, any device), once per graph."""
+    dev = rowptr.device
+    ntiles = (n + R - 1) // R
+    rp = rowptr.to(torch.int64)
+    rowlen = rp[1:] - rp[:-1]
+    rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), rowlen)
+    lc = lcol16.to(torch.int64) & 0xFFFF
+    L = int(lc.max()) + 1 if lc.numel() else R
+    tile_ptr = rp[torch.arange(0, ntiles + 1, device=dev, dtype=torch.int64).mul(R).clamp_max(n)]
+    wdt = torch.float16 if dev.type == "cuda" else torch.float32
+    ar = torch.arange(R, device=dev, dtype=torch.int64)
+    tb = torch.minimum(ar[:, None], ar[None, :]) * R + torch.maximum(ar[:, None], ar[None, :])      # strict order on unordered pairs
+    pos = torch.empty(ntiles * R, dtype=torch.int64, device=dev)
+    for c0 in range(0, ntiles, chunk_tiles):
+        c1 = min(ntiles, c0 + chunk_tiles)
+        T = c1 - c0
+        e0, e1 = int(tile_ptr[c0]), int(tile_ptr[c1])
+        pat = torch.zeros(T, R, L, dtype=wdt, device=dev)
+        pat[rows[e0:e1] // R - c0, rows[e0:e1] % R, lc[e0:e1]] = 1
+        W = torch.bmm(pat, pat.transpose(1, 2)).to(torch.float32).to(torch.int64) * (R * R) + tb     # [T, R, R], symmetric
+        del pat
+        W.diagonal(dim1=1, dim2=2).fill_(-1)
+        alive = torch.ones(T, R, dtype=torch.bool, device=dev)
+        partner = torch.full((T, R), -1, dtype=torch.int64, device=dev)
+        for _ in range(R // 2):
+            best = W.masked_fill(~alive[:, None, :], -1).argmax(2)
+            mutual = alive & alive.gather(1, best) & (best.gather(1, best) == ar)
+            partner = torch.where(mutual, best, partner)
+            alive &= ~mutual
+            if not bool(alive.any()):
+                break
+        del W
+        # pair order: by the smaller row of the pair; the smaller row takes the even position
+        lo = torch.minimum(ar.expand(T, R), partner)
+        order = torch.argsort(lo * (2 * R) + ar, dim=1, stable=True)                 # rows of a tile sorted by (pair key, row)
+        pr = torch.empty(T, R, dtype=torch.int64, device=dev)
+        pr.scatter_(1, order, ar.expand(T, R).contiguous())
+        pos[c0 * R:c1 * R] = pr.reshape(-1)
+    return pos
+
+
 def pair_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, spatial_pos: torch.Tensor = None, R: int = 128):
     """Paired-row entry streams of the v6 SpMM walk (csrc/lap_spmm_wi.cu, PAIR = true).  Two spatially adjacent rows of a tile
     share most of their columns (kNN graph in Morton order: the union of a pair's lists is ~0.66 of their sum), so a slot of
     8 lanes walks the UNION list of a row pair: one 64-byte X-row load from shared memory feeds both rows (32 FMAs instead
     of 16 per load -- the walk is bound by shared-memory wavefronts).  Layout, per tile of R = 128 rows:
 
-    * the 64 pairs are Morton-adjacent rows (``spatial_pos``: position of every row in the spatial order; None = rows 2p, 2p+1),
+    * the 64 pairs are the rows at positions 2p, 2p + 1 of ``spatial_pos`` (position of every row in its tile's pair order:
+      ``pair_matching``, or the Morton order of the rows; None = rows 2p, 2p + 1),
       ordered by union length (descending) so the 4 pairs of a warp block run in lock-step; ``qrow[128 tile + 2 pi + h]`` is the
       tile-local row that half h of pair pi outputs (uint8);
     * warp block b = 16 tile + (pi >> 2), slot = pi & 3; stream position qptr[b] + 32 t + 8 slot + l holds the union entry that
@@ -223,7 +273,9 @@ def pair_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, spatial_pos
     ar = lambda m: torch.arange(m, device=dev, dtype=torch.int64)
     # spatial position of every (real or virtual) row inside its tile -> first-cut pair id and half
     q0 = ar(NT) % R
-    if spatial_pos is not None:
+    if spatial_pos is not None and spatial_pos.numel() == NT:          # a full pair order (pair_matching): virtual rows included
+        q0 = spatial_pos.to(torch.int64) % R
+    elif spatial_pos is not None:
         q0[:n] = spatial_pos.to(torch.int64) % R
         if NT > n:                                                   # virtual rows take the positions the real rows left free
             used = torch.zeros(R, dtype=torch.bool, device=dev)
@@ -493,7 +545,8 @@ class GraphStructure:
             return None
         if "qptr" not in t and not self.__dict__.get("_pair_tried"):
             self._pair_tried = True
-            q = pair_streams(self.rowptr, t["lcol"][:self.nnz], self.n, self.morton_pos, self.TILE_ROWS)
+            lc = t["lcol"][:self.nnz]
+            q = pair_streams(self.rowptr, lc, self.n, pair_matching(self.rowptr, lc, self.n, self.TILE_ROWS), self.TILE_ROWS)
             if q is not None:
                 t.update(q)
         return t if "qptr" in t else None

@@ -263,3 +263,40 @@ def test_pair_streams_reproduce_the_matvec_and_keep_lane_parity():
     lcol = (torch.arange(n).repeat_interleave(8) // 2 * 2 + torch.arange(8).repeat(n) * 16).remainder(300).to(torch.int16)
     t = pair_streams(rowptr, lcol, n, None, R)
     assert t["q_unions"] == 8 * n // 2
+
+
+def test_pair_matching_is_a_perfect_matching_that_beats_adjacent_rows():
+    from manifold_gp_b200.graph import pair_matching, pair_streams
+    g = torch.Generator().manual_seed(4)
+    R = 128
+    for n in (300, 256, 77):
+        ntiles = (n + R - 1) // R
+        # rows k and k + 64 of a tile share most of their columns: adjacent pairing finds nothing, the matching everything
+        rowlen = torch.full((n,), 12)
+        rowptr = torch.zeros(n + 1, dtype=torch.int32)
+        rowptr[1:] = torch.cumsum(rowlen, 0)
+        rows = torch.repeat_interleave(torch.arange(n), rowlen)
+        grp = (rows % R) % 64
+        lcol = (grp * 4 + torch.arange(12).repeat(n) % 12 + (torch.rand(rows.numel(), generator=g) < 0.1) * 300).to(torch.int16)
+        # make the columns of a row distinct
+        lcol = (grp * 12 + torch.arange(12).repeat(n)).to(torch.int16)
+        pos = pair_matching(rowptr, lcol, n, R)
+        assert pos.numel() == ntiles * R
+        assert torch.equal(torch.sort(pos.view(ntiles, R), 1).values, torch.arange(R).expand(ntiles, R))
+        t_match = pair_streams(rowptr, lcol, n, pos, R)
+        t_adj = pair_streams(rowptr, lcol, n, None, R)
+        assert t_match["q_unions"] < t_adj["q_unions"]
+        a = torch.randn(int(rowptr[-1]), generator=g, dtype=torch.float64)
+        xs = torch.randn(ntiles, 800, 3, generator=g, dtype=torch.float64)
+        y, _ = _emulate_pair_walk(t_match, a, xs, n)
+        ref = torch.zeros(n, 3, dtype=torch.float64)
+        ref.index_add_(0, rows, a.unsqueeze(1) * xs[rows // R, lcol.long()])
+        assert torch.allclose(y, ref, atol=1e-12)
+    # full tiles: every row k is matched with k + 64 (identical column lists)
+    n = 256
+    rowptr = torch.arange(0, 12 * (n + 1), 12, dtype=torch.int32)
+    rows = torch.repeat_interleave(torch.arange(n), 12)
+    lcol = (((rows % R) % 64) * 12 + torch.arange(12).repeat(n)).to(torch.int16)
+    pos = pair_matching(rowptr, lcol, n, R).view(2, R)
+    for k in range(64):
+        assert int(pos[0, k]) // 2 == int(pos[0, k + 64]) // 2
