@@ -305,6 +305,8 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&desc_bar[s]);                                 // release: the filler may take the tile
+          // (An L2 bulk prefetch of the streams 6 tiles ahead was measured: 113.3 vs 110.8 us without -- the fill is not bound by
+          // the DRAM round trip.)
           if (((t + 1) & 31) == 0 && c + 2 <= ch_last) request_meta(c + 2);   // this chunk is finished: refill its ring slot
         }
         a_phead += size;
