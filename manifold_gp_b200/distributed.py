@@ -346,6 +346,44 @@ class DistCG:
         info = dict(iterations=int(tail[solvers.K_ITER]), mean_residual=float(tail[solvers.K_MEAN]), converged=(done == 1.0))
         return out, info
 
+    def apply(self, x_loc: torch.Tensor) -> torch.Tensor:
+        """(P x) on this rank's rows, outside the iteration: halo all-to-all + the chained local SpMM launches (the NCCL
+        transport of ``DistPrecision.matvec``; bare precision operator).  Every rank must call it."""
+        op, c = self.op, self.c
+        bufs = self.__dict__.get("_apply_bufs")
+        if bufs is None:
+            z = lambda rows: torch.zeros((rows, self.ld), dtype=self.dt, device=self.dev)
+            bufs = self._apply_bufs = (z(op.n_ext), z(op.n_ext), z(op.n_loc))
+        src, tmp, out = bufs
+        src[:op.n_loc, :c].copy_(x_loc)
+        op.matvec(src, out, tmp, c)
+        return out[:, :c]
+
+    def solve_polished(self, b_loc: torch.Tensor, factor: float = 8.0):
+        """``solve`` plus the one true-residual correction of ``settings.cg_polish`` (solvers._polish) on the partitioned solver:
+        fp32 mBCG stops on the recurrence residual, whose drift leaves a TRUE residual of ~2e-4 at cfg-C; evaluate r = b - P x once
+        (global norms: two all-reduced sums), solve P d = r to ``factor * tol * |b| / |r|`` with the same kernels, return x + d.
+        info gains ``polish = {true_residual_before, iterations}``.  Bare precision operator, fp32, converged solves only."""
+        x, info = self.solve(b_loc)
+        if self.dt != torch.float32 or self.tol > 1e-4 or not info["converged"] or self.op.coef is not None:
+            return x, info
+        r = b_loc - self.apply(x)
+        sums = torch.stack((r.double().square().sum(0), b_loc.double().square().sum(0)))
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(sums, group=self.group)
+        before = float((sums[0] / sums[1].clamp_min(1e-300)).sqrt().mean())
+        info["polish"] = {"true_residual_before": before, "iterations": 0}
+        if not (before > factor * self.tol) or before != before:
+            return x, info
+        tol0 = self.tol
+        self.tol = min(0.5, factor * tol0 / before)          # the tolerance is written to the device state by the solve's init step
+        try:
+            d, dinfo = self.solve(r.contiguous())
+        finally:
+            self.tol = tol0
+        info["polish"]["iterations"] = int(dinfo["iterations"])
+        return x + d, info
+
 
 class PeerMemory:
     """Peer-mapped ("symmetric") device allocations of one process group: every rank allocates the same shape and gets the
@@ -908,7 +946,8 @@ def bench_main(args, CFG, clock_sampler=None):
         cg = DistCG(op, c, torch.float32, tolerance=CFG["tol"], max_iter=CFG["max_iter"])
 
     def solve():
-        return cg.solve(b_loc)
+        # like the single-GPU arm: the timed solve includes the one true-residual correction (settings.cg_polish)
+        return cg.solve_polished(b_loc)
 
     for _ in range(args.warmup):
         xs, info = solve()
@@ -958,13 +997,14 @@ def bench_main(args, CFG, clock_sampler=None):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
     for _ in range(max(1, min(args.steps, 2))):
         bl = Bh.to(dev, non_blocking=True)
-        xs2, _ = cg.solve(bl)
+        xs2, _ = cg.solve_polished(bl)
         Xh.copy_(xs2, non_blocking=True)
         torch.cuda.synchronize()
     dist.barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, min(args.steps, 2))
     if rank == 0:
-        iters = int(info["iterations"])
+        polish = dict(info.get("polish") or {})
+        iters = int(info["iterations"]) + int(polish.get("iterations", 0))
         unit = "CG iterations/s (N=1M, k=32, nu=2, 16 RHS per iteration)"
         out = {"metric": "precision_cg_iterations_per_s", "value": round(iters / (float(ms) * 1e-3), 1), "unit": unit, "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(ms), 3), "solve_ms": round(float(ms), 3),
@@ -975,8 +1015,9 @@ def bench_main(args, CFG, clock_sampler=None):
                           "self_loops": CFG["self_loops"], "partition": "contiguous row blocks of the Morton order",
                           "halo_rows_rank0": int(op.plan.halo_ids.numel()), "rows_rank0": int(op.n_loc),
                           "l2": "inputs larger than L2 at 1-2 GPUs; at 8 GPUs a rank's share (~50 MB) is L2 resident (strong scaling)"},
-               "cg_iterations": iters, "cg_converged": bool(info["converged"]),
-               "cg_true_relative_residual": true_rel, "parity_vs_single_gpu": vs_single, "knn_build_s": round(t_knn, 4),
+               "cg_iterations": int(info["iterations"]), "cg_polish_iterations": int(polish.get("iterations", 0)),
+               "cg_converged": bool(info["converged"]) and true_rel <= 10 * CFG["tol"], "cg_converged_recurrence": bool(info["converged"]),
+               "cg_true_relative_residual": true_rel, "cg_true_relative_residual_unpolished": polish.get("true_residual_before"), "parity_vs_single_gpu": vs_single, "knn_build_s": round(t_knn, 4),
                "e2e": {"value": round(iters / (e2e_ms * 1e-3), 1), "unit": unit, "solve_ms": round(e2e_ms, 3),
                        "h2d_bytes_per_step": int(Bh.numel() * 4 * world), "d2h_bytes_per_step": int(Xh.numel() * 4 * world)},
                "gpu_launches": int(launches),

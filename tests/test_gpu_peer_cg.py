@@ -162,3 +162,37 @@ def test_distributed_lanczos_matches_the_single_gpu_driver(pg1):
     ref_vecs = q_ref.T @ v_ref
     assert evecs.shape == ref_vecs.shape
     assert rel_err(evecs.abs(), ref_vecs.abs()) < 1e-6
+
+
+def test_partitioned_solve_with_the_true_residual_correction(pg1):
+    """DistCG.solve_polished (the partitioned form of settings.cg_polish): on an ill-conditioned fp32 system the recurrence
+    converges while the true residual drifts; one correction solve on r = b - P x brings the TRUE residual within 10 x tol, the
+    iteration counts of the main run are unchanged, and the result agrees with the single-GPU polished solve."""
+    from manifold_gp_b200 import distributed as D, settings, solvers
+    n, k, c, nu = 60000, 16, 16, 2
+    lap, prec = _problem(n, k, torch.float32, nu=nu, kappa=0.5)
+    gst = lap.structure
+    _, _, diag, a = lap._values()
+    part = D.RowPartition(n, 1, align=gst.TILE_ROWS)
+    op = D.DistPrecision(gst, diag, a, prec._shift(), nu, part, 0)
+    B = torch.randn(n, c, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+    tol = 1e-6
+    cg = D.PeerCG(op, c, torch.float32, tolerance=tol, max_iter=4000)
+    b_loc = gst.to_internal(B).contiguous()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x0, info0 = cg.solve(b_loc)
+        x1, info1 = cg.solve_polished(b_loc)
+        with settings.cg_polish(True):
+            ref, rinfo = solvers.linear_cg(prec, B, tolerance=tol, max_iter=4000, return_info=True)
+    assert info0["converged"] and info1["converged"] and info1["iterations"] == info0["iterations"]
+    true = lambda xs: float(((prec._matmul(gst.to_external(xs)) - B).double().norm(dim=0) / B.double().norm(dim=0)).mean())
+    t0, t1 = true(x0), true(x1)
+    assert abs(info1["polish"]["true_residual_before"] - t0) < 0.05 * t0
+    if t0 > 8 * tol:                                   # the drift is there: the correction must remove it
+        assert info1["polish"]["iterations"] > 0 and t1 <= 10 * tol and t1 < 0.5 * t0
+    else:
+        assert info1["polish"]["iterations"] == 0
+    assert rel_err(gst.to_external(x1), ref) < 1e-4
+    # apply(): the partitioned operator outside the iteration equals the single-GPU matvec
+    assert rel_err(gst.to_external(cg.apply(b_loc)), prec._matmul(B)) < 1e-5
