@@ -114,6 +114,14 @@ int mgp_lap_values_f32(const int32_t* rowptr, const int32_t* col, const float* d
 int mgp_lap_values_f64(const int32_t* rowptr, const int32_t* col, const double* d2csr, int64_t n,
                        const double* eps, int32_t self_loops,
                        double* deg_unnorm, double* deg, double* diag, double* a, void* stream);
+/* One pass (1, 2 or 3) of the same build on the rows of a row-partitioned structure (SURVEY.md 8e "value build"): n = rows this
+ * rank owns, `col` in the rank's extended numbering [own rows | halo rows], deg_unnorm / deg with n_ext entries.  The caller
+ * fills the halo part of deg_unnorm (halo exchange) between pass 1 and 2 and the halo part of deg between pass 2 and 3 --
+ * the two halo gathers that replace the reference's global scatter_add_ passes (graph_laplacian_operator.py:52-106). */
+int mgp_lap_values_pass_f32(int32_t pass, const int32_t* rowptr, const int32_t* col, const float* d2csr, int64_t n, const float* eps,
+                            int32_t self_loops, float* deg_unnorm, float* deg, float* diag, float* a, void* stream);
+int mgp_lap_values_pass_f64(int32_t pass, const int32_t* rowptr, const int32_t* col, const double* d2csr, int64_t n, const double* eps,
+                            int32_t self_loops, double* deg_unnorm, double* deg, double* diag, double* a, void* stream);
 
 /* Backward of mgp_lap_values w.r.t. eps (what autograd through graph_laplacian_operator.py:52-106 yields for
  * raw_graphbandwidth; exercised by the reference's test_grad / test_ml, test/_test_functions.py:59-104):

@@ -102,6 +102,8 @@ _SIG = {
     "mgp_lanczos_ws_bytes": (c_size_t, [c_int64, c_int32]),
     "mgp_lanczos_reorth_f32": (c_int32, [P, c_int64, c_int32, P, c_int64, P, P, P, P]),
     "mgp_lanczos_reorth_f64": (c_int32, [P, c_int64, c_int32, P, c_int64, P, P, P, P]),
+    "mgp_lap_values_pass_f32": (c_int32, [c_int32, P, P, P, c_int64, P, c_int32, P, P, P, P, P]),
+    "mgp_lap_values_pass_f64": (c_int32, [c_int32, P, P, P, c_int64, P, c_int32, P, P, P, P, P]),
     "mgp_lap_pair_values_f32": (c_int32, [P, P, c_int64, P, P]),
     "mgp_lap_pair_values_f64": (c_int32, [P, P, c_int64, P, P]),
     "mgp_lanczos_axpy_f32": (c_int32, [P, c_int64, c_int32, P, c_int64, P, P, P, P]),

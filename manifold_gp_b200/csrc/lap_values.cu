@@ -188,9 +188,37 @@ static int lap_values(const int* rowptr, const int* col, const T* d2, int64_t n,
   return MGP_OK;
 }
 
+// One pass of the value build on the rows of a row-partitioned structure (SURVEY.md 8e "value build: two halo gathers"):
+// n = rows this rank owns; col indexes the rank's extended numbering [own rows | halo rows]; dt / dg hold n_ext entries, the
+// halo part of dt must be filled (halo exchange) before pass 2, the halo part of dg before pass 3.
+template <typename T>
+static int lap_values_pass(int pass, const int* rowptr, const int* col, const T* d2, int64_t n, const T* eps, int self_loops,
+                           T* dt, T* dg, T* diag, T* a, cudaStream_t st) {
+  MGP_CHECK_ARG(rowptr && col && d2 && eps && dt, "lap_values_pass: null pointer");
+  MGP_CHECK_ARG(pass >= 1 && pass <= 3 && (pass < 2 || dg) && (pass < 3 || (diag && a)), "lap_values_pass: pass %d lacks its outputs", pass);
+  MGP_CHECK_ARG(n > 0, "lap_values_pass: n must be positive");
+  const int block = 256;
+  const int64_t grid = ceil_div(n * kValLanes, block);
+  MGP_CHECK_ARG(grid < ((int64_t)1 << 31), "lap_values_pass: n too large for one launch");
+  if (pass == 1) lap_values_kernel<T, 1><<<(unsigned)grid, block, 0, st>>>(rowptr, col, d2, n, eps, self_loops, dt, dg, diag, a);
+  else if (pass == 2) lap_values_kernel<T, 2><<<(unsigned)grid, block, 0, st>>>(rowptr, col, d2, n, eps, self_loops, dt, dg, diag, a);
+  else lap_values_kernel<T, 3><<<(unsigned)grid, block, 0, st>>>(rowptr, col, d2, n, eps, self_loops, dt, dg, diag, a);
+  MGP_LAUNCH_CHECK();
+  return MGP_OK;
+}
+
 }  // namespace mgp
 
 extern "C" {
+
+int mgp_lap_values_pass_f32(int32_t pass, const int32_t* rowptr, const int32_t* col, const float* d2csr, int64_t n, const float* eps,
+                            int32_t self_loops, float* deg_unnorm, float* deg, float* diag, float* a, void* stream) {
+  return mgp::lap_values_pass<float>(pass, rowptr, col, d2csr, n, eps, self_loops, deg_unnorm, deg, diag, a, (cudaStream_t)stream);
+}
+int mgp_lap_values_pass_f64(int32_t pass, const int32_t* rowptr, const int32_t* col, const double* d2csr, int64_t n, const double* eps,
+                            int32_t self_loops, double* deg_unnorm, double* deg, double* diag, double* a, void* stream) {
+  return mgp::lap_values_pass<double>(pass, rowptr, col, d2csr, n, eps, self_loops, deg_unnorm, deg, diag, a, (cudaStream_t)stream);
+}
 
 int mgp_lap_values_f32(const int32_t* rowptr, const int32_t* col, const float* d2csr, int64_t n, const float* eps,
                        int32_t self_loops, float* deg_unnorm, float* deg, float* diag, float* a, void* stream) {

@@ -1028,3 +1028,187 @@ def bench_main(args, CFG, clock_sampler=None):
         print(json.dumps(out))
     dist.barrier()
     return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Partitioned graph construction (SURVEY.md 8e rows "symmetrise + coalesce" and "value build"): a rank builds, holds and
+# updates ONLY its rows -- no rank ever sees the whole edge list.
+# ---------------------------------------------------------------------------------------------------------------------------
+def partitioned_symmetrize(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, part: RowPartition, rank: int, group=None):
+    """Row-partitioned form of ``NearestNeighbors.graph``'s symmetrise + mean-coalesce (nearest_neighbors.py:45-51).
+
+    In: the directed kNN edges of the rows this rank owns (``rows`` in [lo, hi), ``cols`` anywhere, ``vals`` squared distances,
+    self column already dropped).  The reference maps an edge to (min, max) and averages duplicates; row i of the symmetric
+    operator then lists every j with i -> j or j -> i.  Here ONE ``all_to_all_v`` sends each edge i -> j to the owner of j as
+    (j, i, d): afterwards a rank holds both directions of every edge incident to its rows and coalesces them locally -- the
+    mean over the duplicates of {i, j} is taken from exactly the directed edges the reference averages.  A surviving
+    ``j == i`` (duplicate points) is listed twice, as the reference's two scatter passes count it.
+    Returns (row, col, val) of the rank's rows, sorted by (row, col), columns in the GLOBAL numbering.  Device-agnostic."""
+    world = part.world
+    dev = rows.device
+    rows, cols = rows.to(torch.int64), cols.to(torch.int64)
+    owner = part.owner(cols).clamp_(max=world - 1)
+    notdiag = cols != rows                          # i -> i is its own reverse: it already sits in the out-list
+    o_nd = owner[notdiag]
+    order = torch.argsort(o_nd, stable=True)
+    send_ids = torch.stack((cols[notdiag][order], rows[notdiag][order]), dim=1).contiguous()      # (their row, their column)
+    send_vals = vals[notdiag][order].contiguous()
+    send_counts = torch.bincount(o_nd, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    recv_ids = torch.empty((int(sum(rc)), 2), dtype=torch.int64, device=dev)
+    recv_vals = torch.empty(int(sum(rc)), dtype=vals.dtype, device=dev)
+    dist.all_to_all_single(recv_ids, send_ids, rc, sc, group=group)
+    dist.all_to_all_single(recv_vals, send_vals, rc, sc, group=group)
+    r = torch.cat((rows, recv_ids[:, 0]))
+    c = torch.cat((cols, recv_ids[:, 1]))
+    v = torch.cat((vals, recv_vals))
+    key = r * part.n + c
+    ukey, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+    acc = torch.zeros(ukey.numel(), dtype=v.dtype, device=dev).scatter_add_(0, inv, v)
+    val = acc / cnt.to(v.dtype)
+    row, col = ukey // part.n, ukey % part.n
+    rep = 1 + (row == col).to(torch.int64)          # diagonal entries count twice
+    if bool((rep > 1).any()):
+        row, col, val = row.repeat_interleave(rep), col.repeat_interleave(rep), val.repeat_interleave(rep)
+    return row, col, val
+
+
+class PartitionedGraph:
+    """The kNN graph of a point cloud, ROW-PARTITIONED AT CONSTRUCTION (one process per GPU): the database is replicated (as in
+    ``sharded_knn``: the exhaustive search needs all points), everything after the search is partitioned --
+
+    * rows are contiguous, tile-aligned blocks of the Morton order of the points (computed redundantly, deterministic);
+    * a rank searches the neighbours of ITS rows only, exchanges the reverse edges (``partitioned_symmetrize``: one
+      all_to_all_v of (row, col, dist^2) triples) and builds the CSR / tile / stream structure of its rows
+      (``GraphStructure.from_rows``; columns in the extended numbering [own rows | halo rows] of its ``HaloPlan``);
+    * ``values`` runs the three passes of the value build on its rows with two halo gathers (degrees, then normalised
+      degrees) between them (``mgp_lap_values_pass``).
+
+    Per rank: nnz / world entries instead of the whole structure (8 GB at N = 10M, k = 32 when replicated)."""
+
+    def __init__(self, x: torch.Tensor, k: int, group=None):
+        from . import graph
+        from .utils import NearestNeighbors
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = int(x.shape[0])
+        self.n, self.k = n, int(k)
+        self.perm = graph.morton_permutation(x)                       # new position -> original index
+        self.inv = torch.empty_like(self.perm)
+        self.inv[self.perm] = torch.arange(n, device=x.device)
+        self.part = RowPartition(n, self.world, align=graph.GraphStructure.TILE_ROWS)
+        lo, hi = self.part.range(self.rank)
+        self.lo, self.hi = lo, hi
+        knn = NearestNeighbors(x)
+        d2, nbr = knn.search(x.index_select(0, self.perm[lo:hi]).contiguous(), k)
+        self.knn_info = knn.last_search
+        self.kth_dist2 = d2[:, k - 1].contiguous()                   # bandwidth heuristics (median k-th neighbour distance)
+        rows = torch.arange(lo, hi, device=x.device, dtype=torch.int64).repeat_interleave(k - 1)
+        cols = self.inv[nbr[:, 1:].reshape(-1).to(torch.int64)]
+        row, col, val = partitioned_symmetrize(rows, cols, d2[:, 1:].reshape(-1), self.part, self.rank, group)
+        self.plan = HaloPlan(self.part, self.rank, col, group=group)
+        n_loc = hi - lo
+        rowptr = torch.searchsorted(row, torch.arange(lo, hi + 1, device=x.device, dtype=torch.int64))
+        self.st = graph.GraphStructure.from_rows(rowptr, self.plan.to_local(col), n_loc, n_loc + int(self.plan.halo_ids.numel()))
+        self.entry_d2 = val.contiguous()                             # per entry, in the order the structure's ``eid`` indexes
+        self.st._pair_tried = True          # the partitioned solvers keep ONE value-stream buffer alive across bandwidths (captured
+                                            # graphs): that hook exists for the single-row streams only, so no paired walk here
+        self.n_loc, self.n_ext = n_loc, self.st.n_cols
+        t = self.st.tiles
+        if t is not None and "hcol" in t:
+            # peer-memory variant of the halo lists: (owner rank << 26) | row inside the owner's block
+            loc = t["hcol"].to(torch.int64)
+            gid = torch.where(loc < n_loc, loc + lo, self.plan.halo_ids[(loc - n_loc).clamp(min=0, max=max(self.plan.halo_ids.numel() - 1, 0))]
+                              if self.plan.halo_ids.numel() else loc + lo)
+            own = self.part.owner(gid).clamp_(max=self.world - 1)
+            starts = torch.tensor(self.part.bounds[:-1], dtype=torch.int64, device=x.device)
+            t["hcol_peer"] = ((own << 26) | (gid - starts[own])).to(torch.int32).contiguous()
+
+    def values(self, eps, self_loops: bool = True, dtype=torch.float32):
+        """(deg_unnorm [n_ext], deg [n_ext], diag [n_loc], a [nnz_loc]) for bandwidth ``eps`` -- graph_laplacian_operator.py:52-106
+        on this rank's rows; the halo parts of the two degree vectors come from their owners (two halo gathers)."""
+        from . import _lib, graph
+        from ._lib import c_int32, c_int64, ptr, stream
+        st = self.st
+        d2 = st.d2csr(self.entry_d2.to(dtype))
+        dev = st.device
+        eps_t = graph._device_scalar(eps, dtype, dev)
+        dt = torch.zeros(self.n_ext, dtype=dtype, device=dev)
+        dg = torch.zeros(self.n_ext, dtype=dtype, device=dev)
+        diag = torch.empty(self.n_loc, dtype=dtype, device=dev)
+        a = torch.zeros(st.nnz + 8, dtype=dtype, device=dev)[:st.nnz]
+        sfx = _lib.suffix(dtype)
+        for p in (1, 2, 3):
+            _lib.call("mgp_lap_values_pass_" + sfx, c_int32(p), ptr(st.rowptr), ptr(st.col), ptr(d2), c_int64(self.n_loc), ptr(eps_t),
+                      c_int32(1 if self_loops else 0), ptr(dt), ptr(dg), ptr(diag), ptr(a), stream())
+            if p == 1:
+                self.plan.exchange(dt.view(-1, 1))
+            elif p == 2:
+                self.plan.exchange(dg.view(-1, 1))
+        return dt, dg, diag, a
+
+    # rows of a replicated [n, C] array that this rank owns, in the structure's order / back
+    def to_local(self, v: torch.Tensor) -> torch.Tensor:
+        return v.index_select(0, self.perm[self.lo:self.hi])
+
+    def gather(self, v_loc: torch.Tensor) -> torch.Tensor:
+        """[n, C] in the caller's point order from every rank's block (one all-gather)."""
+        sizes = [self.part.range(r)[1] - self.part.range(r)[0] for r in range(self.world)]
+        if self.world == 1:
+            full = v_loc
+        else:
+            parts = [torch.empty((s,) + tuple(v_loc.shape[1:]), dtype=v_loc.dtype, device=v_loc.device) for s in sizes]
+            dist.all_gather(parts, v_loc.contiguous(), group=self.group)
+            full = torch.cat(parts)
+        return full.index_select(0, self.inv)
+
+
+class PartitionedPrecision(DistPrecision):
+    """``DistPrecision`` on a ``PartitionedGraph``: same surface for the partitioned solvers (``DistCG`` / ``PeerCG`` /
+    ``dist_lanczos_tridiag``), but structure and values are built from this rank's rows only; ``update`` re-runs the
+    partitioned value build into the same buffers (captured CUDA graphs and peer-memory registrations survive)."""
+
+    def __init__(self, pg: PartitionedGraph, eps, nu: int, kappa, self_loops: bool = True, dtype=torch.float32, coef=None, noise=None):
+        self.pg, self.plan, self.st, self.gst = pg, pg.plan, pg.st, None
+        self.lo, self.hi, self.nu = pg.lo, pg.hi, int(nu)
+        self.n_loc, self.n_ext = pg.n_loc, pg.n_ext
+        self.self_loops = bool(self_loops)
+        dev = pg.st.device
+        self.diag = torch.empty(self.n_loc, dtype=dtype, device=dev)
+        self.a = torch.zeros(pg.st.nnz + 8, dtype=dtype, device=dev)[:pg.st.nnz]
+        self.shift = torch.empty(1, dtype=dtype, device=dev)
+        self.coef = torch.ones(1, dtype=dtype, device=dev) if (coef is not None or noise is not None) else None
+        self.ncoef = torch.zeros(1, dtype=dtype, device=dev) if noise is not None else None
+        self.has_noise = noise is not None
+        t = pg.st.tiles
+        if t is not None and "wptr" in t:
+            self._aw = torch.zeros(t["nnzw"] + 64, dtype=dtype, device=dev)
+        else:
+            self._aw = None
+        self.update(eps, kappa, coef, noise)
+
+    def update(self, eps, kappa, coef=None, noise=None):
+        """New bandwidth / lengthscale / scales: same memory, new contents."""
+        from . import graph
+        with torch.no_grad():
+            _, _, diag, a = self.pg.values(eps, self.self_loops, self.a.dtype)
+            self.diag.copy_(diag)
+            self.a.copy_(a)
+            kap = graph._device_scalar(kappa, self.a.dtype, self.a.device)
+            self.shift.copy_((2.0 * self.nu) / kap.square())
+            if self._aw is not None:
+                self.st.__dict__["_aw_persistent"] = None
+                self._aw.copy_(self.st.wi_values(self.a))
+                self.st._aw_persistent = self._aw
+            if self.coef is not None:
+                c = torch.ones(1, dtype=self.coef.dtype, device=self.coef.device) if coef is None else \
+                    graph._device_scalar(coef, self.coef.dtype, self.coef.device)
+                self.coef.copy_(c)
+                if self.ncoef is not None:
+                    self.ncoef.copy_(-graph._device_scalar(noise, self.coef.dtype, self.coef.device) * c)
+
+    def update_values(self, *a, **k):  # the replicated-values entry of the base class does not apply
+        raise RuntimeError("PartitionedPrecision: use update(eps, kappa, ...) -- values are built from this rank's rows")

@@ -442,6 +442,32 @@ class GraphStructure:
         self._tiles_tried = False
         self.build_tiles()   # now: it may reorder the entries inside rows, which must happen before any value build
 
+    @classmethod
+    def from_rows(cls, rowptr: torch.Tensor, col: torch.Tensor, n_rows: int, n_cols: int):
+        """Rank-local structure of a ROW PARTITION (distributed.PartitionedGraph): ``n_rows`` rows this rank owns, entries of
+        BOTH directions of every incident edge already present (``rowptr`` [n_rows + 1], ``col`` [nnz] in the rank's extended
+        numbering: own rows 0 .. n_rows - 1 first, halo rows n_rows .. n_cols - 1 after).  Vectors the SpMM reads have ``n_cols``
+        rows, vectors it writes ``n_rows``.  ``eid`` is the identity: per-entry values are passed where the square structure
+        takes per-edge values (``d2csr`` gathers through ``eid``, so the in-row reordering of ``build_tiles`` is followed)."""
+        if not col.is_cuda:
+            raise RuntimeError("GraphStructure.from_rows: arrays must be CUDA tensors (no CPU fallback exists)")
+        st = object.__new__(cls)
+        st.perm = st.inv = st.perm32 = st.morton_pos = None
+        st.n, st.n_cols = int(n_rows), int(n_cols)
+        st.nnz = int(col.numel())
+        st.m = st.nnz
+        st.device = col.device
+        st.rowptr = rowptr.to(torch.int32).contiguous()
+        st.col = col.to(torch.int32).contiguous()
+        st.eid = torch.arange(st.nnz, dtype=torch.int32, device=st.device)
+        st._d2 = {}
+        st._dot_ws = None
+        st._upper_pos = None
+        st.tiles = None
+        st._tiles_tried = False
+        st.build_tiles()
+        return st
+
     # -- tile-compacted structure for the v2 SpMM kernel (csrc/lap_spmm_tiled.cu) ----------------------------------------
     TILE_ROWS = 128
     TILED_SMEM_LIMIT = 200 * 1024
@@ -535,6 +561,8 @@ class GraphStructure:
         return self._value_layout(a, "pad")
 
     def wi_values(self, a: torch.Tensor) -> torch.Tensor:
+        if self.__dict__.get("_aw_persistent") is not None:
+            return self._aw_persistent     # the owner keeps ONE buffer alive across bandwidths (captured CUDA graphs point at it)
         return self._value_layout(a, "wi")
 
     def pair_tiles(self):

@@ -135,3 +135,71 @@ def test_row_partition_alignment():
         own = p.owner(ids)
         for i, o in zip(ids.tolist(), own.tolist()):
             assert p.bounds[o] <= i < p.bounds[o + 1]
+
+
+def _worker_symm(rank, world, port, results):
+    """partitioned_symmetrize over gloo: every rank's rows of the symmetrised, mean-coalesced graph equal the oracle's
+    restatement of nearest_neighbors.py:39-55 on the whole point cloud -- both directions of every edge, diagonal entries
+    twice -- and the partitioned three-pass value build with its two halo gathers (restated with torch ops here; the CUDA
+    passes are mgp_lap_values_pass) equals the oracle's values on those rows."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from manifold_gp_b200.distributed import HaloPlan, RowPartition, partitioned_symmetrize
+        n, k = 900, 7
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(n, 3, generator=g)
+        x[17] = x[3]; x[400] = x[3]; x[401] = x[3]                  # duplicate points: ties and self matches off column 0
+        d2, nbr = oracle.knn_search(x, x, k)
+        ref_idx, ref_val = oracle.symmetrize_coalesce(d2, nbr, n, drop_first=True)
+        # the reference's rows (both directions; a diagonal COO entry twice)
+        rr = torch.cat([ref_idx[0], ref_idx[1]]); rc = torch.cat([ref_idx[1], ref_idx[0]]); rv = torch.cat([ref_val, ref_val])
+        o = torch.argsort(rr * n + rc, stable=True); rr, rc, rv = rr[o], rc[o], rv[o]
+        part = RowPartition(n, world, align=128)
+        lo, hi = part.range(rank)
+        rows = torch.arange(lo, hi).repeat_interleave(k - 1)
+        cols = nbr[lo:hi, 1:].reshape(-1).to(torch.int64)
+        vals = d2[lo:hi, 1:].reshape(-1)
+        row, col, val = partitioned_symmetrize(rows, cols, vals, part, rank)
+        sel = (rr >= lo) & (rr < hi)
+        assert torch.equal(row, rr[sel]) and torch.equal(col, rc[sel])
+        assert torch.allclose(val, rv[sel], rtol=1e-6, atol=0)
+        assert int((row == col).sum()) == int((rr[sel] == rc[sel]).sum())
+        # ---- value build on my rows with two halo gathers ---------------------------------------------------------------
+        plan = HaloPlan(part, rank, col)
+        n_loc, H = hi - lo, plan.halo_ids.numel()
+        lc = plan.to_local(col); lr = row - lo
+        eps = 0.6
+        W = torch.exp(val.double() / (-4 * eps * eps))
+        dt = torch.zeros(n_loc + H, 1, dtype=torch.float64)
+        dt[:n_loc, 0] = 1.0
+        dt[:n_loc, 0].index_add_(0, lr, W)
+        plan.exchange(dt)                                            # gather 1: unnormalised degrees of the halo rows
+        at = W / (dt[lr, 0] * dt[lc, 0])
+        dg = torch.zeros(n_loc + H, 1, dtype=torch.float64)
+        dg[:n_loc, 0] = 1.0 / dt[:n_loc, 0] ** 2
+        dg[:n_loc, 0].index_add_(0, lr, at)
+        plan.exchange(dg)                                            # gather 2: normalised degrees of the halo rows
+        a = at / (dg[lr, 0].sqrt() * dg[lc, 0].sqrt()) / eps ** 2
+        lap = oracle.LaplacianOracle(ref_val.double(), ref_idx, n, eps, "symmetric", True)
+        assert torch.allclose(dt[:n_loc, 0], lap.degree_unnorm_mat[lo:hi], rtol=1e-12)
+        assert torch.allclose(dg[:n_loc, 0], lap.degree_mat[lo:hi], rtol=1e-12)
+        # my rows of L X against the oracle (diagonal entries twice, as in the reference's two scatter passes)
+        X = torch.randn(n, 2, generator=torch.Generator().manual_seed(6), dtype=torch.float64)
+        xe = torch.zeros(n_loc + H, 2, dtype=torch.float64); xe[:n_loc] = X[lo:hi]
+        plan.exchange(xe)
+        y = lap.laplacian_diag[lo:hi].unsqueeze(1) * xe[:n_loc]
+        y.index_add_(0, lr, -(a.unsqueeze(1) * xe[lc]))
+        assert torch.allclose(y, lap.matmul(X)[lo:hi], rtol=1e-10, atol=1e-10)
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_symmetrize_and_value_build_gloo():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_symm, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}

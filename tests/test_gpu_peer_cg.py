@@ -196,3 +196,47 @@ def test_partitioned_solve_with_the_true_residual_correction(pg1):
     assert rel_err(gst.to_external(x1), ref) < 1e-4
     # apply(): the partitioned operator outside the iteration equals the single-GPU matvec
     assert rel_err(gst.to_external(cg.apply(b_loc)), prec._matmul(B)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_partitioned_graph_construction_matches_the_replicated_operators(pg1, dtype):
+    """distributed.PartitionedGraph / PartitionedPrecision (a rank searches, symmetrises, builds structure and values for ITS rows
+    only; here the group has one rank, so "its rows" are all rows and every exchange is the degenerate case -- the 2-rank
+    protocol is covered by tests/test_distributed_cpu.py over gloo and by profiles/dist_check_partitioned.py on 2 GPUs):
+    degrees, diagonal, the matvec and the CG solve against the replicated operators built by NearestNeighbors.graph."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import distributed as D, solvers
+    n, k, nu, kappa, c = 30000, 12, 2, 0.7, 16
+    x = oracle.datasets.torus(n, seed=4).to(DEV)
+    x[100] = x[7]; x[101] = x[7]                                   # duplicate points (self match off column 0)
+    pg = D.PartitionedGraph(x, k)
+    idx, val = mgp.NearestNeighbors(x).graph(k)
+    eps = float(pg.kth_dist2.sqrt().median())
+    lap = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, torch.tensor([[eps]], dtype=dtype, device=DEV), "symmetric", True)
+    prec = mgp.PrecisionMaternOperator(lap, nu, torch.tensor([[kappa]], dtype=dtype, device=DEV))
+    assert pg.st.nnz == lap.structure.nnz and pg.n_loc == n and pg.n_ext == n
+    tol = 1e-10 if dtype == torch.float64 else 1e-5
+    dt, dg, diag, a = pg.values(eps, True, dtype)
+    assert rel_err(pg.gather(dt[:n].unsqueeze(1)).squeeze(1), lap.degree_unnorm_mat) < tol
+    assert rel_err(pg.gather(dg[:n].unsqueeze(1)).squeeze(1), lap.degree_mat) < tol
+    assert rel_err(pg.gather(diag.unsqueeze(1)).squeeze(1), lap.laplacian_diag) < tol
+    op = D.PartitionedPrecision(pg, eps, nu, kappa, True, dtype)
+    B = torch.randn(n, c, dtype=dtype, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    cg_tol = 1e-6 if dtype == torch.float64 else 1e-5
+    cg = D.PeerCG(op, c, dtype, tolerance=cg_tol, max_iter=3000)
+    b_loc = pg.to_local(B).contiguous()
+    assert rel_err(pg.gather(cg.apply(b_loc)), prec._matmul(B)) < tol
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref, rinfo = solvers.linear_cg(prec, B, tolerance=cg_tol, max_iter=3000, return_info=True)
+        xs, info = cg.solve(b_loc)
+    assert info["converged"]
+    assert abs(info["iterations"] - rinfo["iterations"]) <= max(3, rinfo["iterations"] // 50)
+    assert rel_err(pg.gather(xs), ref) < (1e-6 if dtype == torch.float64 else 2e-3)
+    # a new bandwidth re-runs the partitioned value build into the same buffers
+    ptr_a, ptr_aw = op.a.data_ptr(), op._aw.data_ptr()
+    op.update(1.3 * eps, kappa)
+    lap2 = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, torch.tensor([[1.3 * eps]], dtype=dtype, device=DEV), "symmetric", True)
+    prec2 = mgp.PrecisionMaternOperator(lap2, nu, torch.tensor([[kappa]], dtype=dtype, device=DEV))
+    assert op.a.data_ptr() == ptr_a and op._aw.data_ptr() == ptr_aw
+    assert rel_err(pg.gather(cg.apply(b_loc)), prec2._matmul(B)) < tol
