@@ -909,35 +909,56 @@ def bench_main(args, CFG, clock_sampler=None):
     warnings.simplefilter("ignore")
     n, k, c = args.n, CFG["k"], CFG["rhs"]
     x = synthetic.torus(n, seed=CFG["seed"], device=dev)
-    # ---- graph: queries sharded, everything after replicated ------------------------------------------------------------
-    qpart = RowPartition(n, world, align=64)
-    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-    d2, nbr, knn = sharded_knn(x, k, qpart, rank)
-    torch.cuda.synchronize(); dist.barrier(); t_knn = time.perf_counter() - t0
-    eps = float(d2[:, k - 1].sqrt().median())
-    # symmetrise on every rank (deterministic, identical results)
-    from ._lib import c_int32, c_int64, c_size_t, ptr, stream
-    cap = n * (k - 1)
-    eidx = torch.empty((2, cap), dtype=torch.int64, device=dev)
-    ev = torch.empty(cap, dtype=torch.float32, device=dev)
-    m_out = torch.zeros(1, dtype=torch.int64, device=dev)
-    wsb = _lib.workspace(_lib.query("mgp_graph_symmetrize_ws_bytes", c_int64(n), c_int32(k)), dev)
-    _lib.call("mgp_graph_symmetrize_f32", ptr(d2.contiguous()), ptr(nbr.contiguous()), c_int64(n), c_int32(k), c_int32(1),
-              ptr(eidx), ptr(ev), c_int64(cap), ptr(m_out), ptr(wsb), c_size_t(wsb.numel()), stream())
-    m = int(m_out.item())
-    idx, val = eidx[:, :m].contiguous(), ev[:m].contiguous()
-    del eidx, ev, wsb
-    graph.attach_permutation(idx, graph.morton_permutation(x))
-    lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[eps]], device=dev), CFG["normalization"], CFG["self_loops"])
-    prec = mgp.PrecisionMaternOperator(lap, CFG["nu"], torch.tensor([[CFG["kappa"]]], device=dev))
-    gst = lap.structure
-    _, _, diag, a = lap._values()
-    part = RowPartition(n, world, align=gst.TILE_ROWS)
-    op = DistPrecision(gst, diag, a, prec._shift(), CFG["nu"], part, rank)
-    lo, hi = part.range(rank)
-    g = torch.Generator(device=dev).manual_seed(CFG["rhs_seed"])
-    B = torch.randn(n, c, device=dev, generator=g)           # identical on every rank (same seed)
-    b_loc = gst.to_internal(B)[lo:hi].contiguous()
+    # ---- graph ----------------------------------------------------------------------------------------------------------
+    # "partitioned" (default): a rank searches, symmetrises and builds structure + values for ITS rows only (PartitionedGraph);
+    # "replicated": the round-1 form -- queries sharded, symmetrise / structure / values on every rank for the whole graph.
+    build = os.environ.get("MGP_DIST_BUILD", "partitioned")
+    pg = None
+    if build == "partitioned":
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        pg = PartitionedGraph(x, k)
+        torch.cuda.synchronize(); dist.barrier(); t_knn = time.perf_counter() - t0
+        eps = float(pg.gather(pg.kth_dist2.unsqueeze(1)).squeeze(1).sqrt().median())
+        op = PartitionedPrecision(pg, eps, CFG["nu"], CFG["kappa"], CFG["self_loops"])
+        part = pg.part
+        lo, hi = part.range(rank)
+        nnz_t = torch.tensor([pg.st.nnz], dtype=torch.int64, device=dev)
+        dist.all_reduce(nnz_t)
+        m = int(nnz_t.item()) // 2
+        g = torch.Generator(device=dev).manual_seed(CFG["rhs_seed"])
+        B = torch.randn(n, c, device=dev, generator=g)           # identical on every rank (same seed)
+        b_loc = pg.to_local(B).contiguous()
+    else:
+        # ---- graph: queries sharded, everything after replicated ------------------------------------------------------------
+        qpart = RowPartition(n, world, align=64)
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        d2, nbr, knn = sharded_knn(x, k, qpart, rank)
+        torch.cuda.synchronize(); dist.barrier(); t_knn = time.perf_counter() - t0
+        eps = float(d2[:, k - 1].sqrt().median())
+        # symmetrise on every rank (deterministic, identical results)
+        from ._lib import c_int32, c_int64, c_size_t, ptr, stream
+        cap = n * (k - 1)
+        eidx = torch.empty((2, cap), dtype=torch.int64, device=dev)
+        ev = torch.empty(cap, dtype=torch.float32, device=dev)
+        m_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        wsb = _lib.workspace(_lib.query("mgp_graph_symmetrize_ws_bytes", c_int64(n), c_int32(k)), dev)
+        _lib.call("mgp_graph_symmetrize_f32", ptr(d2.contiguous()), ptr(nbr.contiguous()), c_int64(n), c_int32(k), c_int32(1),
+                  ptr(eidx), ptr(ev), c_int64(cap), ptr(m_out), ptr(wsb), c_size_t(wsb.numel()), stream())
+        m = int(m_out.item())
+        idx, val = eidx[:, :m].contiguous(), ev[:m].contiguous()
+        del eidx, ev, wsb
+        graph.attach_permutation(idx, graph.morton_permutation(x))
+        lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[eps]], device=dev), CFG["normalization"], CFG["self_loops"])
+        prec = mgp.PrecisionMaternOperator(lap, CFG["nu"], torch.tensor([[CFG["kappa"]]], device=dev))
+        gst = lap.structure
+        _, _, diag, a = lap._values()
+        part = RowPartition(n, world, align=gst.TILE_ROWS)
+        op = DistPrecision(gst, diag, a, prec._shift(), CFG["nu"], part, rank)
+        lo, hi = part.range(rank)
+        g = torch.Generator(device=dev).manual_seed(CFG["rhs_seed"])
+        B = torch.randn(n, c, device=dev, generator=g)           # identical on every rank (same seed)
+        b_loc = gst.to_internal(B)[lo:hi].contiguous()
+
 
     transport = os.environ.get("MGP_DIST_TRANSPORT", "peer")
     if transport == "peer":
@@ -978,10 +999,22 @@ def bench_main(args, CFG, clock_sampler=None):
     launches = _lib.launch_count()
     # check against the global residual and against the SINGLE-GPU solve of the same system (every rank holds the replicated
     # operator; rank 0 runs solvers.linear_cg on it after the timed region)
-    x_all = [torch.empty((part.range(r)[1] - part.range(r)[0], c), device=dev) for r in range(world)]
-    dist.all_gather(x_all, xs.contiguous())
-    sol = gst.to_external(torch.cat(x_all))
-    true_rel = float(((prec.matmul(sol) - B).double().norm(dim=0) / B.double().norm(dim=0)).mean())
+    if pg is not None:
+        sol = pg.gather(xs)
+        res = b_loc - cg.apply(xs)                               # true residual from the partitioned operator itself
+        sums = torch.stack((res.double().square().sum(0), b_loc.double().square().sum(0)))
+        dist.all_reduce(sums)
+        true_rel = float((sums[0] / sums[1]).sqrt().mean())
+        prec = None
+        if rank == 0:                                            # the replicated operator exists on rank 0 only, for the check below
+            idx, val = mgp.NearestNeighbors(x).graph(k)
+            lap = mgp.GraphLaplacianOperator(val, idx, n, torch.tensor([[eps]], device=dev), CFG["normalization"], CFG["self_loops"])
+            prec = mgp.PrecisionMaternOperator(lap, CFG["nu"], torch.tensor([[CFG["kappa"]]], device=dev))
+    else:
+        x_all = [torch.empty((part.range(r)[1] - part.range(r)[0], c), device=dev) for r in range(world)]
+        dist.all_gather(x_all, xs.contiguous())
+        sol = gst.to_external(torch.cat(x_all))
+        true_rel = float(((prec.matmul(sol) - B).double().norm(dim=0) / B.double().norm(dim=0)).mean())
     vs_single = None
     if rank == 0:
         from . import settings, solvers
@@ -1013,6 +1046,10 @@ def bench_main(args, CFG, clock_sampler=None):
                "config": {"workload": CFG["workload"], "n": n, "k": k, "edges_M": m, "nnz": 2 * m, "nu": CFG["nu"], "kappa": CFG["kappa"],
                           "eps": round(eps, 6), "rhs": c, "tol": CFG["tol"], "normalization": CFG["normalization"],
                           "self_loops": CFG["self_loops"], "partition": "contiguous row blocks of the Morton order",
+                          "graph_build": ("partitioned: every rank searches, symmetrises (one all_to_all_v) and builds structure + values "
+                                          "(two halo gathers) for its rows only" if pg is not None else
+                                          "replicated: queries sharded, symmetrise / structure / values on every rank"),
+                          "entries_rank0": int(op.st.nnz if pg is not None else 0) or None,
                           "halo_rows_rank0": int(op.plan.halo_ids.numel()), "rows_rank0": int(op.n_loc),
                           "l2": "inputs larger than L2 at 1-2 GPUs; at 8 GPUs a rank's share (~50 MB) is L2 resident (strong scaling)"},
                "cg_iterations": int(info["iterations"]), "cg_polish_iterations": int(polish.get("iterations", 0)),
@@ -1109,8 +1146,9 @@ class PartitionedGraph:
         rows = torch.arange(lo, hi, device=x.device, dtype=torch.int64).repeat_interleave(k - 1)
         cols = self.inv[nbr[:, 1:].reshape(-1).to(torch.int64)]
         row, col, val = partitioned_symmetrize(rows, cols, d2[:, 1:].reshape(-1), self.part, self.rank, group)
-        self.plan = HaloPlan(self.part, self.rank, col, group=group)
         n_loc = hi - lo
+        row, col, val = self._sort_rows_inside_tiles(row, col, val, n_loc)
+        self.plan = HaloPlan(self.part, self.rank, col, group=group)
         rowptr = torch.searchsorted(row, torch.arange(lo, hi + 1, device=x.device, dtype=torch.int64))
         self.st = graph.GraphStructure.from_rows(rowptr, self.plan.to_local(col), n_loc, n_loc + int(self.plan.halo_ids.numel()))
         self.entry_d2 = val.contiguous()                             # per entry, in the order the structure's ``eid`` indexes
@@ -1126,6 +1164,40 @@ class PartitionedGraph:
             own = self.part.owner(gid).clamp_(max=self.world - 1)
             starts = torch.tensor(self.part.bounds[:-1], dtype=torch.int64, device=x.device)
             t["hcol_peer"] = ((own << 26) | (gid - starts[own])).to(torch.int32).contiguous()
+
+    def _sort_rows_inside_tiles(self, row, col, val, n_loc):
+        """Inside every 128-row tile, order the rows by their number of entries (descending) -- what GraphStructure does for the
+        replicated structure: the 8 row slots of a warp block walk in lock-step, so they want rows of equal length (measured on
+        2 GPUs at cfg-C: 360 ms without against 343 ms for the replicated build).  The renumbering is local to a rank's block, but
+        the other ranks name these rows as halo columns: one halo gather of the new ids translates them, and the row order of
+        the whole partition (``perm``) is re-assembled with one all-gather."""
+        from . import graph
+        R = graph.GraphStructure.TILE_ROWS
+        lo, dev = self.lo, row.device
+        deg = torch.bincount(row - lo, minlength=n_loc)
+        ar = torch.arange(n_loc, device=dev, dtype=torch.int64)
+        key = ((ar // R) << 20) | ((1 << 20) - 1 - deg.clamp_max((1 << 20) - 1))
+        order = torch.argsort(key, stable=True)                      # new local position -> old local row
+        newpos = torch.empty_like(order)
+        newpos[order] = ar
+        plan0 = HaloPlan(self.part, self.rank, col, group=self.group)
+        ids = torch.zeros((n_loc + int(plan0.halo_ids.numel()), 1), dtype=torch.int64, device=dev)
+        ids[:n_loc, 0] = lo + newpos
+        plan0.exchange(ids)                                          # new global ids of the halo rows, from their owners
+        col = ids[plan0.to_local(col), 0]
+        row = lo + newpos[row - lo]
+        o = torch.argsort(row * self.part.n + col, stable=True)
+        block = self.perm[lo:self.hi][order].contiguous()            # my block of the refined row order
+        if self.world > 1:
+            sizes = [self.part.range(r)[1] - self.part.range(r)[0] for r in range(self.world)]
+            parts = [torch.empty(sz, dtype=block.dtype, device=dev) for sz in sizes]
+            dist.all_gather(parts, block, group=self.group)
+            self.perm = torch.cat(parts)
+        else:
+            self.perm = block
+        self.inv = torch.empty_like(self.perm)
+        self.inv[self.perm] = torch.arange(self.n, device=dev)
+        return row[o], col[o], val[o]
 
     def values(self, eps, self_loops: bool = True, dtype=torch.float32):
         """(deg_unnorm [n_ext], deg [n_ext], diag [n_loc], a [nnz_loc]) for bandwidth ``eps`` -- graph_laplacian_operator.py:52-106
