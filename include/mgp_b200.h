@@ -281,9 +281,6 @@ typedef struct mgp_wi_ext {
                                  walks the union list of two spatially adjacent rows, aw holds two values per entry (mgp_lap_pair_values),
                                  pair_rows[128 tile + 2 pair + half] is the tile-local row that position outputs */
 } mgp_wi_ext;
-/* Development aid (MGP_WI_TRACE=1): clock64() of block 0's producer / consumer events per tile of the last mgp_lap_spmm_wi* launch,
- * [64 tiles][16 events] (profiles/trace_spmm.py).  MGP_EUNSUPPORTED when tracing was off. */
-int mgp_wi_trace_dump(uint64_t* host);
 /* out[i] = src[i] >= 0 ? a[src[i]] : 0 -- the value stream of the paired layout (two sources per stream entry), once per bandwidth. */
 int mgp_lap_pair_values_f32(const int32_t* src, const float* a, int64_t count, float* out, void* stream);
 int mgp_lap_pair_values_f64(const int32_t* src, const double* a, int64_t count, double* out, void* stream);

@@ -104,7 +104,6 @@ _SIG = {
     "mgp_lanczos_reorth_f64": (c_int32, [P, c_int64, c_int32, P, c_int64, P, P, P, P]),
     "mgp_lap_values_pass_f32": (c_int32, [c_int32, P, P, P, c_int64, P, c_int32, P, P, P, P, P]),
     "mgp_lap_values_pass_f64": (c_int32, [c_int32, P, P, P, c_int64, P, c_int32, P, P, P, P, P]),
-    "mgp_wi_trace_dump": (c_int32, [P]),
     "mgp_lap_pair_values_f32": (c_int32, [P, P, c_int64, P, P]),
     "mgp_lap_pair_values_f64": (c_int32, [P, P, c_int64, P, P]),
     "mgp_lanczos_axpy_f32": (c_int32, [P, c_int64, c_int32, P, c_int64, P, P, P, P]),

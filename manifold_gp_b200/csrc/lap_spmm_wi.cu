@@ -96,7 +96,6 @@ struct WiArgs {
   int last_pass;                       // 1 on the launch of the last column pass
   const T* ep_coef;                    // optional epilogue: Y <- coef * Y (+ ADD) with coef = *ep_coef; the dot epilogue sees the scaled Y
   int ep_add;                          // 1: ADD = dot_with (rows like X; no dot product on such a launch) -- y = add + coef * (A' x)
-  unsigned long long* trace;   // experiments only (MGP_WI_TRACE=1): block 0 records clock64() per tile and event, [tile][16]
   int debug;     // timing experiments only (MGP_WI_DEBUG bit mask): 1 = consumers skip the row walk, 2 = producers skip the halo rows
                  // (same-process A/B on B200, cfg-C: 150 us full, 104 without halo copies, 90 without the walk, 62 with neither)
 };
@@ -325,16 +324,13 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         const int nrows = (int)min((int64_t)R, g.n - row0);
         int* const sm = slot_meta + s * kWiSlotMeta;
         mbar_wait(&desc_bar[s], (uint32_t)(i / kWiSlots) & 1u);
-        if (g.trace && blockIdx.x == 0 && lane == 0 && i < 64) g.trace[i * 16 + 0] = clock64();
         const int cnt = sm[16], need = sm[21];
         const uint32_t off = (uint32_t)sm[17], xbytes = (uint32_t)sm[18], cbytes0 = (uint32_t)sm[19];
         const int base = sm[20];
         // the region may be written once every older tile whose region it overlaps -- and the previous user of the slot --
         // has been released by all 16 consumer warps.  Tiles are released in order: the waits are a prefix of those in flight.
         for (; tail <= need; ++tail) mbar_wait(&empty_bar[tail & (kWiSlots - 1)], (uint32_t)(tail / kWiSlots) & 1u);
-        if (g.trace && blockIdx.x == 0 && lane == 0 && i < 64) g.trace[i * 16 + 1] = clock64();
         mbar_wait(&ids_bar[i % kWiIdSlots], (uint32_t)((i / kWiIdSlots) & 1));
-        if (g.trace && blockIdx.x == 0 && lane == 0 && i < 64) g.trace[i * 16 + 2] = clock64();
         unsigned char* const xs = smem_raw + off;
         unsigned char* const vs = xs + xbytes;
         unsigned char* const cs = xs + cbytes0;
@@ -360,7 +356,6 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
           if (own_contig) bulk_g2s(xs, g.x + row0 * g.ldx + g.c0, (uint32_t)nrows * ROW_BYTES, &full_bar[s]);
           if (dbytes) bulk_g2s(dgs, g.diag + row0, dbytes, &full_bar[s]);
           if constexpr (PAIR) bulk_g2s(dgs + (size_t)R * sizeof(T), g.qrow + row0, (uint32_t)R, &full_bar[s]);
-          if (g.trace && blockIdx.x == 0 && i < 64) g.trace[i * 16 + 3] = clock64();
         }
         __syncwarp();
       }
@@ -379,7 +374,6 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         const int nown = own_contig ? 0 : (int)min((int64_t)R, g.n - row0);
         const int* ids = ids_ring + (size_t)(i % kWiIdSlots) * g.hmax;
         asm volatile("barrier.sync %0, %1;" ::"r"(1 + s), "n"((PW - 1) * 32) : "memory");
-        if (g.trace && blockIdx.x == 0 && tid == 64 && i < 64) g.trace[i * 16 + 4] = clock64();
         unsigned char* const xs = smem_raw + (uint32_t)sm[17];
         const int nh = (sm[18] >> 6) - R;
         const int nscat = (g.debug & 2) ? 0 : nown + nh;
@@ -421,7 +415,6 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         }
         cp_async_arrive_noinc(&full_bar[s]);                          // arrives once this thread's copies have landed
         mbar_arrive(&issued_bar[i % kWiIdSlots]);                     // this thread is done with the tile's id list
-        if (g.trace && blockIdx.x == 0 && tid == 64 && i < 64) g.trace[i * 16 + 5] = clock64();
       }
     }
   } else {
@@ -436,17 +429,10 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
     const uint32_t o2 = (uint32_t)(((2 + l) & 3) * 16), o3 = (uint32_t)(((3 + l) & 3) * 16);
     // Fixed warp <-> block map: warp w walks rows 8w .. 8w+7 of every tile.  (Handing the 16 blocks of a tile out
     // dynamically -- shared-memory ticket counter -- was measured in the same process: 150.3 vs 149.6 us, no gain.)
-    // Two groups of 8 consumer warps take ALTERNATE tiles (a warp walks blocks w and w + 8 of its tile): with all 16 warps on
-    // the same tile they are phase-locked -- everybody walks (shared-memory pipe saturated), then everybody reduces / stores
-    // (pipe idle): the per-tile trace of block 0 (profiles/trace_spmm.py) showed 3050 of 4100 cycles per tile in the walk and
-    // only 210 waiting for data.  Out of phase, one group's epilogue runs under the other group's walk.  (MGP_WI_DEBUG bit 4:
-    // the old map, for A/B.)
-    const int cwarp = warp - kWiProducerWarps;
-    const bool split = !(g.debug & 4);
-    for (unsigned int it = 0;; ++it) {
-      const int ti = split ? (cwarp >> 3) + 2 * (int)(it >> 1) : (int)it;
+    for (unsigned int tk = (unsigned int)(warp - kWiProducerWarps);; tk += 16) {
+      const int ti = (int)(tk >> 4);
       if (ti >= t1 - t0) break;
-      const int w = split ? (cwarp & 7) + 8 * (int)(it & 1u) : cwarp;     // warp block of the tile: rows 8w .. 8w+7
+      const int w = (int)(tk & 15u);                 // warp block of the tile: rows 8w .. 8w+7
       const int tile = t0 + ti;
       const int64_t row0 = (int64_t)tile * R;
       int r = w * 8 + rpos;                          // row inside the tile (PAIR: position in the tile's row table, see below)
@@ -472,10 +458,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         po = (g.post && active) ? __ldg(g.post + row) : T(1);
       };
       if constexpr (!PAIR) issue_epilogue_loads();
-      const bool tr = g.trace && blockIdx.x == 0 && lane == 0 && ti < 64 && (w == 0 || w == 15);
-      if (tr) g.trace[ti * 16 + (w == 0 ? 6 : 10)] = clock64();
       mbar_wait(&full_bar[s], ph);                   // (sleep quanta of 32 / 96 / 320 ns between polls: no measurable difference)
-      if (tr) g.trace[ti * 16 + (w == 0 ? 7 : 11)] = clock64();
       const int ofs = rp[w];
       const int steps = (g.debug & 1) ? 0 : (rp[w + 1] - ofs) >> 5;
       unsigned char* const xs = smem_raw + (uint32_t)rp[17];
@@ -597,7 +580,6 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
           wv = wn;
         }
       }
-      if (tr) g.trace[ti * 16 + (w == 0 ? 8 : 12)] = clock64();
       // acc[c] of lane l holds chunk (c + l) mod 4 of the slot's partial sums; lane l ends up with chunk l complete:
       // its own acc[0] plus acc[4 - d] of the lane d places further (mod 4) in the slot, d = 1..3
       T res[VEC];
@@ -629,7 +611,6 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         }
       }
       __syncwarp();
-      if (tr) g.trace[ti * 16 + (w == 0 ? 9 : 13)] = clock64();
       if (lane == 0) mbar_arrive(&empty_bar[s]);      // this block of stage s is done (16 arrivals free the stage)
     }
   }
@@ -719,8 +700,6 @@ static int lap_wi_values(const int* rowptr, const int* wptr, const T* a, int64_t
   return MGP_OK;
 }
 
-static unsigned long long*& wi_trace_ptr() { static unsigned long long* p = nullptr; return p; }
-
 template <typename T>
 static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw, const T* diag, const int* hptr,
                        const int* hcol, int tile_rows, int lmax, int wnzmax, int hmax, const T* shift, const T* post, const int* xmap,
@@ -800,14 +779,6 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
   g.partials = dot_out ? reinterpret_cast<T*>(reinterpret_cast<char*>(dot_ws) + 256) : nullptr;
   g.dot_is_x = ((dot_out || g.ep_add) && dot_with == x) ? 1 : 0;
   { const char* dbg = getenv("MGP_WI_DEBUG"); g.debug = dbg ? atoi(dbg) : 0; }
-  g.trace = nullptr;
-  if (getenv("MGP_WI_TRACE")) {
-    static unsigned long long* trace_buf = nullptr;
-    if (!trace_buf) { MGP_CUDA(cudaMalloc(&trace_buf, 64 * 16 * 8)); }
-    MGP_CUDA(cudaMemsetAsync(trace_buf, 0, 64 * 16 * 8, st));
-    g.trace = trace_buf;
-    wi_trace_ptr() = trace_buf;
-  }
   // producer warps: measured on B200 (cfg-C, C = 16, fp32): 4 -> 163.7 us, 8 -> 144.0, 12 -> 133.4, 16 -> 127.0 (the halo
   // cp.async issue shares the LSU queue with the consumers' shared-memory loads; more producer warps = a larger share)
   static const int pw = [] {
@@ -849,13 +820,6 @@ int mgp_lap_wi_values_f32(const int32_t* rowptr, const int32_t* wptr, const floa
 }
 int mgp_lap_wi_values_f64(const int32_t* rowptr, const int32_t* wptr, const double* a, int64_t n, double* aw, void* stream) {
   return mgp::lap_wi_values<double>(rowptr, wptr, a, n, aw, (cudaStream_t)stream);
-}
-
-/* experiments only: copy the last launch's per-tile event clocks of block 0 ([64][16] uint64, see WiArgs::trace) to the host */
-int mgp_wi_trace_dump(uint64_t* host) {
-  if (!mgp::wi_trace_ptr()) return MGP_EUNSUPPORTED;
-  MGP_CUDA(cudaMemcpy(host, mgp::wi_trace_ptr(), 64 * 16 * 8, cudaMemcpyDeviceToHost));
-  return MGP_OK;
 }
 
 int mgp_lap_pair_values_f32(const int32_t* src, const float* a, int64_t count, float* out, void* stream) {

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Per-tile timeline of block 0 of lap_spmm_wi_kernel at cfg-C (MGP_WI_TRACE=1: clock64() stamps of the filler, one helper warp and
+"""NEEDS THE INSTRUMENTED KERNEL of the commit "Temporary: per-tile clock64 trace ..." (reverted right after: the stamps cost ~4 us per
+launch); kept with its output (r02_spmm_trace_block0_*.json) as the record of how the numbers were taken.
+Per-tile timeline of block 0 of lap_spmm_wi_kernel at cfg-C (MGP_WI_TRACE=1: clock64() stamps of the filler, one helper warp and
 two consumer warps per tile; development aid).   python profiles/trace_spmm.py wp|wi"""
 import ctypes, json, os, sys
 os.environ["MGP_WI_TRACE"] = "1"
