@@ -529,6 +529,8 @@ class PeerCG(DistCG):
         eps_ = op.stage_epilogues()
         nstage = len(eps_)
         src, src_ptrs = self.r, self.r_ptrs
+        # paired-row walk (fp32, whole 64-byte rows) when the operator keeps the paired value stream alive (PartitionedPrecision)
+        qrow = op.pair_rows() if (self.dt == torch.float32 and c % 16 == 0 and hasattr(op, "pair_rows")) else None
         for s in range(nstage):
             last = s == nstage - 1
             dst, dst_ptrs = (self.v, None) if last else self.tmps[s % len(self.tmps)]
@@ -538,10 +540,10 @@ class PeerCG(DistCG):
                                   publish_flags=None if last else self.flag_tabs[s + 1], ticket=self.tickets[8 * s:],
                                   red_ptrs=self.red2_ptrs if last else None, red_flags=self.flag_tabs[nstage] if last else None,
                                   ship_extra=self.gamma_loc if last else None, ship_ncols=c if last else 0,
-                                  ep_coef=ep_coef, ep_add=ep_add)
+                                  ep_coef=ep_coef, ep_add=ep_add, pair_rows=qrow)
             else:                        # default: "source complete" published by block 0 of the CONSUMING launch at its start
                 ext = _lib.wi_ext(done_flag=self.done_scalar, wait_flags=self.flag_tabs[s], publish_at_start=True,
-                                  ep_coef=ep_coef, ep_add=ep_add)
+                                  ep_coef=ep_coef, ep_add=ep_add, pair_rows=qrow)
             graph.lap_spmm(op.st, op.a, op.diag, src[:n_loc, :c], shift=op.shift, out=dst[:n_loc, :c],
                            dot_with=self.r[:n_loc, :c] if (last or ep_add) else None, dot_out=self.rbuf_pap if last else None,
                            peer_x=src_ptrs, peer_ext=(self.rank, self.iter_scalar, ext))
@@ -1152,8 +1154,6 @@ class PartitionedGraph:
         rowptr = torch.searchsorted(row, torch.arange(lo, hi + 1, device=x.device, dtype=torch.int64))
         self.st = graph.GraphStructure.from_rows(rowptr, self.plan.to_local(col), n_loc, n_loc + int(self.plan.halo_ids.numel()))
         self.entry_d2 = val.contiguous()                             # per entry, in the order the structure's ``eid`` indexes
-        self.st._pair_tried = True          # the partitioned solvers keep ONE value-stream buffer alive across bandwidths (captured
-                                            # graphs): that hook exists for the single-row streams only, so no paired walk here
         self.n_loc, self.n_ext = n_loc, self.st.n_cols
         t = self.st.tiles
         if t is not None and "hcol" in t:
@@ -1260,7 +1260,19 @@ class PartitionedPrecision(DistPrecision):
             self._aw = torch.zeros(t["nnzw"] + 64, dtype=dtype, device=dev)
         else:
             self._aw = None
+        # paired-row streams (fp32): the value stream lives in ONE buffer across bandwidths, like the single-row one
+        self._aq = None
+        if self._aw is not None and dtype == torch.float32 and os.environ.get("MGP_DIST_PAIR", "1") != "0":
+            tq = pg.st.pair_tiles()
+            if tq is not None:
+                self._aq = torch.zeros(tq["qsrc"].numel(), dtype=dtype, device=dev)
+        if self._aq is None:
+            pg.st._pair_tried = True        # no paired walk on this structure (auto dispatch of the NCCL-transport matvec included)
         self.update(eps, kappa, coef, noise)
+
+    def pair_rows(self):
+        """Row table of the paired-row streams when this operator keeps their value stream alive, else None."""
+        return self.st.tiles["qrow"] if self._aq is not None else None
 
     def update(self, eps, kappa, coef=None, noise=None):
         """New bandwidth / lengthscale / scales: same memory, new contents."""
@@ -1275,6 +1287,10 @@ class PartitionedPrecision(DistPrecision):
                 self.st.__dict__["_aw_persistent"] = None
                 self._aw.copy_(self.st.wi_values(self.a))
                 self.st._aw_persistent = self._aw
+            if self._aq is not None:
+                self.st.__dict__["_aq_persistent"] = None
+                self._aq.copy_(self.st.pair_values(self.a))
+                self.st._aq_persistent = self._aq
             if self.coef is not None:
                 c = torch.ones(1, dtype=self.coef.dtype, device=self.coef.device) if coef is None else \
                     graph._device_scalar(coef, self.coef.dtype, self.coef.device)

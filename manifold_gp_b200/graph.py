@@ -580,6 +580,8 @@ class GraphStructure:
         return t if "qptr" in t else None
 
     def pair_values(self, a: torch.Tensor) -> torch.Tensor:
+        if self.__dict__.get("_aq_persistent") is not None:
+            return self._aq_persistent     # see wi_values
         return self._value_layout(a, "pair")
 
     def tiled_ok(self, dtype, cw: int) -> bool:
@@ -745,8 +747,13 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
             raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
         if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi", "wp") or peer_x is not None):
             # paired-row walk (v6): fp32, whole 64-byte rows of right-hand sides, single GPU
-            pair = (SPMM_KERNEL in ("auto", "wp") and PAIR_WALK and dt == torch.float32 and c % 16 == 0 and peer_x is None
-                    and peer_ext is None and hasattr(st, "pair_tiles") and st.pair_tiles() is not None)
+            # (with peer memory: only when the caller's hook block names the row table, i.e. keeps the paired value stream alive)
+            ext_pair = peer_ext is not None and bool(peer_ext[2].pair_rows)
+            pair = (SPMM_KERNEL in ("auto", "wp") and PAIR_WALK and dt == torch.float32 and c % 16 == 0
+                    and ((peer_x is None and peer_ext is None) or ext_pair)
+                    and hasattr(st, "pair_tiles") and st.pair_tiles() is not None)
+            if ext_pair and not pair:
+                raise RuntimeError("lap_spmm: the hook block asks for the paired-row walk but this call does not qualify")
             if SPMM_KERNEL == "wp" and not pair:
                 raise RuntimeError("lap_spmm: paired-row kernel requested but this call does not qualify (fp32, multiples of 16 "
                                    "columns, no peer memory)")
