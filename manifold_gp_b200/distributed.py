@@ -9,11 +9,13 @@ over NVLink/NVSwitch; gloo in the CPU tests) for the plumbing:
   buffer is the halo region of the local vector, ordered by owner so each peer's rows land contiguously);
 * every CG inner product is an all-reduce of ``C`` floats (p^T A p comes out of the SpMM epilogue, r^T r out of the fused
   update kernel; ``mgp_cg_dist_scalars`` finishes alpha/beta/flags on every rank identically);
-* graph construction is replicated in round 1 (kNN queries are sharded and all-gathered; the O(nnz) structure / value
-  builds run on every rank): only the solve is partitioned.
-
-The local operator is a *view* of the global tile-compacted structure (no index rebasing: row pointers keep global
-positions so the TMA copies stay 16-byte aligned) with the halo column ids translated to local vector rows.
+* graph construction: ``PartitionedGraph`` / ``PartitionedPrecision`` (end of this file) search, symmetrise and build structure
+  and values per rank -- no rank holds the whole edge list (symmetrise = one all_to_all_v of triples, value build = three local
+  passes with two halo gathers); ``bench.py --gpus N`` runs on them.  The round-1 form is kept for ``DistBackend`` (the
+  reference's UNCHANGED training loop builds its operators on every rank by construction): kNN queries sharded and
+  all-gathered, the O(nnz) structure / value builds replicated, the local operator a *view* of the global tile-compacted
+  structure (``LocalStructure``: no index rebasing, row pointers keep global positions so the TMA copies stay 16-byte aligned)
+  with the halo column ids translated to local vector rows.
 """
 from __future__ import annotations
 

@@ -213,6 +213,8 @@ def pair_matching(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 1
     ar = torch.arange(R, device=dev, dtype=torch.int64)
     tb = torch.minimum(ar[:, None], ar[None, :]) * R + torch.maximum(ar[:, None], ar[None, :])      # strict order on unordered pairs
     pos = torch.empty(ntiles * R, dtype=torch.int64, device=dev)
+    # bound the dense 0/1 pattern of a chunk (T x R x L) to ~1 GiB: graphs without locality have wide tiles
+    chunk_tiles = max(1, min(int(chunk_tiles), (1 << 30) // (R * L * (2 if wdt == torch.float16 else 4))))
     for c0 in range(0, ntiles, chunk_tiles):
         c1 = min(ntiles, c0 + chunk_tiles)
         T = c1 - c0
@@ -573,6 +575,8 @@ class GraphStructure:
             return None
         if "qptr" not in t and not self.__dict__.get("_pair_tried"):
             self._pair_tried = True
+            if (self.TILE_ROWS + t["hmax"]) * 64 + t["wnzmax"] * 6 > 200 * 1024:
+                return None                  # a tile this wide does not fit the kernel's ring in either layout: do not build the streams
             lc = t["lcol"][:self.nnz]
             q = pair_streams(self.rowptr, lc, self.n, pair_matching(self.rowptr, lc, self.n, self.TILE_ROWS), self.TILE_ROWS)
             if q is not None:
