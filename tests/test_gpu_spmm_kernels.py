@@ -243,3 +243,32 @@ def test_paired_walk_on_ragged_graphs_and_epilogues(problem):
                 assert (dot.double() - (Z.double() * ref).sum(0)).abs().max() < 1e-4 * (Z.double().norm() * ref.norm()) / c ** 0.5
                 res[kern] = Y
             assert rel_err(res["wp"], res["wi"]) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_sddmm_all_column_widths_against_torch(problem, dtype):
+    """mgp_lap_sddmm (backward of the SpMM w.r.t. the matrix entries; both its scalar and its 128-bit instantiations) against the
+    definition evaluated with torch ops: g_a[p] = -post_i pre_j <gy_i, x_j>, g_diag[i] = post_i pre_i <gy_i, x_i>."""
+    import manifold_gp_b200 as mgp
+    from manifold_gp_b200 import graph
+    x, idx, val = problem
+    n = x.shape[0]
+    lap = mgp.GraphLaplacianOperator(val.to(dtype), idx, n, torch.tensor([[0.15]], dtype=dtype, device=DEV), "symmetric")
+    st = lap.structure
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    rows = torch.repeat_interleave(torch.arange(n, device=DEV), (st.rowptr[1:] - st.rowptr[:-1]).long())
+    cols = st.col.long()
+    pre = torch.rand(n, dtype=dtype, device=DEV, generator=gen) + 0.5
+    post = torch.rand(n, dtype=dtype, device=DEV, generator=gen) + 0.5
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    for c in (1, 2, 3, 4, 8, 11, 12, 16, 24, 32):
+        X = torch.randn(n, c, dtype=dtype, device=DEV, generator=gen)
+        G = torch.randn(n, c, dtype=dtype, device=DEV, generator=gen)
+        for use in (False, True):
+            g_a, g_d = graph.lap_sddmm(st, G, X, pre=pre if use else None, post=post if use else None)
+            pi = post.double() if use else torch.ones(n, dtype=torch.float64, device=DEV)
+            pj = pre.double() if use else torch.ones(n, dtype=torch.float64, device=DEV)
+            ref_a = -(pi[rows] * pj[cols]) * (G.double()[rows] * X.double()[cols]).sum(1)
+            ref_d = pi * pj * (G.double() * X.double()).sum(1)
+            assert rel_err(g_a, ref_a) < tol, (c, use)
+            assert rel_err(g_d, ref_d) < tol, (c, use)
