@@ -6,6 +6,8 @@ once per graph and cached on the ``idx`` tensor.  Per-bandwidth values are produ
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -678,10 +680,8 @@ LAST_SPMM_KERNEL = None  # name of the kernel the most recent lap_spmm call laun
 SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "wp" | "spmv"  (tests force each; "auto": wp (fp32, whole 64-byte rows), else wi, else pipe, else tiled, else csr; one column: spmv)
 
 
-PAIR_WALK = True       # "auto" may take the paired-row walk of the warp-interleaved kernel (MGP_PAIR_WALK=0 turns it off)
-import os as _os
-if _os.environ.get("MGP_PAIR_WALK", "1") == "0":
-    PAIR_WALK = False
+# "auto" may take the paired-row walk of the warp-interleaved kernel (MGP_PAIR_WALK=0 turns it off)
+PAIR_WALK = os.environ.get("MGP_PAIR_WALK", "1") != "0"
 
 
 def _note_kernel(name):
