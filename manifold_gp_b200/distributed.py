@@ -1116,6 +1116,51 @@ def partitioned_symmetrize(rows: torch.Tensor, cols: torch.Tensor, vals: torch.T
     return row, col, val
 
 
+def _all_gather_blocks(block: torch.Tensor, part: RowPartition, group=None) -> torch.Tensor:
+    """Concatenation of every rank's row block (blocks of a RowPartition differ in length: the last one is shorter).  Padded to a
+    common length so that any backend's equal-size all_gather serves (gloo has no uneven form)."""
+    world = part.world
+    if world == 1:
+        return block
+    sizes = [part.range(r)[1] - part.range(r)[0] for r in range(world)]
+    mx = max(sizes)
+    padded = torch.zeros((mx,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
+    padded[:block.shape[0]] = block
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:sz] for p, sz in zip(parts, sizes)])
+
+
+def partitioned_sort_rows(row, col, val, part: RowPartition, rank: int, perm_block: torch.Tensor, tile_rows: int = 128, group=None):
+    """Inside every ``tile_rows``-row tile of this rank's block, order the rows by their number of entries (descending) -- what
+    GraphStructure does for the replicated structure: the 8 row slots of a warp block walk in lock-step, so they want rows of
+    equal length (measured on 2 GPUs at cfg-C: 360 ms without against 343 ms for the replicated build).  The renumbering is local
+    to a rank's block, but the other ranks name these rows as halo columns: one halo gather of the new ids translates them, and
+    the row order of the whole partition is re-assembled with one all-gather.
+    In: the rank's entries (global ``row`` in [lo, hi), global ``col``, ``val``) and ``perm_block`` = original index of each of
+    its rows.  Returns (row, col, val) renumbered and sorted by (row, col), and the refined ``perm`` [n] of ALL rows.
+    Device-agnostic (collectives: the HaloPlan handshake, one exchange, one all-gather)."""
+    lo, hi = part.range(rank)
+    n_loc, dev = hi - lo, row.device
+    world = part.world
+    deg = torch.bincount(row - lo, minlength=n_loc)
+    ar = torch.arange(n_loc, device=dev, dtype=torch.int64)
+    key = ((ar // tile_rows) << 20) | ((1 << 20) - 1 - deg.clamp_max((1 << 20) - 1))
+    order = torch.argsort(key, stable=True)                      # new local position -> old local row
+    newpos = torch.empty_like(order)
+    newpos[order] = ar
+    plan0 = HaloPlan(part, rank, col, group=group)
+    ids = torch.zeros((n_loc + int(plan0.halo_ids.numel()), 1), dtype=torch.int64, device=dev)
+    ids[:n_loc, 0] = lo + newpos
+    plan0.exchange(ids)                                          # new global ids of the halo rows, from their owners
+    col = ids[plan0.to_local(col), 0]
+    row = lo + newpos[row - lo]
+    o = torch.argsort(row * part.n + col, stable=True)
+    block = perm_block[order].contiguous()                       # my block of the refined row order
+    perm = _all_gather_blocks(block, part, group)
+    return row[o], col[o], val[o], perm
+
+
 class PartitionedGraph:
     """The kNN graph of a point cloud, ROW-PARTITIONED AT CONSTRUCTION (one process per GPU): the database is replicated (as in
     ``sharded_knn``: the exhaustive search needs all points), everything after the search is partitioned --
@@ -1168,38 +1213,13 @@ class PartitionedGraph:
             t["hcol_peer"] = ((own << 26) | (gid - starts[own])).to(torch.int32).contiguous()
 
     def _sort_rows_inside_tiles(self, row, col, val, n_loc):
-        """Inside every 128-row tile, order the rows by their number of entries (descending) -- what GraphStructure does for the
-        replicated structure: the 8 row slots of a warp block walk in lock-step, so they want rows of equal length (measured on
-        2 GPUs at cfg-C: 360 ms without against 343 ms for the replicated build).  The renumbering is local to a rank's block, but
-        the other ranks name these rows as halo columns: one halo gather of the new ids translates them, and the row order of
-        the whole partition (``perm``) is re-assembled with one all-gather."""
+        """See ``partitioned_sort_rows``; also refreshes ``perm`` / ``inv`` with the refined row order of the whole partition."""
         from . import graph
-        R = graph.GraphStructure.TILE_ROWS
-        lo, dev = self.lo, row.device
-        deg = torch.bincount(row - lo, minlength=n_loc)
-        ar = torch.arange(n_loc, device=dev, dtype=torch.int64)
-        key = ((ar // R) << 20) | ((1 << 20) - 1 - deg.clamp_max((1 << 20) - 1))
-        order = torch.argsort(key, stable=True)                      # new local position -> old local row
-        newpos = torch.empty_like(order)
-        newpos[order] = ar
-        plan0 = HaloPlan(self.part, self.rank, col, group=self.group)
-        ids = torch.zeros((n_loc + int(plan0.halo_ids.numel()), 1), dtype=torch.int64, device=dev)
-        ids[:n_loc, 0] = lo + newpos
-        plan0.exchange(ids)                                          # new global ids of the halo rows, from their owners
-        col = ids[plan0.to_local(col), 0]
-        row = lo + newpos[row - lo]
-        o = torch.argsort(row * self.part.n + col, stable=True)
-        block = self.perm[lo:self.hi][order].contiguous()            # my block of the refined row order
-        if self.world > 1:
-            sizes = [self.part.range(r)[1] - self.part.range(r)[0] for r in range(self.world)]
-            parts = [torch.empty(sz, dtype=block.dtype, device=dev) for sz in sizes]
-            dist.all_gather(parts, block, group=self.group)
-            self.perm = torch.cat(parts)
-        else:
-            self.perm = block
+        row, col, val, self.perm = partitioned_sort_rows(row, col, val, self.part, self.rank, self.perm[self.lo:self.hi],
+                                                         graph.GraphStructure.TILE_ROWS, self.group)
         self.inv = torch.empty_like(self.perm)
-        self.inv[self.perm] = torch.arange(self.n, device=dev)
-        return row[o], col[o], val[o]
+        self.inv[self.perm] = torch.arange(self.n, device=row.device)
+        return row, col, val
 
     def values(self, eps, self_loops: bool = True, dtype=torch.float32):
         """(deg_unnorm [n_ext], deg [n_ext], diag [n_loc], a [nnz_loc]) for bandwidth ``eps`` -- graph_laplacian_operator.py:52-106
@@ -1230,14 +1250,7 @@ class PartitionedGraph:
 
     def gather(self, v_loc: torch.Tensor) -> torch.Tensor:
         """[n, C] in the caller's point order from every rank's block (one all-gather)."""
-        sizes = [self.part.range(r)[1] - self.part.range(r)[0] for r in range(self.world)]
-        if self.world == 1:
-            full = v_loc
-        else:
-            parts = [torch.empty((s,) + tuple(v_loc.shape[1:]), dtype=v_loc.dtype, device=v_loc.device) for s in sizes]
-            dist.all_gather(parts, v_loc.contiguous(), group=self.group)
-            full = torch.cat(parts)
-        return full.index_select(0, self.inv)
+        return _all_gather_blocks(v_loc.contiguous(), self.part, self.group).index_select(0, self.inv)
 
 
 class PartitionedPrecision(DistPrecision):

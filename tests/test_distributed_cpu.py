@@ -192,6 +192,23 @@ def _worker_symm(rank, world, port, results):
         y = lap.laplacian_diag[lo:hi].unsqueeze(1) * xe[:n_loc]
         y.index_add_(0, lr, -(a.unsqueeze(1) * xe[lc]))
         assert torch.allclose(y, lap.matmul(X)[lo:hi], rtol=1e-10, atol=1e-10)
+        # ---- rows sorted by length inside tiles across the partition (partitioned_sort_rows) ----------------------------
+        from manifold_gp_b200.distributed import partitioned_sort_rows
+        perm0 = torch.arange(n)                                       # the rows' original indices before the refinement
+        row2, col2, val2, perm2 = partitioned_sort_rows(row, col, val, part, rank, perm0[lo:hi], 128)
+        assert torch.equal(torch.sort(perm2).values, torch.arange(n))                  # a permutation of all rows ...
+        assert torch.equal(torch.sort(perm2[lo:hi]).values, torch.arange(lo, hi))      # ... that keeps every rank's block
+        deg2 = torch.bincount(row2 - lo, minlength=n_loc)
+        for t0 in range(0, n_loc, 128):                                                # descending lengths inside every tile
+            d = deg2[t0:t0 + 128]
+            assert bool((d[1:] <= d[:-1]).all())
+        # the renumbered entries are the old ones under perm2: new id g names the row that had id perm2[g] before
+        key_old = torch.sort(row * n + col).values
+        key_new = torch.sort(perm2[row2] * n + perm2[col2]).values
+        assert torch.equal(key_old, key_new)
+        o_old = torch.argsort(row * n + col, stable=True); o_new = torch.argsort(perm2[row2] * n + perm2[col2], stable=True)
+        assert torch.equal(val[o_old], val2[o_new])
+        assert bool(((row2[1:] * n + col2[1:]) >= (row2[:-1] * n + col2[:-1])).all())  # sorted by (row, col)
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
