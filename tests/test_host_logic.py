@@ -300,3 +300,18 @@ def test_pair_matching_is_a_perfect_matching_that_beats_adjacent_rows():
     pos = pair_matching(rowptr, lcol, n, R).view(2, R)
     for k in range(64):
         assert int(pos[0, k]) // 2 == int(pos[0, k + 64]) // 2
+
+
+def test_pair_matching_is_chunk_independent():
+    """The matching is computed per tile; the chunking of tiles (bounded dense pattern memory) must not change it."""
+    from manifold_gp_b200.graph import pair_matching
+    g = torch.Generator().manual_seed(7)
+    R, n = 128, 700
+    rowlen = torch.randint(3, 20, (n,), generator=g)
+    rowptr = torch.zeros(n + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(rowlen, 0)
+    lcol = torch.cat([(r % R) // 3 + torch.randperm(48, generator=g)[:int(rowlen[r])] for r in range(n)]).to(torch.int16)
+    a = pair_matching(rowptr, lcol, n, R, chunk_tiles=2048)
+    b = pair_matching(rowptr, lcol, n, R, chunk_tiles=1)
+    c = pair_matching(rowptr, lcol, n, R, chunk_tiles=4)
+    assert torch.equal(a, b) and torch.equal(a, c)
