@@ -276,7 +276,7 @@ typedef struct mgp_wi_ext {
   int32_t ep_add;
   const void* ep_coef;
   int32_t publish_at_start;
-  int32_t group_rows;         /* with pair_rows: rows per slot of the grouped streams -- 0 or 2 = pairs, 4 = quads (four values per entry) */
+  int32_t reserved;
   const uint8_t* pair_rows;   /* non-NULL (fp32 only): wptr / wcol / aw are the PAIRED-ROW streams of graph.pair_streams -- a slot of 8 lanes
                                  walks the union list of two spatially adjacent rows, aw holds two values per entry (mgp_lap_pair_values),
                                  pair_rows[128 tile + 2 pair + half] is the tile-local row that position outputs */

@@ -120,12 +120,12 @@ class WiExt(ctypes.Structure):
     """``mgp_wi_ext`` of include/mgp_b200.h (optional hooks of mgp_lap_spmm_wi_ex)."""
     _fields_ = [("done_flag", c_void_p), ("wait_flags", c_void_p), ("publish_flags", c_void_p), ("ticket", c_void_p),
                 ("red_ptrs", c_void_p), ("red_flags", c_void_p), ("ship_extra", c_void_p), ("ship_ncols", c_int32),
-                ("ep_add", c_int32), ("ep_coef", c_void_p), ("publish_at_start", c_int32), ("group_rows", c_int32),
+                ("ep_add", c_int32), ("ep_coef", c_void_p), ("publish_at_start", c_int32), ("reserved", c_int32),
                 ("pair_rows", c_void_p)]
 
 
 def wi_ext(done_flag=None, wait_flags=None, publish_flags=None, ticket=None, red_ptrs=None, red_flags=None, ship_extra=None,
-           ship_ncols=0, ep_coef=None, ep_add=False, publish_at_start=False, pair_rows=None, group_rows=0):
+           ship_ncols=0, ep_coef=None, ep_add=False, publish_at_start=False, pair_rows=None):
     def dp(t):
         if t is None:
             return None
@@ -133,7 +133,7 @@ def wi_ext(done_flag=None, wait_flags=None, publish_flags=None, ticket=None, red
             raise RuntimeError("manifold_gp_b200: expected a CUDA tensor (no CPU fallback exists)")
         return t.data_ptr()
     return WiExt(dp(done_flag), dp(wait_flags), dp(publish_flags), dp(ticket), dp(red_ptrs), dp(red_flags), dp(ship_extra),
-                 int(ship_ncols), 1 if ep_add else 0, dp(ep_coef), 1 if publish_at_start else 0, int(group_rows), dp(pair_rows))
+                 int(ship_ncols), 1 if ep_add else 0, dp(ep_coef), 1 if publish_at_start else 0, 0, dp(pair_rows))
 
 
 for _name, (_res, _args) in _SIG.items():

@@ -155,27 +155,21 @@ __device__ __forceinline__ void lds_v2b64(uint32_t addr, uint64_t& lo, uint64_t&
 // Lanes 0-3 of a slot end up with row A, lanes 4-7 with row B: one exchange across lane ^ 4 (16 shuffles), then the same
 // 12-shuffle rotation as the single-row walk.  Morton-adjacent rows share a third of their columns: 0.73 stream slots and
 // 0.43 shared-memory wavefronts per nonzero against 1.05 and 0.59.
-//
-// GROUP = 4 (fp32, "v7"): a slot is 16 lanes walking the union list of a row QUAD (graph.group_streams with group = 4): 64 FMAs per
-// X-row load, four values per entry (own row, own ^ 1, own ^ 2, own ^ 3 in units of the slot's row groups), three exchanges across
-// lane ^ 4, ^ 8, ^ 12 before the rotation.  Matched quads: 0.372 union entries per nonzero against 0.594 for pairs.
-template <typename T, int PW, int GROUP>
+template <typename T, int PW, bool PAIR>
 __global__ void __launch_bounds__((kWiConsumerWarps + PW) * 32, 1)
 lap_spmm_wi_kernel(const WiArgs<T> g) {
-  constexpr bool PAIR = GROUP == 2, QUAD = GROUP == 4, TABLE = GROUP > 1;
-  static_assert(GROUP == 1 || GROUP == 2 || GROUP == 4, "row groups of 1, 2 or 4");
-  static_assert(!TABLE || sizeof(T) == 4, "the grouped walks are fp32 kernels");
+  static_assert(!PAIR || sizeof(T) == 4, "the paired walk is an fp32 kernel");
   constexpr int kWiProducerWarps = PW, kWiProducerThreads = PW * 32, kWiThreads = (kWiConsumerWarps + PW) * 32;
   constexpr int R = kWiRows;
   constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte chunk
   constexpr int CW = 4 * VEC;                  // columns per pass: 64-byte rows
   constexpr uint32_t ROW_BYTES = 64;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr uint32_t VB = (uint32_t)GROUP * (uint32_t)sizeof(T);       // bytes of value(s) per stream entry
+  constexpr uint32_t VB = (PAIR ? 2u : 1u) * (uint32_t)sizeof(T);      // bytes of value(s) per stream entry
   // tail of a tile's region: the tile's slice of the diagonal [R] and (PAIR) its row table [R bytes] -- bulk-copied with the
   // streams so the consumers' epilogue has no global load on its critical path (ncu, round 2: 14 % of the paired walk's
   // consumer stall samples were the row-table load and the diagonal load behind it)
-  constexpr uint32_t kTailBytes = (uint32_t)R * (uint32_t)sizeof(T) + (TABLE ? (uint32_t)R : 0u);
+  constexpr uint32_t kTailBytes = (uint32_t)R * (uint32_t)sizeof(T) + (PAIR ? (uint32_t)R : 0u);
   __shared__ __align__(8) uint64_t full_bar[kWiSlots];
   __shared__ __align__(8) uint64_t empty_bar[kWiSlots];
   __shared__ __align__(8) uint64_t meta_bar[2];
@@ -230,13 +224,8 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
   // unrolled step re-materialised the stage base and shuffled accumulator pairs with 8 IMAD.MOV per 2 steps).  setmaxnreg is
   // warpgroup-granular; producers = warpgroups 0..3, consumers = warpgroups 4..7; 16 x 32 x (40 + 88) = 65536 registers.
   if constexpr (PW == 16 && sizeof(T) == 4) {
-    if constexpr (QUAD) {      // 64 accumulators per lane: 16 x 32 x (24 + 104) = 65536
-      if (warp < kWiProducerWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-      else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    } else {
-      if (warp < kWiProducerWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-      else asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-    }
+    if (warp < kWiProducerWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
   }
   if (warp < kWiProducerWarps) {
     // =================================================== producers ==================================================
@@ -358,7 +347,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         asm volatile("barrier.arrive %0, %1;" ::"r"(1 + s), "n"((PW - 1) * 32) : "memory");
         if (lane == 0) {
           const uint32_t dbytes = ((uint32_t)nrows * (uint32_t)sizeof(T)) & ~15u;
-          const uint32_t bytes = (uint32_t)cnt * (2u + VB) + (own_contig ? (uint32_t)nrows * ROW_BYTES : 0u) + dbytes + (TABLE ? (uint32_t)R : 0u);
+          const uint32_t bytes = (uint32_t)cnt * (2u + VB) + (own_contig ? (uint32_t)nrows * ROW_BYTES : 0u) + dbytes + (PAIR ? (uint32_t)R : 0u);
           mbar_arrive_expect_tx(&full_bar[s], bytes);
           if (cnt > 0) {
             bulk_g2s(vs, reinterpret_cast<const unsigned char*>(g.aw) + (size_t)base * VB, (uint32_t)cnt * VB, &full_bar[s]);
@@ -366,7 +355,7 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
           }
           if (own_contig) bulk_g2s(xs, g.x + row0 * g.ldx + g.c0, (uint32_t)nrows * ROW_BYTES, &full_bar[s]);
           if (dbytes) bulk_g2s(dgs, g.diag + row0, dbytes, &full_bar[s]);
-          if constexpr (TABLE) bulk_g2s(dgs + (size_t)R * sizeof(T), g.qrow + row0, (uint32_t)R, &full_bar[s]);
+          if constexpr (PAIR) bulk_g2s(dgs + (size_t)R * sizeof(T), g.qrow + row0, (uint32_t)R, &full_bar[s]);
         }
         __syncwarp();
       }
@@ -468,14 +457,14 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
         if (g.ymap && active) yrow = (int64_t)__ldg(g.ymap + row);
         po = (g.post && active) ? __ldg(g.post + row) : T(1);
       };
-      if constexpr (!TABLE) issue_epilogue_loads();
+      if constexpr (!PAIR) issue_epilogue_loads();
       mbar_wait(&full_bar[s], ph);                   // (sleep quanta of 32 / 96 / 320 ns between polls: no measurable difference)
       const int ofs = rp[w];
       const int steps = (g.debug & 1) ? 0 : (rp[w + 1] - ofs) >> 5;
       unsigned char* const xs = smem_raw + (uint32_t)rp[17];
       const unsigned short* cp = reinterpret_cast<const unsigned short*>(xs + (uint32_t)rp[19]) + ofs + lane;
       const unsigned char* const tailp = xs + (uint32_t)rp[19] + (uint32_t)(rp[16] + 32) * 2u;   // diagonal slice | row table
-      if constexpr (TABLE) {
+      if constexpr (PAIR) {
         r = (int)tailp[R * sizeof(T) + r];
         issue_epilogue_loads();
       }
@@ -528,56 +517,6 @@ lap_spmm_wi_kernel(const WiArgs<T> g) {
           acc[c][1] = m1 + __shfl_xor_sync(0xffffffffu, q1, 4);
           acc[c][2] = m2 + __shfl_xor_sync(0xffffffffu, q2, 4);
           acc[c][3] = m3 + __shfl_xor_sync(0xffffffffu, q3, 4);
-        }
-      } else if constexpr (QUAD) {
-        const float4* vp = reinterpret_cast<const float4*>(xs + (uint32_t)rp[18]) + ofs + lane;
-        float4 wv = vp[0];
-        uint64_t aq[4][4][2];                        // [row of the quad relative to this lane's own: own ^ d][chunk][pair of columns]
-#pragma unroll
-        for (int d = 0; d < 4; ++d)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) { aq[d][c][0] = 0ull; aq[d][c][1] = 0ull; }
-        const uint32_t xb = smem_u32(xs);
-        const uint32_t b0 = xb + o0, b1 = xb + o1, b2 = xb + o2, b3 = xb + o3;
-#pragma unroll 1
-        for (int t = 0; t < steps; ++t) {
-          const uint32_t jn = cp[32];                // next step in flight (the last one reads the slack past the block: unused)
-          const float4 wn = vp[32];
-          cp += 32;
-          vp += 32;
-          const uint32_t off = j << 6;               // j * ROW_BYTES
-          uint64_t xr[8];
-          lds_v2b64(b0 + off, xr[0], xr[1]);
-          lds_v2b64(b1 + off, xr[2], xr[3]);
-          lds_v2b64(b2 + off, xr[4], xr[5]);
-          lds_v2b64(b3 + off, xr[6], xr[7]);
-          const uint64_t w0 = pack_f32x2(wv.x, wv.x), w1 = pack_f32x2(wv.y, wv.y);
-          const uint64_t w2 = pack_f32x2(wv.z, wv.z), w3 = pack_f32x2(wv.w, wv.w);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            ffma2_acc(aq[0][c][0], w0, xr[2 * c]); ffma2_acc(aq[0][c][1], w0, xr[2 * c + 1]);
-            ffma2_acc(aq[1][c][0], w1, xr[2 * c]); ffma2_acc(aq[1][c][1], w1, xr[2 * c + 1]);
-            ffma2_acc(aq[2][c][0], w2, xr[2 * c]); ffma2_acc(aq[2][c][1], w2, xr[2 * c + 1]);
-            ffma2_acc(aq[3][c][0], w3, xr[2 * c]); ffma2_acc(aq[3][c][1], w3, xr[2 * c + 1]);
-          }
-          j = jn;
-          wv = wn;
-        }
-        // lane L of row group g = (L >> 2) & 3 holds in aq[d] the partial sums of row group g ^ d; the lane that outputs that row
-        // with the same chunk rotation is L ^ 4d, and ITS aq[d] is my row
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float m[4];
-          unpack_f32x2(aq[0][c][0], m[0], m[1]); unpack_f32x2(aq[0][c][1], m[2], m[3]);
-#pragma unroll
-          for (int d = 1; d < 4; ++d) {
-            float q[4];
-            unpack_f32x2(aq[d][c][0], q[0], q[1]); unpack_f32x2(aq[d][c][1], q[2], q[3]);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) m[v] += __shfl_xor_sync(0xffffffffu, q[v], 4 * d);
-          }
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[c][v] = m[v];
         }
       } else if constexpr (sizeof(T) == 4) {
         const T* vp = reinterpret_cast<const T*>(xs + (uint32_t)rp[18]) + ofs + lane;
@@ -823,9 +762,8 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
     if (sizeof(T) != 4) return MGP_EUNSUPPORTED;
     g.qrow = reinterpret_cast<const unsigned char*>(ext->pair_rows);
   }
-  const bool pair = g.qrow != nullptr;                   // grouped rows: pairs or quads
-  const int group = !pair ? 1 : (ext->group_rows == 4 ? 4 : 2);
-  const size_t entry_bytes = 2 + (size_t)group * sizeof(T);
+  const bool pair = g.qrow != nullptr;
+  const size_t entry_bytes = 2 + (pair ? 2 : 1) * sizeof(T);
   const size_t aux = wi_aux_bytes(g.hmax);
   // the ring takes all the shared memory there is: a tile occupies what it needs, so more bytes = more tiles in flight
   const size_t worst = ((size_t)(R + g.hmax) * 64 + (size_t)(wnzmax + 32) * entry_bytes + R * sizeof(T) + (pair ? R : 0) + 127) & ~(size_t)127;
@@ -849,19 +787,18 @@ static int lap_spmm_wi(const int* wptr, const unsigned short* wcol, const T* aw,
     if (v == 16) return sizeof(T) == 4 ? 16 : 12;      // fp64 at 1024 threads would spill (64 registers)
     return (v == 4 || v == 8 || v == 12) ? v : 8;
   }();
-  auto kern = pw == 16 ? lap_spmm_wi_kernel<T, 16, 1> : pw == 12 ? lap_spmm_wi_kernel<T, 12, 1> : pw == 8 ? lap_spmm_wi_kernel<T, 8, 1> : lap_spmm_wi_kernel<T, 4, 1>;
+  auto kern = pw == 16 ? lap_spmm_wi_kernel<T, 16, false> : pw == 12 ? lap_spmm_wi_kernel<T, 12, false> : pw == 8 ? lap_spmm_wi_kernel<T, 8, false> : lap_spmm_wi_kernel<T, 4, false>;
   int kWiThreads = (kWiConsumerWarps + pw) * 32;
   if constexpr (sizeof(T) == 4) {
     if (pair) {
-      kern = group == 4 ? lap_spmm_wi_kernel<T, 16, 4> : lap_spmm_wi_kernel<T, 16, 2>;
+      kern = lap_spmm_wi_kernel<T, 16, true>;
       kWiThreads = (kWiConsumerWarps + 16) * 32;
     }
   }
-  static size_t configured[3] = {0, 0, 0};   // per instantiation (pw is fixed per process)
-  const int ci = !pair ? 0 : (group == 4 ? 2 : 1);
-  if (smem > configured[ci]) {
+  static size_t configured[2] = {0, 0};   // per instantiation (pw is fixed per process)
+  if (smem > configured[pair ? 1 : 0]) {
     MGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[ci] = smem;
+    configured[pair ? 1 : 0] = smem;
   }
   int64_t blocks = kNumSMs;
   if (blocks > g.ntiles) blocks = g.ntiles;

@@ -194,26 +194,6 @@ def wi_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 128)
     return dict(wptr=wpad, wcol=wcol, nnzw=nnzw, wnzmax=int(tile_tot.max()))
 
 
-def _greedy_match(W: torch.Tensor) -> torch.Tensor:
-    """Greedy maximum-weight perfect matching of the m items of every batch entry of ``W`` [T, m, m] (symmetric, distinct
-    off-diagonal weights, m even), in its locally-dominant-edge form: every round each free item points at its heaviest free
-    partner and mutual choices are matched; the heaviest remaining edge is always mutual, so m / 2 rounds suffice.
-    Returns ``partner`` [T, m].  Overwrites the diagonal of ``W``."""
-    T, m = W.shape[0], W.shape[1]
-    ar = torch.arange(m, device=W.device, dtype=torch.int64)
-    W.diagonal(dim1=1, dim2=2).fill_(-1)
-    alive = torch.ones(T, m, dtype=torch.bool, device=W.device)
-    partner = torch.full((T, m), -1, dtype=torch.int64, device=W.device)
-    for _ in range(m // 2):
-        best = W.masked_fill(~alive[:, None, :], -1).argmax(2)
-        mutual = alive & alive.gather(1, best) & (best.gather(1, best) == ar)
-        partner = torch.where(mutual, best, partner)
-        alive &= ~mutual
-        if not bool(alive.any()):
-            break
-    return partner
-
-
 def pair_matching(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 128, chunk_tiles: int = 2048):
     """Which rows of a tile share a slot of the paired-row walk: a greedy maximum-weight matching of every tile's rows, weight =
     number of columns two rows have in common (the X-row loads the pair saves).  Per tile the 128 x 128 weight matrix is one
@@ -245,7 +225,16 @@ def pair_matching(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 1
         pat[rows[e0:e1] // R - c0, rows[e0:e1] % R, lc[e0:e1]] = 1
         W = torch.bmm(pat, pat.transpose(1, 2)).to(torch.float32).to(torch.int64) * (R * R) + tb     # [T, R, R], symmetric
         del pat
-        partner = _greedy_match(W)
+        W.diagonal(dim1=1, dim2=2).fill_(-1)
+        alive = torch.ones(T, R, dtype=torch.bool, device=dev)
+        partner = torch.full((T, R), -1, dtype=torch.int64, device=dev)
+        for _ in range(R // 2):
+            best = W.masked_fill(~alive[:, None, :], -1).argmax(2)
+            mutual = alive & alive.gather(1, best) & (best.gather(1, best) == ar)
+            partner = torch.where(mutual, best, partner)
+            alive &= ~mutual
+            if not bool(alive.any()):
+                break
         del W
         # pair order: by the smaller row of the pair; the smaller row takes the even position
         lo = torch.minimum(ar.expand(T, R), partner)
@@ -384,170 +373,6 @@ def pair_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, spatial_pos
     qpad[:nblk + 1] = qptr.to(torch.int32)
     return dict(qptr=qpad, qcol=qcol, qsrc=qsrc.reshape(-1).contiguous(), qrow=qrow, nnzq=nnzq, qnzmax=int(tile_tot.max()),
                 q_unions=nu)
-
-
-def quad_matching(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, R: int = 128, chunk_tiles: int = 1024):
-    """Row QUADS of every tile for the quad-row walk: the greedy matching of ``pair_matching`` applied twice -- rows into pairs by
-    shared columns, then pairs into quads by the shared columns of their union lists (0.372 union entries per nonzero on the
-    cfg-C torus against 0.594 for pairs).  Returns ``pos`` [ntiles * R]: rows at positions 4q .. 4q + 3 of a tile form a quad."""
-    dev = rowptr.device
-    ntiles = (n + R - 1) // R
-    rp = rowptr.to(torch.int64)
-    rowlen = rp[1:] - rp[:-1]
-    rows = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), rowlen)
-    lc = lcol16.to(torch.int64) & 0xFFFF
-    L = int(lc.max()) + 1 if lc.numel() else R
-    tile_ptr = rp[torch.arange(0, ntiles + 1, device=dev, dtype=torch.int64).mul(R).clamp_max(n)]
-    wdt = torch.float16 if dev.type == "cuda" else torch.float32
-    H = R // 2
-
-    def tiebreak(m):
-        a = torch.arange(m, device=dev, dtype=torch.int64)
-        return a, torch.minimum(a[:, None], a[None, :]) * m + torch.maximum(a[:, None], a[None, :])
-
-    ar, tb = tiebreak(R)
-    ah, tbh = tiebreak(H)
-    pos = torch.empty(ntiles * R, dtype=torch.int64, device=dev)
-    chunk_tiles = max(1, min(int(chunk_tiles), (1 << 29) // (R * L * (2 if wdt == torch.float16 else 4))))
-    for c0 in range(0, ntiles, chunk_tiles):
-        c1 = min(ntiles, c0 + chunk_tiles)
-        T = c1 - c0
-        e0, e1 = int(tile_ptr[c0]), int(tile_ptr[c1])
-        pat = torch.zeros(T, R, L, dtype=wdt, device=dev)
-        pat[rows[e0:e1] // R - c0, rows[e0:e1] % R, lc[e0:e1]] = 1
-        W = torch.bmm(pat, pat.transpose(1, 2)).to(torch.float32).to(torch.int64) * (R * R) + tb
-        partner = _greedy_match(W)
-        del W
-        lo = torch.minimum(ar.expand(T, R), partner)
-        order1 = torch.argsort(lo * (2 * R) + ar, dim=1, stable=True)                # position in pair order -> row
-        # union patterns of the pairs, then the same matching one level up
-        pu = pat.gather(1, order1.unsqueeze(-1).expand(T, R, L)).view(T, H, 2, L).amax(2)
-        del pat
-        W2 = torch.bmm(pu, pu.transpose(1, 2)).to(torch.float32).to(torch.int64) * (H * H) + tbh
-        del pu
-        partner2 = _greedy_match(W2)
-        del W2
-        lo2 = torch.minimum(ah.expand(T, H), partner2)
-        order2 = torch.argsort(lo2 * (2 * H) + ah, dim=1, stable=True)               # position in quad order (in pairs) -> pair
-        # row at final position 2 * k + h is the h-th row of pair order2[k]
-        final_rows = order1.view(T, H, 2).gather(1, order2.unsqueeze(-1).expand(T, H, 2)).reshape(T, R)
-        pr = torch.empty(T, R, dtype=torch.int64, device=dev)
-        pr.scatter_(1, final_rows, ar.expand(T, R).contiguous())
-        pos[c0 * R:c1 * R] = pr.reshape(-1)
-    return pos
-
-
-def group_streams(rowptr: torch.Tensor, lcol16: torch.Tensor, n: int, pos: torch.Tensor, R: int = 128, group: int = 4):
-    """Grouped-row entry streams of the SpMM walk for row groups of ``group`` = 2 or 4 (csrc/lap_spmm_wi.cu, GROUP template
-    argument); ``group = 2`` reproduces ``pair_streams`` bit for bit (tests/test_host_logic.py), ``group = 4`` is the quad-row
-    layout: a slot of 16 lanes walks the union list of four rows (the rows at positions 4q .. 4q + 3 of ``pos``, e.g. from
-    ``quad_matching``), two slots per warp block of 8 rows.  Lane l of a slot belongs to row group rg = l >> 2 (the row it
-    outputs); stream position qptr[b] + 32 t + 16 slot + l holds the union entry that lane consumes in step t: its tile-local
-    column in ``qcol`` and ``group`` value sources in ``qsrc[group * pos + d]`` = CSR position of the value of row rg ^ d (own row
-    first), -1 = zero.  Lanes of even row groups are filled with even columns, lanes of odd row groups with odd ones (a
-    quarter-warp is two row groups: conflict-free 128-bit loads), the surplus of one parity spills into the other side's free
-    positions; padding entries carry a valid own-row index of the parity their lane expects.  ``qrow[128 tile + group * gi + m]``
-    is the tile-local row of member m of the tile's gi-th group (groups ordered by union length, descending)."""
-    assert R == 128 and group in (2, 4)
-    G = group
-    LS = 4 * G                     # lanes per slot
-    SPW = 32 // LS                 # slots per warp
-    GPT = R // G                   # groups per tile
-    half = LS // 2                 # lanes of one column parity per slot and step
-    dev = rowptr.device
-    ntiles = (n + R - 1) // R
-    nblk = ntiles * 16
-    NT = ntiles * R
-    rp = rowptr.to(torch.int64)
-    nnz = int(rp[-1])
-    rowlen = rp[1:] - rp[:-1]
-    ar = lambda m: torch.arange(m, device=dev, dtype=torch.int64)
-    q0 = pos.to(torch.int64) % R if pos is not None else ar(NT) % R
-    assert q0.numel() == NT
-    g_row = (ar(NT) // R) * GPT + q0 // G                            # global group id of every row (before the length sort)
-    m_row = q0 % G
-    rows = torch.repeat_interleave(ar(n), rowlen)
-    lc = lcol16.to(torch.int64) & 0xFFFF
-    k1 = rows * 65536 + lc
-    o1 = torch.argsort(k1, stable=True)
-    k1s = k1[o1]
-    first = torch.ones(nnz, dtype=torch.bool, device=dev)
-    first[1:] = k1s[1:] != k1s[:-1]
-    start = torch.cummax(torch.where(first, ar(nnz), torch.zeros((), dtype=torch.int64, device=dev)), 0).values
-    occ = torch.empty(nnz, dtype=torch.int64, device=dev)
-    occ[o1] = ar(nnz) - start
-    assert nnz == 0 or int(occ.max()) < 8
-    del k1, k1s, first, start
-    k2 = ((g_row[rows] * 65536 + lc) * 8 + occ) * G + m_row[rows]
-    o2 = torch.argsort(k2)
-    k2s = k2[o2]
-    ukey_s = k2s // G
-    newg = torch.ones(nnz, dtype=torch.bool, device=dev)
-    newg[1:] = ukey_s[1:] != ukey_s[:-1]
-    uid = torch.cumsum(newg.to(torch.int64), 0) - 1
-    nu = int(uid[-1]) + 1 if nnz else 0
-    src = torch.full((nu, G), -1, dtype=torch.int64, device=dev)
-    src[uid, k2s % G] = o2
-    u_g = torch.empty(nu, dtype=torch.int64, device=dev)
-    u_lc = torch.empty(nu, dtype=torch.int64, device=dev)
-    u_g[uid] = ukey_s >> 19
-    u_lc[uid] = (ukey_s >> 3) & 0xFFFF
-    del k2, k2s, ukey_s, newg, uid, o1, o2, occ
-    ngroups = ntiles * GPT
-    ucount = torch.bincount(u_g, minlength=ngroups)
-    gk = (ar(ngroups) // GPT) * (1 << 20) + ((1 << 20) - 1 - ucount)
-    gorder = torch.argsort(gk, stable=True)
-    gi_of = torch.empty(ngroups, dtype=torch.int64, device=dev)
-    gi_of[gorder] = ar(ngroups) % GPT
-    tile_of_group = ar(ngroups) // GPT
-    blk_of_group = tile_of_group * 16 + gi_of // SPW
-    steps = torch.zeros(nblk, dtype=torch.int64, device=dev)
-    steps.scatter_reduce_(0, blk_of_group, (ucount + LS - 1) // LS, reduce="amax")
-    qptr = torch.zeros(nblk + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(steps * 32, 0, out=qptr[1:])
-    nnzq = int(qptr[-1])
-    if nnzq >= 2 ** 30 - 64:
-        return None
-    qrow = torch.zeros(NT, dtype=torch.uint8, device=dev)
-    qrow[(ar(NT) // R) * R + G * gi_of[g_row] + m_row] = (ar(NT) % R).to(torch.uint8)
-    par = u_lc & 1
-    k3 = u_g * 2 + par
-    o3 = torch.argsort(k3, stable=True)
-    cnt3 = torch.bincount(k3, minlength=2 * ngroups)
-    st3 = torch.cumsum(cnt3, 0) - cnt3
-    rk = torch.empty(nu, dtype=torch.int64, device=dev)
-    rk[o3] = ar(nu) - st3[k3[o3]]
-    cap = half * steps[blk_of_group[u_g]]
-    spill = rk >= cap
-    cls = torch.where(spill, 1 - par, par)
-    r = torch.where(spill, cnt3[u_g * 2 + (1 - par)] + (rk - cap), rk)
-    wi_ = r % half
-    rg = 2 * (wi_ // 4) + cls                                        # row group of the lane that consumes the entry
-    lane_in_slot = rg * 4 + (wi_ % 4)
-    p_ = qptr[blk_of_group[u_g]] + (r // half) * 32 + (gi_of[u_g] % SPW) * LS + lane_in_slot
-    # padding index per position
-    pp = ar(nnzq)
-    blk = torch.repeat_interleave(ar(nblk), steps * 32)
-    lane = (pp - qptr[blk]) & 31
-    tile_p = blk >> 4
-    gi_p = (blk & 15) * SPW + lane // LS
-    ra = qrow[tile_p * R + gi_p * G].to(torch.int64)
-    want = ((lane % LS) >> 2) & 1
-    cand = (ra & ~1) | want
-    nrows_t = torch.clamp(n - tile_p * R, max=R)
-    cand = torch.where(cand < nrows_t, cand, torch.where(ra < nrows_t, ra, torch.zeros_like(ra)))
-    qcol = torch.zeros(nnzq + 64, dtype=torch.int16, device=dev)
-    qcol[:nnzq] = cand.to(torch.int32).to(torch.int16)
-    del pp, blk, lane, tile_p, gi_p, ra, want, cand
-    qcol[p_] = u_lc.to(torch.int32).to(torch.int16)
-    qsrc = torch.full((nnzq + 64, G), -1, dtype=torch.int32, device=dev)
-    for d in range(G):
-        qsrc[p_, d] = src.gather(1, (rg ^ d).unsqueeze(1)).squeeze(1).to(torch.int32)
-    tile_tot = qptr[16::16] - qptr[:-1:16]
-    qpad = torch.full((512 * ((ntiles + 31) // 32) + 4,), nnzq, dtype=torch.int32, device=dev)
-    qpad[:nblk + 1] = qptr.to(torch.int32)
-    return dict(qptr=qpad, qcol=qcol, qsrc=qsrc.reshape(-1).contiguous(), qrow=qrow, nnzq=nnzq, qnzmax=int(tile_tot.max()),
-                q_unions=nu, group=G)
 
 
 def wi_halo_lists(halo_ptr: torch.Tensor, halo_col: torch.Tensor, ntiles: int):
@@ -722,10 +547,9 @@ class GraphStructure:
             out = torch.empty(t["nnzp"] + 8, dtype=a.dtype, device=a.device)
             out[t["nnzp"]:].zero_()
             _lib.call("mgp_lap_pad_values_" + sfx, ptr(self.rowptr), ptr(t["prowptr"]), ptr(a), c_int64(self.n), ptr(out), stream())
-        elif kind in ("pair", "quad"):
-            srcs = t["qsrc"] if kind == "pair" else t["gsrc"]
-            out = torch.empty(srcs.numel(), dtype=a.dtype, device=a.device)
-            _lib.call("mgp_lap_pair_values_" + sfx, ptr(srcs), ptr(a), c_int64(out.numel()), ptr(out), stream())
+        elif kind == "pair":
+            out = torch.empty(t["qsrc"].numel(), dtype=a.dtype, device=a.device)
+            _lib.call("mgp_lap_pair_values_" + sfx, ptr(t["qsrc"]), ptr(a), c_int64(out.numel()), ptr(out), stream())
         else:
             out = torch.empty(t["nnzw"] + 64, dtype=a.dtype, device=a.device)
             out[t["nnzw"]:].zero_()
@@ -760,26 +584,6 @@ class GraphStructure:
             if q is not None:
                 t.update(q)
         return t if "qptr" in t else None
-
-    def quad_tiles(self):
-        """The quad-row streams (``quad_matching`` + ``group_streams``) of this structure, built on first use; keys ``gptr, gcol,
-        gsrc, grow, nnzg, gnzmax`` beside the pair streams."""
-        t = self.build_tiles()
-        if t is None or "wptr" not in t:
-            return None
-        if "gptr" not in t and not self.__dict__.get("_quad_tried"):
-            self._quad_tried = True
-            if (self.TILE_ROWS + t["hmax"]) * 64 + t["wnzmax"] * 6 > 200 * 1024:
-                return None
-            lc = t["lcol"][:self.nnz]
-            q = group_streams(self.rowptr, lc, self.n, quad_matching(self.rowptr, lc, self.n, self.TILE_ROWS), self.TILE_ROWS, group=4)
-            if q is not None:
-                t.update(gptr=q["qptr"], gcol=q["qcol"], gsrc=q["qsrc"], grow=q["qrow"], nnzg=q["nnzq"], gnzmax=q["qnzmax"],
-                         g_unions=q["q_unions"])
-        return t if "gptr" in t else None
-
-    def quad_values(self, a: torch.Tensor) -> torch.Tensor:
-        return self._value_layout(a, "quad")
 
     def pair_values(self, a: torch.Tensor) -> torch.Tensor:
         if self.__dict__.get("_aq_persistent") is not None:
@@ -878,8 +682,6 @@ SPMM_KERNEL = "auto"   # "auto" | "csr" | "tiled" | "pipe" | "wi" | "wp" | "spmv
 
 # "auto" may take the paired-row walk of the warp-interleaved kernel (MGP_PAIR_WALK=0 turns it off)
 PAIR_WALK = os.environ.get("MGP_PAIR_WALK", "1") != "0"
-# "auto" prefers the quad-row walk (MGP_QUAD_WALK=1; off by default: see DESIGN.md section 4 for its status)
-QUAD_WALK = os.environ.get("MGP_QUAD_WALK", "0") == "1"
 
 
 def _note_kernel(name):
@@ -938,8 +740,8 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
     slack_ok = a.untyped_storage().nbytes() >= (a.storage_offset() + st.nnz + 8) * a.element_size()
     # measured on B200 (profiles/): the tile-compacted kernels win from 4 columns up; for 1-3 columns the CSR sub-warp
     # kernel (X served from L1/L2) is faster
-    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "wp", "wq"))
-    if SPMM_KERNEL in ("tiled", "pipe", "wi", "wp", "wq") and not use_tiled:
+    use_tiled = SPMM_KERNEL not in ("csr", "spmv") and slack_ok and st.tiled_ok(dt, c) and (c >= 4 or SPMM_KERNEL in ("tiled", "pipe", "wi", "wp"))
+    if SPMM_KERNEL in ("tiled", "pipe", "wi", "wp") and not use_tiled:
         raise RuntimeError("lap_spmm: tiled kernel requested but the tile structure does not fit in shared memory")
     if use_tiled:
         t = st.tiles
@@ -947,7 +749,7 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
             out = torch.empty((st.n, c), dtype=dt, device=x.device)
         if peer_x is not None and not (pre is None and "wptr" in t):
             raise RuntimeError("lap_spmm: peer-memory halo reads need the warp-interleaved kernel (no pre scaling)")
-        if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi", "wp", "wq") or peer_x is not None):
+        if pre is None and "wptr" in t and (SPMM_KERNEL in ("auto", "wi", "wp") or peer_x is not None):
             # paired-row walk (v6): fp32, whole 64-byte rows of right-hand sides, single GPU
             # (with peer memory: only when the caller's hook block names the row table, i.e. keeps the paired value stream alive)
             ext_pair = peer_ext is not None and bool(peer_ext[2].pair_rows)
@@ -959,17 +761,8 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
             if SPMM_KERNEL == "wp" and not pair:
                 raise RuntimeError("lap_spmm: paired-row kernel requested but this call does not qualify (fp32, multiples of 16 "
                                    "columns, no peer memory)")
-            # quad-row walk (v7): same conditions, single GPU; "wq" forces it, "auto" takes it when QUAD_WALK is on
-            quad = ((SPMM_KERNEL == "wq" or (SPMM_KERNEL == "auto" and QUAD_WALK)) and dt == torch.float32 and c % 16 == 0
-                    and peer_x is None and peer_ext is None and hasattr(st, "quad_tiles") and st.quad_tiles() is not None)
-            if SPMM_KERNEL == "wq" and not quad:
-                raise RuntimeError("lap_spmm: quad-row kernel requested but this call does not qualify")
-            if quad:
-                pair = True                                   # (a grouped walk: the hook block carries the row table)
-            aw = st.quad_values(a) if quad else st.pair_values(a) if pair else st.wi_values(a)
-            sptr, scol, snzmax = (t["gptr"], t["gcol"], t["gnzmax"]) if quad else (t["qptr"], t["qcol"], t["qnzmax"]) if pair else \
-                (t["wptr"], t["wcol"], t["wnzmax"])
-            rowtab, grp = (t["grow"], 4) if quad else (t["qrow"], 2) if pair else (None, 0)
+            aw = st.pair_values(a) if pair else st.wi_values(a)
+            sptr, scol, snzmax = (t["qptr"], t["qcol"], t["qnzmax"]) if pair else (t["wptr"], t["wcol"], t["wnzmax"])
             hcol = t["hcol_peer"] if peer_x is not None else t["hcol"]
             ep_here = _ep is not None and peer_ext is None and not (x_external or y_external)
             if peer_ext is not None or done_flag is not None or ep_here or pair:
@@ -978,12 +771,12 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
                     ext = peer_ext[2]
                 elif ep_here:
                     cf = _ep[0] if _ep[0].dtype == dt else _ep[0].to(dt)
-                    ext = _lib.wi_ext(done_flag=done_flag, ep_coef=cf, ep_add=_ep[1] is not None, pair_rows=rowtab, group_rows=grp)
+                    ext = _lib.wi_ext(done_flag=done_flag, ep_coef=cf, ep_add=_ep[1] is not None, pair_rows=t["qrow"] if pair else None)
                     if _ep[1] is not None:
                         dot_with = _ep[1]
                     _ep[2].append(True)
                 else:
-                    ext = _lib.wi_ext(done_flag=done_flag, pair_rows=rowtab, group_rows=grp)
+                    ext = _lib.wi_ext(done_flag=done_flag, pair_rows=t["qrow"] if pair else None)
                 rc = _lib.call_rc("mgp_lap_spmm_wi_ex_" + sfx, ptr(sptr), ptr(scol), ptr(aw), ptr(diag),
                                   ptr(t["hptr"]), ptr(hcol), c_int32(t["rows"]), c_int32(t["rows"] + t["hmax"]),
                                   c_int32(snzmax), c_int32(t["hmax"]), ptr(shift_t), ptr(post),
@@ -1004,7 +797,7 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
                                   c_int32(0 if peer_sync is None else int(peer_sync[0])), ptr(None if peer_sync is None else peer_sync[1]),
                                   ptr(None if peer_sync is None else peer_sync[2]), stream())
             if rc == 0:
-                _note_kernel("lap_spmm_wi_kernel<quad>" if quad else "lap_spmm_wi_kernel<pair>" if pair else "lap_spmm_wi_kernel")
+                _note_kernel("lap_spmm_wi_kernel<pair>" if pair else "lap_spmm_wi_kernel")
                 return out
             if _ep is not None and _ep[2]:          # not launched: the epilogue algebra falls to the caller's elementwise passes
                 _ep[2].clear()
@@ -1012,7 +805,7 @@ def _lap_spmm(st: GraphStructure, a, diag, x, shift=None, pre=None, post=None, o
                     dot_with = None
             if rc != _lib.MGP_EUNSUPPORTED or peer_x is not None:
                 raise RuntimeError(f"mgp_lap_spmm_wi_{sfx} failed ({rc}): {_lib.last_error()}")
-        if SPMM_KERNEL in ("wi", "wp", "wq"):
+        if SPMM_KERNEL in ("wi", "wp"):
             raise RuntimeError("lap_spmm: warp-interleaved kernel requested but this call does not qualify (pre scaling, "
                                "column count not a multiple of one 64-byte row, alignment or shared memory)")
         if pre is None and "prowptr" in t and SPMM_KERNEL in ("auto", "pipe"):

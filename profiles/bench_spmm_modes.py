@@ -8,7 +8,7 @@ import torch
 import manifold_gp_b200 as mgp
 from manifold_gp_b200 import graph
 from manifold_gp_b200.utils import synthetic
-kerns = sys.argv[1].split(",")   # wi | wp | wq
+kerns = sys.argv[1].split(",")
 modes = [int(m) for m in sys.argv[2].split(",")]
 rings = [int(r) for r in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
 n = 1_000_000

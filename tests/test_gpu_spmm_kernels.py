@@ -82,7 +82,7 @@ def test_tiled_and_csr_kernels_agree_with_dense(problem, dtype):
                 # v5 warp-interleaved kernel (64-byte rows of X, entry streams in lane-consumption order) and the
                 # one-block-per-tile kernel on the same streams
                 # ... and (fp32) the paired-row walk of the same kernel (union lists of spatially adjacent row pairs)
-                for kern64 in ("wi",) + (("wp", "wq") if dtype == torch.float32 else ()):
+                for kern64 in ("wi",) + (("wp",) if dtype == torch.float32 else ()):
                     graph.SPMM_KERNEL = kern64
                     try:
                         dot = torch.zeros(c, dtype=dtype, device=DEV)
@@ -96,7 +96,7 @@ def test_tiled_and_csr_kernels_agree_with_dense(problem, dtype):
                     finally:
                         graph.SPMM_KERNEL = "auto"
                     assert rel_err(Y, ref) < tol, (kern64, c, use_post)
-                    assert graph.LAST_SPMM_KERNEL == {"wp": "lap_spmm_wi_kernel<pair>", "wq": "lap_spmm_wi_kernel<quad>"}.get(kern64, "lap_spmm_wi_kernel")
+                    assert graph.LAST_SPMM_KERNEL == ("lap_spmm_wi_kernel<pair>" if kern64 == "wp" else "lap_spmm_wi_kernel")
                     assert torch.equal(Y, Y2)
                     assert rel_err(dot, (X.double() * ref).sum(0)) < tol * 10, (kern64, c)
                     assert (dot3.double() - (Z.double() * ref).sum(0)).abs().max() < tol * 10 * (Z.double().norm() * ref.norm()) / c ** 0.5
@@ -105,7 +105,7 @@ def test_tiled_and_csr_kernels_agree_with_dense(problem, dtype):
         ref_ext = st.to_external((D @ st.to_internal(Xe).double()) - A @ st.to_internal(Xe).double())
         for kern in ("csr", "tiled") + (("pipe",) if c % (4 if dtype == torch.float32 else 2) == 0 else ()) + \
                 (("wi",) if c % (16 if dtype == torch.float32 else 8) == 0 else ()) + \
-                (("wp", "wq") if dtype == torch.float32 and c % 16 == 0 else ()):
+                (("wp",) if dtype == torch.float32 and c % 16 == 0 else ()):
             graph.SPMM_KERNEL = kern
             try:
                 Y = graph.lap_spmm(st, a, diag, Xe, x_external=True, y_external=True)
@@ -225,7 +225,7 @@ def test_paired_walk_on_ragged_graphs_and_epilogues(problem):
             ref = diag.double().unsqueeze(1) * X.double()
             ref.index_add_(0, rows, -a.double().unsqueeze(1) * X.double()[st.col.long()])
             res = {}
-            for kern in ("wi", "wp", "wq"):
+            for kern in ("wi", "wp"):
                 graph.SPMM_KERNEL = kern
                 try:
                     dot = torch.zeros(c, device=DEV)
@@ -243,7 +243,6 @@ def test_paired_walk_on_ragged_graphs_and_epilogues(problem):
                 assert (dot.double() - (Z.double() * ref).sum(0)).abs().max() < 1e-4 * (Z.double().norm() * ref.norm()) / c ** 0.5
                 res[kern] = Y
             assert rel_err(res["wp"], res["wi"]) < 2e-6
-            assert rel_err(res["wq"], res["wi"]) < 2e-6
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])

@@ -315,71 +315,3 @@ def test_pair_matching_is_chunk_independent():
     b = pair_matching(rowptr, lcol, n, R, chunk_tiles=1)
     c = pair_matching(rowptr, lcol, n, R, chunk_tiles=4)
     assert torch.equal(a, b) and torch.equal(a, c)
-
-
-def _emulate_group_walk(t, a, xs_tiles, n, G, R=128):
-    """Lane walk of the grouped-row kernel (G = 2 pairs, G = 4 quads) on the CPU: lane l of a slot of 4 G lanes belongs to row group
-    rg = l >> 2; the entry's d-th value feeds row group rg ^ d of the slot's group."""
-    qptr, qcol, qsrc, qrow = t["qptr"].long(), t["qcol"].long() & 0xFFFF, t["qsrc"].long().view(-1, G), t["qrow"].long()
-    ntiles = (n + R - 1) // R
-    nnzq = t["nnzq"]
-    LS, SPW = 4 * G, 32 // (4 * G)
-    pos = torch.arange(nnzq)
-    blk = torch.searchsorted(qptr[:16 * ntiles + 1], pos, right=True) - 1
-    lane = (pos - qptr[blk]) & 31
-    tile = blk >> 4
-    a0 = torch.cat([a, torch.zeros(1, dtype=a.dtype)])
-    xr = xs_tiles[tile, qcol[:nnzq]]
-    gi = (blk & 15) * SPW + lane // LS
-    rg = (lane % LS) >> 2
-    y = torch.zeros(ntiles * R, xs_tiles.shape[2], dtype=a.dtype)
-    for d in range(G):
-        row_d = tile * R + qrow[tile * R + gi * G + (rg ^ d)]
-        y.index_add_(0, row_d, a0[qsrc[:nnzq, d]].unsqueeze(1) * xr)
-    return y[:n], dict(lane=lane, blk=blk, col=qcol[:nnzq], real=(qsrc[:nnzq] >= 0).any(1), rg=rg)
-
-
-def test_group_streams_pairs_equal_pair_streams_and_quads_reproduce_the_matvec():
-    from manifold_gp_b200.graph import group_streams, pair_matching, pair_streams, quad_matching
-    g = torch.Generator().manual_seed(11)
-    R = 128
-    for n, maxlen in ((300, 14), (128, 40), (1000, 6), (5, 7), (257, 50), (640, 30)):
-        ntiles = (n + R - 1) // R
-        rowlen = torch.randint(0, maxlen, (n,), generator=g)
-        rowptr = torch.zeros(n + 1, dtype=torch.int32)
-        rowptr[1:] = torch.cumsum(rowlen, 0)
-        nnz = int(rowptr[-1])
-        rows = torch.repeat_interleave(torch.arange(n), rowlen)
-        lcol = torch.cat([(r % R) // 4 + torch.randperm(64, generator=g)[:int(rowlen[r])] for r in range(n)] + [torch.zeros(0, dtype=torch.long)])
-        if nnz > 4:
-            lcol[1] = lcol[0]
-        lcol = lcol.to(torch.int16)
-        a = torch.randn(nnz, generator=g, dtype=torch.float64)
-        xs = torch.randn(ntiles, 256, 4, generator=g, dtype=torch.float64)
-        ref = torch.zeros(n, 4, dtype=torch.float64)
-        ref.index_add_(0, rows, a.unsqueeze(1) * xs[rows // R, lcol.long()])
-        # group = 2 is the pair layout, bit for bit
-        pos2 = pair_matching(rowptr, lcol, n, R)
-        tp, tg = pair_streams(rowptr, lcol, n, pos2, R), group_streams(rowptr, lcol, n, pos2, R, group=2)
-        for key in ("qptr", "qcol", "qsrc", "qrow"):
-            assert torch.equal(tp[key], tg[key]), key
-        assert tp["nnzq"] == tg["nnzq"] and tp["qnzmax"] == tg["qnzmax"] and tp["q_unions"] == tg["q_unions"]
-        # quads
-        pos4 = quad_matching(rowptr, lcol, n, R)
-        assert torch.equal(torch.sort(pos4.view(ntiles, R), 1).values, torch.arange(R).expand(ntiles, R))
-        tq = group_streams(rowptr, lcol, n, pos4, R, group=4)
-        assert tq["qnzmax"] % 32 == 0 and tq["qsrc"].numel() == 4 * (tq["nnzq"] + 64)
-        y, info = _emulate_group_walk(tq, a, xs, n, 4)
-        assert torch.allclose(y, ref, atol=1e-12)
-        used = tq["qsrc"].long(); used = used[used >= 0]
-        assert used.numel() == nnz and torch.equal(torch.sort(used).values, torch.arange(nnz))
-        assert torch.equal(torch.sort(tq["qrow"].long().view(ntiles, R), 1).values, torch.arange(R).expand(ntiles, R))
-        lane, col, real, rg = info["lane"], info["col"], info["real"], info["rg"]
-        nrows_t = torch.clamp(n - (info["blk"] >> 4) * R, max=R)
-        assert bool((col[~real] < nrows_t[~real]).all())                       # padding: valid own rows
-        mism = ((col & 1) != (rg & 1)) & real                                  # even row groups hold even columns, up to the spill
-        assert float(mism.sum()) <= 0.5 * float(real.sum())
-        assert tq["q_unions"] <= tp["q_unions"]                                # a quad's union is no longer than its pairs' unions
-        # the pair emulator agrees on the pair layout too (the generic emulator with G = 2)
-        y2, _ = _emulate_group_walk(tg, a, xs, n, 2)
-        assert torch.allclose(y2, ref, atol=1e-12)
